@@ -1,0 +1,39 @@
+"""pytest configuration: registers the ``gpu`` marker and shared golden-fixture helpers."""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    d["params"] = json.loads(str(d.pop("params_json")))
+    if d["params"].get("percentiles") is not None:
+        d["params"]["percentiles"] = tuple(d["params"]["percentiles"])
+    d["dtypes"] = [t for t in ("f64", "f32") if f"scores_{t}" in d]
+    d["name"] = name
+    return d
+
+
+@pytest.fixture(scope="session")
+def goldens():
+    return {n: load_golden(n) for n in golden_names()}
