@@ -1,0 +1,181 @@
+/*
+ * phet_b200.h -- C ABI of the B200-native PHet fit_predict hot path.
+ *
+ * The reference (kleelab-bch/phet) is pure Python and has no FFI layer; its de-facto operator
+ * interface for this path is the model-class convention `PHet(...).fit_predict(X, y)`
+ * (src/model/phet.py:33-40, 163-518) called from src/train.py:474-477.  The entry points
+ * below are the device boundary a binding for that method needs: each one replaces the span
+ * of phet.py cited beside it.  The Python mirror of the class lives in phet_b200/phet.py and
+ * binds these with ctypes (phet_b200/_capi.py); INTEGRATION.md shows the stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative phet_status; a human-readable
+ * message for the calling thread's last failure is available from phet_last_error().  No C++
+ * exceptions cross the boundary.  Host buffers are caller-allocated and caller-owned.  A
+ * context is bound to one CUDA device and one stream and is not thread-safe.  All kernels are
+ * sm_100a; there is no CPU fallback -- phet_ctx_create fails if no such device is present.
+ */
+#ifndef PHET_B200_H
+#define PHET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHET_B200_ABI_VERSION 1
+
+typedef struct phet_ctx phet_ctx;
+
+typedef enum {
+    PHET_OK = 0,
+    PHET_ERR_INVALID = -1,   /* bad argument / call order                          */
+    PHET_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError name) */
+    PHET_ERR_UNSUPPORTED = -3, /* size outside what the kernels are built for      */
+    PHET_ERR_NOMEM = -4
+} phet_status;
+
+typedef enum { PHET_F32 = 0, PHET_F64 = 1 } phet_dtype;
+typedef enum { PHET_NORM_NONE = 0, PHET_NORM_ZSCORE = 1 } phet_normalize;
+typedef enum { PHET_TEST_T = 0, PHET_TEST_Z = 1 } phet_test;          /* phet.py:425-428 */
+typedef enum { PHET_PERM_HOST = 0, PHET_PERM_DEVICE = 1 } phet_perm_mode;
+
+/* Device buffers a caller may want to wrap (e.g. for an NCCL all-reduce).  phet_device_ptr. */
+typedef enum {
+    PHET_BUF_ACC = 0,      /* double[2][G]: sum_s -2 ln p  then  sum_s delta-IQR  (phet.py:417,432,449-451) */
+    PHET_BUF_O = 1,        /* double[G]: min-over-slices KS p-value (phet.py:496-498)                        */
+    PHET_BUF_H = 2,        /* int32[G][n_slices]: integer KS statistics (debug / parity)                     */
+    PHET_BUF_P = 3,        /* double[G][S_local]: p-values, only when debug capture is on                    */
+    PHET_BUF_DELTA = 4,    /* double[G][S_local]: delta-IQR, only when debug capture is on                   */
+    PHET_BUF_F = 5,        /* double[G]: standardised Fisher statistic (phet.py:458-462)                     */
+    PHET_BUF_R = 6,        /* double[G]: mean delta-IQR (phet.py:435-444)                                    */
+    PHET_BUF_BINS = 7,     /* int8[G]: ordinal bin of o (phet.py:500-504)                                    */
+    PHET_BUF_SCORES = 8,   /* double[G]: final scores (phet.py:510-516)                                      */
+    PHET_BUF_XG = 9,       /* normalised gene-major matrix, storage dtype, [G][n_pad], class-grouped cells   */
+    PHET_BUF_MEAN = 10,    /* double[G] column mean  */
+    PHET_BUF_STD = 11      /* double[G] column population sd */
+} phet_buffer;
+
+/* Order-statistic positions and lerp weights of the two percentiles, computed on the host
+ * with the index arithmetic of scipy.stats.iqr -> stats.quantile(method="linear")
+ * (called at phet.py:413-414): jg = p*m + (1-p); j = floor(jg)-1; g = frac(jg). */
+typedef struct {
+    int32_t j_lo, k_lo;   /* sorted positions y[j], y[j+1] (clipped to [0, m-1]) for the low percentile */
+    int32_t j_hi, k_hi;
+    double g_lo, g_hi;    /* q = (1-g)*y[j] + g*y[k] */
+} phet_quantile_pos;
+
+typedef struct {
+    int32_t test;             /* phet_test: Student pooled t (m < 30) or pooled z (phet.py:425-428)     */
+    double ln_beta;           /* PHET_TEST_T: ln B(df/2, 1/2), df = 2m-2 (host lgamma)                    */
+    double p_flush_below;     /* p-values <= this become 0 (float32 stdtr underflow emulation; 0 = off)  */
+    phet_quantile_pos q;
+    int32_t capture_debug;    /* 1: also write PHET_BUF_P / PHET_BUF_DELTA                               */
+} phet_step1_params;
+
+int phet_abi_version(void);
+const char *phet_last_error(void);
+
+/* Number of CUDA devices visible, or a negative status. */
+int phet_device_count(void);
+
+/* Create a context on `device`.  `stream` is a cudaStream_t owned by the caller (e.g. torch's
+ * current stream) or NULL to let the context create and own one. */
+int phet_ctx_create(int device, void *stream, phet_ctx **out);
+int phet_ctx_destroy(phet_ctx *ctx);
+int phet_ctx_sync(phet_ctx *ctx);
+
+/* Class membership (phet.py:388-392): row numbers of control (y == 0) and case (y == 1) cells,
+ * each ascending.  Must precede phet_load_matrix: the device layout groups cells by class. */
+int phet_set_classes(phet_ctx *ctx, const int32_t *ctrl_rows, int64_t n0,
+                     const int32_t *case_rows, int64_t n1);
+
+/* Replaces phet.py:291,299 (zscore + nan_to_num) and builds the HBM layout.
+ * X: row-major cells x genes, N x G, element type `dtype`, in host memory (is_device = 0,
+ * pageable or pinned) or device memory on the context's device (is_device = 1; not modified).
+ * storage: element type of the normalised gene-major copy kept in HBM and staged to SMEM. */
+int phet_load_matrix(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G,
+                     int dtype, int normalize, int storage);
+
+/* Subsample index sets (phet.py:401-402), host memory, int32[S][2][m]: for each subsample the
+ * control draw then the case draw, ORIGINAL row numbers (duplicates allowed: replace=True). */
+int phet_set_index_sets(phet_ctx *ctx, const int32_t *idx, int64_t S, int64_t m);
+
+/* Replaces the loop phet.py:397-432 for subsamples [s_begin, s_end) over all genes, and
+ * accumulates PHET_BUF_ACC (zeroed first unless accumulate != 0). */
+int phet_step1(phet_ctx *ctx, int64_t s_begin, int64_t s_end, const phet_step1_params *prm,
+               int accumulate);
+
+/* Replaces phet.py:473-498 for genes [g_begin, g_end): per gene, permute each class column,
+ * cut slices of length m over [0, min(n0,n1)), two-sample KS per slice, o = min p.
+ * perm_mode HOST: perm_ctrl / perm_case are host uint32 [G][min_c] class-local positions (the
+ *   first min_c entries of np.random.permutation(n_class), phet.py:486-487) for ALL genes.
+ * perm_mode DEVICE: permutations come from a keyed bijection on the device (seed); the
+ *   pointers are ignored.  Same distribution, not the reference's MT19937 stream.
+ * table_full[0..m] / table_last[0..n_last]: exact two-sided p-value of ks_2samp for equal
+ * sizes as a function of the integer statistic h (host-built, scipy semantics). */
+int phet_step3(phet_ctx *ctx, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode,
+               const uint32_t *perm_ctrl, const uint32_t *perm_case, uint64_t seed,
+               const double *table_full, const double *table_last, int64_t n_last);
+
+/* Replaces phet.py:435-444 and 449-462: r = acc_r / S_total, f = standardised Fisher. */
+int phet_fisher(phet_ctx *ctx, int64_t S_total);
+
+/* min and max of o over all genes (inputs of np.linspace at sklearn _discretization.py:339). */
+int phet_o_minmax(phet_ctx *ctx, double out_minmax[2]);
+
+/* Replaces phet.py:500-504.  edges: host double[B+1] (np.linspace(min o, max o, B+1), or
+ * {-inf, +inf} with B = 1 when o is constant).  counts_out: host int64[B] bin counts. */
+int phet_bin(phet_ctx *ctx, const double *edges, int32_t B, int64_t *counts_out);
+
+/* Replaces phet.py:510-516.  weights: host double[B], already normalised (phet.py:124).
+ * scores_out: host double[G] or NULL (leave on device, PHET_BUF_SCORES). */
+int phet_combine(phet_ctx *ctx, const double *weights, int32_t B, double *scores_out);
+
+/* Raw device pointer / element count of a context buffer (for wrapping, no ownership change). */
+int phet_device_ptr(phet_ctx *ctx, int which, void **ptr_out, int64_t *bytes_out);
+/* Copy a context buffer to host memory (synchronises the stream). */
+int phet_read_buffer(phet_ctx *ctx, int which, void *host_out, int64_t bytes);
+/* Overwrite a context buffer from host memory (e.g. externally reduced accumulators). */
+int phet_write_buffer(phet_ctx *ctx, int which, const void *host_in, int64_t bytes);
+
+/* Introspection for benchmarks: number of kernel launches issued by this context so far,
+ * and the launch geometry chosen for the step-1 kernel (grid, block, dynamic smem bytes,
+ * elements per lane E, staged = gene vector held in shared memory). */
+int64_t phet_launch_count(phet_ctx *ctx);
+int phet_step1_geometry(phet_ctx *ctx, int32_t out[5]);
+
+/* One-call convenience: everything above on one device with host buffers (used by C callers
+ * and by the end-to-end benchmark leg).  perm_mode/seed as in phet_step3; with PHET_PERM_HOST
+ * perm_ctrl/perm_case must be given.  scores_out: host double[G]. */
+typedef struct {
+    int32_t normalize, storage;
+    phet_step1_params step1;
+    int64_t m;
+    int32_t perm_mode;
+    uint64_t seed;
+    int32_t n_bins;
+    const double *weights;      /* double[n_bins] normalised */
+    const double *table_full;   /* double[m+1] */
+    const double *table_last;   /* double[n_last+1] */
+    int64_t n_last;
+} phet_fit_params;
+
+int phet_fit_host(phet_ctx *ctx, const void *X, int dtype, int64_t N, int64_t G,
+                  const int32_t *ctrl_rows, int64_t n0, const int32_t *case_rows, int64_t n1,
+                  const int32_t *idx, int64_t S, const uint32_t *perm_ctrl,
+                  const uint32_t *perm_case, const phet_fit_params *prm,
+                  double *scores_out, int64_t *bin_counts_out);
+
+/* Testing hooks: host evaluations of the exact device routines (same source file) so the
+ * CPU test-suite can check them without a GPU. */
+double phet_host_p_two_sided_t(double t, double df, double ln_beta);
+double phet_host_p_two_sided_z(double z);
+uint32_t phet_host_perm_apply(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t l, uint32_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHET_B200_H */

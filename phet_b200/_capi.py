@@ -1,0 +1,231 @@
+"""ctypes binding of libphet_b200.so (include/phet_b200.h).  No torch types cross this boundary.
+
+The library is built in-tree by ``phet_b200.build`` (nvcc, sm_100a).  There is no CPU fallback:
+if the library cannot be loaded, or no sm_100 device is present, the calls raise ``PhetError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libphet_b200.so")
+
+PHET_F32, PHET_F64 = 0, 1
+NORM_NONE, NORM_ZSCORE = 0, 1
+TEST_T, TEST_Z = 0, 1
+PERM_HOST, PERM_DEVICE = 0, 1
+(BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
+ BUF_STD) = range(12)
+
+EXPORTS = [
+    "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
+    "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
+    "phet_step3", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_device_ptr",
+    "phet_read_buffer", "phet_write_buffer", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
+    "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
+]
+
+
+class PhetError(RuntimeError):
+    pass
+
+
+class QuantilePos(C.Structure):
+    _fields_ = [("j_lo", C.c_int32), ("k_lo", C.c_int32), ("j_hi", C.c_int32), ("k_hi", C.c_int32),
+                ("g_lo", C.c_double), ("g_hi", C.c_double)]
+
+
+class Step1Params(C.Structure):
+    _fields_ = [("test", C.c_int32), ("ln_beta", C.c_double), ("p_flush_below", C.c_double),
+                ("q", QuantilePos), ("capture_debug", C.c_int32)]
+
+
+class FitParams(C.Structure):
+    _fields_ = [("normalize", C.c_int32), ("storage", C.c_int32), ("step1", Step1Params), ("m", C.c_int64),
+                ("perm_mode", C.c_int32), ("seed", C.c_uint64), ("n_bins", C.c_int32),
+                ("weights", C.POINTER(C.c_double)), ("table_full", C.POINTER(C.c_double)),
+                ("table_last", C.POINTER(C.c_double)), ("n_last", C.c_int64)]
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    """Load libphet_b200.so (building it with nvcc first if it is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+        try:
+            if _build.needs_build():
+                _build.build()
+        except Exception as exc:  # no nvcc on the box: use the shipped .so if there is one
+            if not os.path.exists(LIB_PATH):
+                raise PhetError("libphet_b200.so is missing and could not be built: %s" % exc)
+    if not os.path.exists(LIB_PATH):
+        raise PhetError("libphet_b200.so not found at %s (run `python -m phet_b200.build`); "
+                        "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    lib.phet_abi_version.restype = C.c_int
+    lib.phet_last_error.restype = C.c_char_p
+    lib.phet_device_count.restype = C.c_int
+    lib.phet_ctx_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.phet_ctx_destroy.argtypes = [vp]
+    lib.phet_ctx_sync.argtypes = [vp]
+    lib.phet_set_classes.argtypes = [vp, vp, i64, vp, i64]
+    lib.phet_load_matrix.argtypes = [vp, vp, C.c_int, i64, i64, C.c_int, C.c_int, C.c_int]
+    lib.phet_set_index_sets.argtypes = [vp, vp, i64, i64]
+    lib.phet_step1.argtypes = [vp, i64, i64, C.POINTER(Step1Params), C.c_int]
+    lib.phet_step3.argtypes = [vp, i64, i64, i64, C.c_int, vp, vp, u64, vp, vp, i64]
+    lib.phet_fisher.argtypes = [vp, i64]
+    lib.phet_o_minmax.argtypes = [vp, C.POINTER(dbl)]
+    lib.phet_bin.argtypes = [vp, vp, i32, vp]
+    lib.phet_combine.argtypes = [vp, vp, i32, vp]
+    lib.phet_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    lib.phet_read_buffer.argtypes = [vp, C.c_int, vp, i64]
+    lib.phet_write_buffer.argtypes = [vp, C.c_int, vp, i64]
+    lib.phet_launch_count.argtypes = [vp]
+    lib.phet_launch_count.restype = i64
+    lib.phet_step1_geometry.argtypes = [vp, C.POINTER(i32)]
+    lib.phet_fit_host.argtypes = [vp, vp, C.c_int, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp,
+                                  C.POINTER(FitParams), vp, vp]
+    lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
+    lib.phet_host_p_two_sided_t.restype = dbl
+    lib.phet_host_p_two_sided_z.argtypes = [dbl]
+    lib.phet_host_p_two_sided_z.restype = dbl
+    lib.phet_host_perm_apply.argtypes = [u64, u64, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.phet_host_perm_apply.restype = C.c_uint32
+    for name in EXPORTS:
+        getattr(lib, name)
+    if lib.phet_abi_version() != 1:
+        raise PhetError("libphet_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PhetError("phet_b200: %s (status %d)" % (load_library().phet_last_error().decode(), rc))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device, one stream.  Thin object wrapper over the ``phet_ctx`` C handle."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.phet_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.G = 0
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phet_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(self.lib.phet_ctx_sync(self.h))
+
+    def set_classes(self, ctrl_rows, case_rows):
+        a = np.ascontiguousarray(ctrl_rows, dtype=np.int32)
+        b = np.ascontiguousarray(case_rows, dtype=np.int32)
+        _check(self.lib.phet_set_classes(self.h, _ptr(a), a.size, _ptr(b), b.size))
+        self.n0, self.n1 = a.size, b.size
+
+    def load_matrix(self, X: np.ndarray, normalize=NORM_ZSCORE, storage=None):
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        X = np.ascontiguousarray(X)
+        dt = PHET_F32 if X.dtype == np.float32 else PHET_F64
+        st = dt if storage is None else storage
+        _check(self.lib.phet_load_matrix(self.h, _ptr(X), 0, X.shape[0], X.shape[1], dt, normalize, st))
+        self.N, self.G = X.shape
+
+    def load_matrix_device(self, dev_ptr: int, N: int, G: int, dtype: int, normalize=NORM_ZSCORE, storage=None):
+        st = dtype if storage is None else storage
+        _check(self.lib.phet_load_matrix(self.h, C.c_void_p(dev_ptr), 1, N, G, dtype, normalize, st))
+        self.N, self.G = N, G
+
+    def set_index_sets(self, idx: np.ndarray):
+        """idx: int32 (S, 2, m), original row numbers; [:, 0] control draw, [:, 1] case draw."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        assert idx.ndim == 3 and idx.shape[1] == 2
+        _check(self.lib.phet_set_index_sets(self.h, _ptr(idx), idx.shape[0], idx.shape[2]))
+        self.S, self.m = idx.shape[0], idx.shape[2]
+
+    def step1(self, s_begin, s_end, params: Step1Params, accumulate=False):
+        _check(self.lib.phet_step1(self.h, s_begin, s_end, C.byref(params), 1 if accumulate else 0))
+
+    def step3(self, g_begin, g_end, m, table_full, table_last, n_last, perm_ctrl=None, perm_case=None,
+              seed=0):
+        tf = np.ascontiguousarray(table_full, dtype=np.float64)
+        tl = np.ascontiguousarray(table_last, dtype=np.float64)
+        if perm_ctrl is not None:
+            pc = np.ascontiguousarray(perm_ctrl, dtype=np.uint32)
+            pk = np.ascontiguousarray(perm_case, dtype=np.uint32)
+            _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_HOST, _ptr(pc), _ptr(pk), 0, _ptr(tf),
+                                       _ptr(tl), n_last))
+        else:
+            _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_DEVICE, None, None, seed, _ptr(tf),
+                                       _ptr(tl), n_last))
+
+    def fisher(self, S_total):
+        _check(self.lib.phet_fisher(self.h, S_total))
+
+    def o_minmax(self):
+        out = (C.c_double * 2)()
+        _check(self.lib.phet_o_minmax(self.h, out))
+        return float(out[0]), float(out[1])
+
+    def bin(self, edges: np.ndarray):
+        e = np.ascontiguousarray(edges, dtype=np.float64)
+        B = e.size - 1
+        counts = np.zeros(B, dtype=np.int64)
+        _check(self.lib.phet_bin(self.h, _ptr(e), B, _ptr(counts)))
+        return counts
+
+    def combine(self, weights: np.ndarray, fetch=True):
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        out = np.empty(self.G, dtype=np.float64) if fetch else None
+        _check(self.lib.phet_combine(self.h, _ptr(w), w.size, _ptr(out) if fetch else None))
+        return out
+
+    def device_ptr(self, which):
+        p = C.c_void_p()
+        n = C.c_int64()
+        _check(self.lib.phet_device_ptr(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def read(self, which, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        _check(self.lib.phet_read_buffer(self.h, which, _ptr(out), out.nbytes))
+        return out
+
+    def write(self, which, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        _check(self.lib.phet_write_buffer(self.h, which, _ptr(arr), arr.nbytes))
+
+    def launch_count(self):
+        return int(self.lib.phet_launch_count(self.h))
+
+    def step1_geometry(self):
+        out = (C.c_int32 * 5)()
+        _check(self.lib.phet_step1_geometry(self.h, out))
+        return dict(grid=out[0], block=out[1], smem=out[2], E=out[3], staged=bool(out[4]))

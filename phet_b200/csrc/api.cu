@@ -1,0 +1,511 @@
+// C ABI of libphet_b200 (see include/phet_b200.h).  Context management, uploads, and the thin
+// launch wrappers; the kernels live in normalize.cu, step1_*.cu, step3_*.cu and finalize.cu.
+#include "common.cuh"
+#include "pvalue.cuh"
+#include "step1_impl.cuh"
+#include "step3_impl.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace phet {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %s (%s) at %s:%d in `%s`", cudaGetErrorName(e), cudaGetErrorString(e), file,
+             line, what);
+    g_last_error = buf;
+    return e == cudaErrorMemoryAllocation ? PHET_ERR_NOMEM : PHET_ERR_CUDA;
+}
+
+int run_step1_f32(phet_ctx *c, const Step1Args &a);
+int run_step1_f64(phet_ctx *c, const Step1Args &a);
+int run_step3_f32(phet_ctx *c, const Step3Args &a);
+int run_step3_f64(phet_ctx *c, const Step3Args &a);
+
+// original row numbers -> class-grouped positions, in place
+__global__ void k_remap_idx(int32_t *__restrict__ idx, int64_t n, const int32_t *__restrict__ pos_of_row, int64_t N,
+                            int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = idx[i];
+    if (r < 0 || r >= N) {
+        *bad = 1;
+        idx[i] = 0;
+    } else {
+        idx[i] = pos_of_row[r];
+    }
+}
+
+int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate) {
+    Step1Args a;
+    a.xg = c->xg.p;
+    a.n_pad = c->n_pad;
+    a.G = c->G;
+    a.idx = c->idx.p;
+    a.m = c->m;
+    a.s_begin = s_begin;
+    a.s_end = s_end;
+    a.acc_f = c->acc.p;
+    a.acc_r = c->acc.p + c->G;
+    a.dbgP = nullptr;
+    a.dbgD = nullptr;
+    a.dbg_ld = s_end - s_begin;
+    if (prm->capture_debug) {
+        const size_t need = (size_t)c->G * (size_t)(s_end - s_begin);
+        if (int e = c->dbgP.alloc(need)) return e;
+        if (int e = c->dbgD.alloc(need)) return e;
+        PHET_CUDA(cudaMemsetAsync(c->dbgP.p, 0, need * sizeof(double), c->stream));
+        PHET_CUDA(cudaMemsetAsync(c->dbgD.p, 0, need * sizeof(double), c->stream));
+        a.dbgP = c->dbgP.p;
+        a.dbgD = c->dbgD.p;
+        c->S_local = s_end - s_begin;
+    }
+    a.q = prm->q;
+    a.test = prm->test;
+    a.df = 2.0 * (double)c->m - 2.0;
+    a.ln_beta = prm->ln_beta;
+    a.p_flush = prm->p_flush_below;
+    a.accumulate = accumulate;
+    if (s_end <= s_begin) {
+        if (!accumulate) PHET_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double) * 2 * c->G, c->stream));
+        return 0;
+    }
+    return c->storage == PHET_F32 ? run_step1_f32(c, a) : run_step1_f64(c, a);
+}
+
+int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, uint64_t seed,
+                 int64_t n_last) {
+    Step3Args a;
+    a.xg = c->xg.p;
+    a.n_pad = c->n_pad;
+    a.G = c->G;
+    a.n0 = c->n0;
+    a.n1 = c->n1;
+    a.min_c = c->n0 < c->n1 ? c->n0 : c->n1;
+    a.m = m;
+    a.n_slices = c->n_slices;
+    a.n_last = n_last;
+    a.g_begin = g_begin;
+    a.g_end = g_end;
+    a.perm_mode = perm_mode;
+    a.perm0 = c->perm0.p;
+    a.perm1 = c->perm1.p;
+    a.seed = seed;
+    a.tab_full = c->tab_full.p;
+    a.tab_last = c->tab_last.p;
+    a.o = c->o.p;
+    a.H = c->H.p;
+    return c->storage == PHET_F32 ? run_step3_f32(c, a) : run_step3_f64(c, a);
+}
+
+}  // namespace phet
+
+using namespace phet;
+
+extern "C" {
+
+int phet_abi_version(void) { return PHET_B200_ABI_VERSION; }
+
+const char *phet_last_error(void) { return g_last_error.c_str(); }
+
+int phet_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    return n;
+}
+
+int phet_ctx_create(int device, void *stream, phet_ctx **out) {
+    PHET_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    PHET_CUDA(cudaGetDeviceCount(&n));
+    PHET_REQUIRE(device >= 0 && device < n, "device index out of range (no CUDA device? there is no CPU fallback)");
+    PHET_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PHET_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("phet_b200 kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor));
+        return PHET_ERR_UNSUPPORTED;
+    }
+    phet_ctx *c = new (std::nothrow) phet_ctx();
+    if (!c) {
+        set_error("out of host memory");
+        return PHET_ERR_NOMEM;
+    }
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+        }
+        c->own_stream = true;
+    }
+    if (int e = c->scalars.alloc(16)) {
+        delete c;
+        return e;
+    }
+    *out = c;
+    return PHET_OK;
+}
+
+int phet_ctx_destroy(phet_ctx *c) {
+    if (!c) return PHET_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->rows_grouped.release();
+    c->pos_of_row.release();
+    c->xg.release();
+    c->mean.release();
+    c->sd.release();
+    c->colpart.release();
+    c->xraw.release();
+    c->idx.release();
+    c->acc.release();
+    c->dbgP.release();
+    c->dbgD.release();
+    c->o.release();
+    c->H.release();
+    c->perm0.release();
+    c->perm1.release();
+    c->tab_full.release();
+    c->tab_last.release();
+    c->f.release();
+    c->r.release();
+    c->fw.release();
+    c->scores.release();
+    c->bins.release();
+    c->scalars.release();
+    c->edges.release();
+    c->weights.release();
+    c->counts.release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PHET_OK;
+}
+
+int phet_ctx_sync(phet_ctx *c) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_CUDA(cudaSetDevice(c->device));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const int32_t *case_rows, int64_t n1) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(ctrl_rows && case_rows, "row lists are NULL");
+    PHET_REQUIRE(n0 >= 1 && n1 >= 1, "both classes need at least one cell");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const int64_t N = n0 + n1;
+    std::vector<int32_t> grouped((size_t)N), pos((size_t)N, -1);
+    for (int64_t i = 0; i < N; ++i) {
+        const int32_t r = i < n0 ? ctrl_rows[i] : case_rows[i - n0];
+        if (r < 0 || r >= N || pos[(size_t)r] != -1) {
+            set_error("invalid: class row lists must partition [0, n0+n1)");
+            return PHET_ERR_INVALID;
+        }
+        grouped[(size_t)i] = r;
+        pos[(size_t)r] = (int32_t)i;
+    }
+    if (int e = c->rows_grouped.alloc((size_t)N)) return e;
+    if (int e = c->pos_of_row.alloc((size_t)N)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->rows_grouped.p, grouped.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(cudaMemcpyAsync(c->pos_of_row.p, pos.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    c->n0 = n0;
+    c->n1 = n1;
+    c->classes_set = true;
+    c->matrix_set = false;
+    c->idx_set = false;
+    return PHET_OK;
+}
+
+int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype, int normalize,
+                     int storage) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(X != nullptr, "X is NULL");
+    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called before phet_load_matrix");
+    PHET_REQUIRE(N == c->n0 + c->n1, "N does not match the class sizes");
+    PHET_REQUIRE(G >= 1, "G must be >= 1");
+    PHET_REQUIRE(dtype == PHET_F32 || dtype == PHET_F64, "dtype must be PHET_F32 or PHET_F64");
+    PHET_REQUIRE(storage == PHET_F32 || storage == PHET_F64, "storage must be PHET_F32 or PHET_F64");
+    PHET_REQUIRE(normalize == PHET_NORM_NONE || normalize == PHET_NORM_ZSCORE, "normalize must be none or zscore");
+    PHET_REQUIRE(N < (int64_t)1 << 31, "N too large");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const size_t e_in = dtype == PHET_F32 ? 4 : 8;
+    const size_t e_st = storage == PHET_F32 ? 4 : 8;
+    c->N = N;
+    c->G = G;
+    c->storage = storage;
+    const int64_t per16 = 16 / (int64_t)e_st;
+    c->n_pad = (N + per16 - 1) / per16 * per16;
+    if (int e = c->xg.alloc((size_t)G * (size_t)c->n_pad * e_st)) return e;
+    if (int e = c->mean.alloc((size_t)G)) return e;
+    if (int e = c->sd.alloc((size_t)G)) return e;
+    if (int e = c->acc.alloc((size_t)2 * G)) return e;
+    if (int e = c->o.alloc((size_t)G)) return e;
+    if (int e = c->f.alloc((size_t)G)) return e;
+    if (int e = c->r.alloc((size_t)G)) return e;
+    if (int e = c->fw.alloc((size_t)G)) return e;
+    if (int e = c->scores.alloc((size_t)G)) return e;
+    if (int e = c->bins.alloc((size_t)G)) return e;
+    const void *Xdev = X;
+    if (!is_device) {
+        const size_t bytes = (size_t)N * (size_t)G * e_in;
+        if (int e = c->xraw.alloc(bytes)) return e;
+        PHET_CUDA(cudaMemcpyAsync(c->xraw.p, X, bytes, cudaMemcpyHostToDevice, c->stream));
+        Xdev = c->xraw.p;
+    }
+    if (int e = launch_normalize(c, Xdev, dtype, normalize)) return e;
+    PHET_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double) * 2 * G, c->stream));
+    PHET_CUDA(cudaMemsetAsync(c->o.p, 0, sizeof(double) * G, c->stream));
+    if (!is_device) {
+        PHET_CUDA(cudaStreamSynchronize(c->stream));
+        c->xraw.release();  // the normalised gene-major copy is all later steps need
+    }
+    c->matrix_set = true;
+    return PHET_OK;
+}
+
+int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called first");
+    PHET_REQUIRE(idx != nullptr && S >= 1 && m >= 1, "index sets: need S >= 1, m >= 1");
+    PHET_REQUIRE(m <= 512, "subsample size m > 512 is not supported");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const int64_t n = S * 2 * m;
+    if (int e = c->idx.alloc((size_t)n)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->idx.p, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    int *bad = reinterpret_cast<int *>(c->scalars.p + 12);
+    PHET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    k_remap_idx<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->idx.p, n, c->pos_of_row.p, c->n0 + c->n1, bad);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    int hbad = 0;
+    PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    PHET_REQUIRE(hbad == 0, "index sets contain a row number outside [0, N)");
+    c->S = S;
+    c->m = m;
+    c->idx_set = true;
+    return PHET_OK;
+}
+
+int phet_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate) {
+    PHET_REQUIRE(c != nullptr && prm != nullptr, "ctx/params NULL");
+    PHET_REQUIRE(c->matrix_set && c->idx_set, "load the matrix and index sets before phet_step1");
+    PHET_REQUIRE(0 <= s_begin && s_begin <= s_end && s_end <= c->S, "subsample range outside [0, S]");
+    PHET_REQUIRE(prm->test == PHET_TEST_T || prm->test == PHET_TEST_Z, "bad test kind");
+    const phet_quantile_pos &q = prm->q;
+    PHET_REQUIRE(q.j_lo >= 0 && q.k_lo < c->m && q.j_hi >= 0 && q.k_hi < c->m && q.j_lo <= q.k_lo && q.j_hi <= q.k_hi,
+                 "quantile positions outside [0, m)");
+    PHET_CUDA(cudaSetDevice(c->device));
+    return launch_step1(c, s_begin, s_end, prm, accumulate);
+}
+
+int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, const uint32_t *perm_ctrl,
+               const uint32_t *perm_case, uint64_t seed, const double *table_full, const double *table_last,
+               int64_t n_last) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(c->matrix_set, "load the matrix before phet_step3");
+    PHET_REQUIRE(0 <= g_begin && g_begin <= g_end && g_end <= c->G, "gene range outside [0, G]");
+    PHET_REQUIRE(m >= 1 && m <= 512, "slice length m must be in [1, 512]");
+    PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE, "bad perm_mode");
+    PHET_REQUIRE(table_full && table_last, "KS tables are NULL");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
+    const int64_t n_slices = (min_c + m - 1) / m;
+    PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");
+    c->n_slices = n_slices;
+    if (int e = c->H.alloc((size_t)c->G * (size_t)n_slices)) return e;
+    if (int e = c->tab_full.alloc((size_t)m + 1)) return e;
+    if (int e = c->tab_last.alloc((size_t)n_last + 1)) return e;
+    PHET_CUDA(cudaMemsetAsync(c->H.p, 0, sizeof(int32_t) * c->G * n_slices, c->stream));
+    PHET_CUDA(cudaMemsetAsync(c->o.p, 0, sizeof(double) * c->G, c->stream));
+    PHET_CUDA(cudaMemcpyAsync(c->tab_full.p, table_full, sizeof(double) * (m + 1), cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(
+        cudaMemcpyAsync(c->tab_last.p, table_last, sizeof(double) * (n_last + 1), cudaMemcpyHostToDevice, c->stream));
+    if (perm_mode == PHET_PERM_HOST) {
+        PHET_REQUIRE(perm_ctrl && perm_case, "host permutations are NULL");
+        const size_t n = (size_t)c->G * (size_t)min_c;
+        if (int e = c->perm0.alloc(n)) return e;
+        if (int e = c->perm1.alloc(n)) return e;
+        PHET_CUDA(cudaMemcpyAsync(c->perm0.p, perm_ctrl, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        PHET_CUDA(cudaMemcpyAsync(c->perm1.p, perm_case, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = launch_step3(c, g_begin, g_end, m, perm_mode, seed, n_last);
+    if (rc) return rc;
+    // tables and permutations are host buffers owned by the caller: finish the copies before returning
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int phet_fisher(phet_ctx *c, int64_t S_total) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set, "ctx not ready");
+    PHET_REQUIRE(S_total >= 1, "S_total must be >= 1");
+    PHET_CUDA(cudaSetDevice(c->device));
+    return launch_fisher(c, S_total);
+}
+
+int phet_o_minmax(phet_ctx *c, double out_minmax[2]) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set && out_minmax, "ctx not ready");
+    PHET_CUDA(cudaSetDevice(c->device));
+    return launch_o_minmax(c, out_minmax);
+}
+
+int phet_bin(phet_ctx *c, const double *edges, int32_t B, int64_t *counts_out) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set, "ctx not ready");
+    PHET_REQUIRE(edges != nullptr && B >= 1 && B <= 127, "need 1 <= B <= 127 bins");
+    PHET_CUDA(cudaSetDevice(c->device));
+    if (int e = c->edges.alloc((size_t)B + 1)) return e;
+    if (int e = c->counts.alloc((size_t)B)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->edges.p, edges, sizeof(double) * (B + 1), cudaMemcpyHostToDevice, c->stream));
+    c->n_bins = B;
+    int rc = launch_bin(c, B, counts_out);
+    if (rc) return rc;
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int phet_combine(phet_ctx *c, const double *weights, int32_t B, double *scores_out) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set, "ctx not ready");
+    PHET_REQUIRE(weights != nullptr && B >= 1 && B >= c->n_bins, "weights must cover every bin");
+    PHET_CUDA(cudaSetDevice(c->device));
+    if (int e = c->weights.alloc((size_t)B)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->weights.p, weights, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_combine(c, B, scores_out);
+    if (rc) return rc;
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
+    switch (which) {
+        case PHET_BUF_ACC: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 2 * c->G; break;
+        case PHET_BUF_O: *p = c->o.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_H: *p = c->H.p; *bytes = (int64_t)sizeof(int32_t) * c->G * c->n_slices; break;
+        case PHET_BUF_P: *p = c->dbgP.p; *bytes = (int64_t)sizeof(double) * c->G * c->S_local; break;
+        case PHET_BUF_DELTA: *p = c->dbgD.p; *bytes = (int64_t)sizeof(double) * c->G * c->S_local; break;
+        case PHET_BUF_F: *p = c->f.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_R: *p = c->r.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_BINS: *p = c->bins.p; *bytes = c->G; break;
+        case PHET_BUF_SCORES: *p = c->scores.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_XG: *p = c->xg.p; *bytes = c->G * c->n_pad * (c->storage == PHET_F32 ? 4 : 8); break;
+        case PHET_BUF_MEAN: *p = c->mean.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        default:
+            set_error("invalid: unknown buffer id");
+            return PHET_ERR_INVALID;
+    }
+    if (*p == nullptr) {
+        set_error("invalid: buffer has not been produced yet");
+        return PHET_ERR_INVALID;
+    }
+    return PHET_OK;
+}
+
+int phet_device_ptr(phet_ctx *c, int which, void **ptr_out, int64_t *bytes_out) {
+    PHET_REQUIRE(c != nullptr && ptr_out && bytes_out, "NULL argument");
+    return buffer_info(c, which, ptr_out, bytes_out);
+}
+
+int phet_read_buffer(phet_ctx *c, int which, void *host_out, int64_t bytes) {
+    PHET_REQUIRE(c != nullptr && host_out, "NULL argument");
+    void *p = nullptr;
+    int64_t have = 0;
+    if (int e = buffer_info(c, which, &p, &have)) return e;
+    PHET_REQUIRE(bytes <= have, "requested more bytes than the buffer holds");
+    PHET_CUDA(cudaSetDevice(c->device));
+    PHET_CUDA(cudaMemcpyAsync(host_out, p, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int phet_write_buffer(phet_ctx *c, int which, const void *host_in, int64_t bytes) {
+    PHET_REQUIRE(c != nullptr && host_in, "NULL argument");
+    void *p = nullptr;
+    int64_t have = 0;
+    if (int e = buffer_info(c, which, &p, &have)) return e;
+    PHET_REQUIRE(bytes <= have, "more bytes than the buffer holds");
+    PHET_CUDA(cudaSetDevice(c->device));
+    PHET_CUDA(cudaMemcpyAsync(p, host_in, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int64_t phet_launch_count(phet_ctx *c) { return c ? c->launches : 0; }
+
+int phet_step1_geometry(phet_ctx *c, int32_t out[5]) {
+    PHET_REQUIRE(c != nullptr && out, "NULL argument");
+    memcpy(out, c->step1_geom, sizeof(c->step1_geom));
+    return PHET_OK;
+}
+
+// np.linspace(lo, hi, B + 1) restated (numpy function_base.linspace): step = (hi-lo)/B;
+// y[i] = i*step + lo (product and sum rounded separately); y[B] = hi.
+static void linspace_edges(double lo, double hi, int B, std::vector<double> &e) {
+    e.resize((size_t)B + 1);
+    const double delta = hi - lo;
+    const double step = delta / (double)B;
+    for (int i = 0; i <= B; ++i) {
+        volatile double prod = (step != 0.0) ? (double)i * step : ((double)i / (double)B) * delta;
+        e[(size_t)i] = prod + lo;
+    }
+    e[(size_t)B] = hi;
+}
+
+int phet_fit_host(phet_ctx *c, const void *X, int dtype, int64_t N, int64_t G, const int32_t *ctrl_rows, int64_t n0,
+                  const int32_t *case_rows, int64_t n1, const int32_t *idx, int64_t S, const uint32_t *perm_ctrl,
+                  const uint32_t *perm_case, const phet_fit_params *prm, double *scores_out,
+                  int64_t *bin_counts_out) {
+    PHET_REQUIRE(c != nullptr && prm != nullptr && scores_out != nullptr, "NULL argument");
+    PHET_REQUIRE(prm->n_bins >= 2 && prm->weights, "need at least two feature weights");  // phet.py:122-123
+    if (int e = phet_set_classes(c, ctrl_rows, n0, case_rows, n1)) return e;
+    if (int e = phet_load_matrix(c, X, 0, N, G, dtype, prm->normalize, prm->storage)) return e;
+    if (int e = phet_set_index_sets(c, idx, S, prm->m)) return e;
+    if (int e = phet_step1(c, 0, S, &prm->step1, 0)) return e;
+    if (int e = phet_step3(c, 0, G, prm->m, prm->perm_mode, perm_ctrl, perm_case, prm->seed, prm->table_full,
+                           prm->table_last, prm->n_last))
+        return e;
+    if (int e = phet_fisher(c, S)) return e;
+    double mm[2];
+    if (int e = phet_o_minmax(c, mm)) return e;
+    std::vector<double> edges;
+    int B = prm->n_bins;
+    if (mm[0] == mm[1]) {  // sklearn: constant feature -> one bin, everything ordinal 0
+        edges = {-INFINITY, INFINITY};
+        std::vector<int64_t> cnt1(1);
+        if (int e = phet_bin(c, edges.data(), 1, cnt1.data())) return e;
+        if (bin_counts_out) {
+            for (int i = 0; i < B; ++i) bin_counts_out[i] = 0;
+            bin_counts_out[0] = cnt1[0];
+        }
+    } else {
+        linspace_edges(mm[0], mm[1], B, edges);
+        if (int e = phet_bin(c, edges.data(), B, bin_counts_out)) return e;
+    }
+    return phet_combine(c, prm->weights, B, scores_out);
+}
+
+// Host evaluations of the device p-value routines (same source, pvalue.cuh) for CPU unit tests.
+double phet_host_p_two_sided_t(double t, double df, double ln_beta) { return p_two_sided_t(t, df, ln_beta); }
+double phet_host_p_two_sided_z(double z) { return p_two_sided_z(z); }
+uint32_t phet_host_perm_apply(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t l, uint32_t i) {
+    return perm_apply(make_perm_key(seed, gene, cls, l), i);
+}
+
+}  // extern "C"

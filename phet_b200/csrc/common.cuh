@@ -1,0 +1,111 @@
+// Shared declarations for the phet_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/phet_b200.h"
+
+namespace phet {
+
+constexpr int kWarp = 32;
+constexpr int kMaxSmemOptin = 232448;  // 227 KB: per-CTA dynamic shared memory limit on sm_100
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PHET_CUDA(call)                                                           \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::phet::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PHET_REQUIRE(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::phet::set_error(std::string("invalid: ") + (msg)); \
+            return PHET_ERR_INVALID;                              \
+        }                                                         \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;  // elements
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        release();
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            n = 0;
+            return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+        }
+        n = count;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace phet
+
+// The context.  Plain struct: the C ABI only ever hands out pointers to it.
+struct phet_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+
+    // problem
+    int64_t N = 0, G = 0, n_pad = 0;   // cells, genes, padded row length of the gene-major copy
+    int64_t n0 = 0, n1 = 0;            // class sizes
+    int storage = PHET_F32;
+    bool classes_set = false, matrix_set = false, idx_set = false;
+    int64_t S = 0, m = 0;              // uploaded index sets
+    int64_t S_local = 0;               // subsamples covered by the debug buffers
+    int64_t n_slices = 0;
+    int32_t n_bins = 0;
+
+    phet::DevBuf<int32_t> rows_grouped;  // [N]: source row of grouped position q (controls, then cases)
+    phet::DevBuf<int32_t> pos_of_row;    // [N]: grouped position of original row
+    phet::DevBuf<unsigned char> xg;      // [G][n_pad] storage dtype
+    phet::DevBuf<double> mean, sd;       // [G]
+    phet::DevBuf<double> colpart;        // scratch for column statistics
+    phet::DevBuf<unsigned char> xraw;    // staging copy of a host matrix
+    phet::DevBuf<int32_t> idx;           // [S][2][m] grouped positions
+    phet::DevBuf<double> acc;            // [2][G]
+    phet::DevBuf<double> dbgP, dbgD;     // [G][S_local]
+    phet::DevBuf<double> o;              // [G]
+    phet::DevBuf<int32_t> H;             // [G][n_slices]
+    phet::DevBuf<uint32_t> perm0, perm1; // [G][min_c] (host mode)
+    phet::DevBuf<double> tab_full, tab_last;
+    phet::DevBuf<double> f, r, fw, scores;   // [G]
+    phet::DevBuf<signed char> bins;      // [G]
+    phet::DevBuf<double> scalars;        // small scratch: sums, min/max
+    phet::DevBuf<double> edges, weights;
+    phet::DevBuf<unsigned long long> counts;
+
+    int32_t step1_geom[5] = {0, 0, 0, 0, 0};
+};
+
+namespace phet {
+
+// kernels' host launchers (defined in the .cu files)
+int launch_normalize(phet_ctx *c, const void *Xdev, int dtype, int normalize);
+int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate);
+int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, uint64_t seed,
+                 int64_t n_last);
+int launch_fisher(phet_ctx *c, int64_t S_total);
+int launch_o_minmax(phet_ctx *c, double out[2]);
+int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
+int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
+
+}  // namespace phet

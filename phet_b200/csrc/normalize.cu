@@ -1,0 +1,159 @@
+// Stage 0: per-gene z-score (population sd) + NaN/inf -> 0, fused with the transpose from the
+// caller's cells x genes row-major matrix to the gene-major, class-grouped HBM layout.
+// Replaces /root/reference/src/model/phet.py:291,299 (scipy.stats.zscore(X, axis=0); nan_to_num).
+//
+// HBM layout produced: xg[g][n_pad] (storage dtype), position q < n0 holds control cell
+// ctrl_rows[q], position n0 + q' holds case cell case_rows[q'], positions >= N are 0.
+// Algorithmic traffic: read X twice (statistics, then normalise) + write once: 3*N*G*e bytes.
+#include "common.cuh"
+
+namespace phet {
+
+constexpr int kTile = 32;
+constexpr int kRowsPerBlock = 8;
+
+// Shifted sums per column over a chunk of rows: s = sum(x - K), ss = sum((x - K)^2), K = X[0][g].
+// fp64 accumulation; the shift removes the cancellation of the one-pass variance formula.
+template <typename Tin>
+__global__ void __launch_bounds__(kTile *kRowsPerBlock)
+    k_colstats_partial(const Tin *__restrict__ X, int64_t N, int64_t G, int64_t rows_per_chunk,
+                       double *__restrict__ part) {
+    __shared__ double sm_s[kRowsPerBlock][kTile + 1];
+    __shared__ double sm_q[kRowsPerBlock][kTile + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t g = (int64_t)blockIdx.x * kTile + tx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = min(r0 + rows_per_chunk, N);
+    double s = 0.0, q = 0.0;
+    if (g < G) {
+        const double K = (double)X[g];
+        int64_t r = r0 + ty;
+        for (; r + 3 * kRowsPerBlock < r1; r += 4 * kRowsPerBlock) {
+            const double d0 = (double)X[r * G + g] - K;
+            const double d1 = (double)X[(r + kRowsPerBlock) * G + g] - K;
+            const double d2 = (double)X[(r + 2 * kRowsPerBlock) * G + g] - K;
+            const double d3 = (double)X[(r + 3 * kRowsPerBlock) * G + g] - K;
+            s += d0; q += d0 * d0;
+            s += d1; q += d1 * d1;
+            s += d2; q += d2 * d2;
+            s += d3; q += d3 * d3;
+        }
+        for (; r < r1; r += kRowsPerBlock) {
+            const double d = (double)X[r * G + g] - K;
+            s += d;
+            q += d * d;
+        }
+    }
+    sm_s[ty][tx] = s;
+    sm_q[ty][tx] = q;
+    __syncthreads();
+    if (ty == 0 && g < G) {
+        double ts = 0.0, tq = 0.0;
+#pragma unroll
+        for (int i = 0; i < kRowsPerBlock; ++i) {
+            ts += sm_s[i][tx];
+            tq += sm_q[i][tx];
+        }
+        part[((int64_t)blockIdx.y * 2 + 0) * G + g] = ts;
+        part[((int64_t)blockIdx.y * 2 + 1) * G + g] = tq;
+    }
+}
+
+template <typename Tin>
+__global__ void k_colstats_final(const Tin *__restrict__ X, int64_t N, int64_t G, int chunks,
+                                 const double *__restrict__ part, double *__restrict__ mean,
+                                 double *__restrict__ sd) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < chunks; ++c) {  // fixed order: reproducible
+        s += part[((int64_t)c * 2 + 0) * G + g];
+        q += part[((int64_t)c * 2 + 1) * G + g];
+    }
+    const double n = (double)N;
+    const double K = (double)X[g];
+    double var = (q - s * s / n) / n;
+    if (var < 0.0) var = 0.0;
+    mean[g] = K + s / n;
+    sd[g] = sqrt(var);
+}
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kTile *kRowsPerBlock)
+    k_normalize_transpose(const Tin *__restrict__ X, int64_t N, int64_t G, int64_t n_pad,
+                          const int32_t *__restrict__ rows_grouped, const double *__restrict__ mean,
+                          const double *__restrict__ sd, int normalize, Tout *__restrict__ xg) {
+    __shared__ Tout tile[kTile][kTile + 1];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t g0 = (int64_t)blockIdx.x * kTile;
+    const int64_t q0 = (int64_t)blockIdx.y * kTile;
+    {
+        const int64_t g = g0 + tx;
+        double mu = 0.0, sg = 1.0;
+        if (normalize && g < G) {
+            mu = mean[g];
+            sg = sd[g];
+        }
+#pragma unroll
+        for (int i = ty; i < kTile; i += kRowsPerBlock) {
+            const int64_t q = q0 + i;
+            double z = 0.0;
+            if (q < N && g < G) {
+                const int64_t row = rows_grouped[q];
+                const double x = (double)X[row * G + g];
+                z = normalize ? (x - mu) / sg : x;
+                if (!isfinite(z)) z = 0.0;  // nan_to_num(nan=0, posinf=0, neginf=0), phet.py:299
+            }
+            tile[i][tx] = (Tout)z;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < kTile; i += kRowsPerBlock) {
+        const int64_t g = g0 + i;
+        const int64_t q = q0 + tx;
+        if (g < G && q < n_pad) xg[g * n_pad + q] = tile[tx][i];
+    }
+}
+
+template <typename Tin>
+static int run_normalize(phet_ctx *c, const Tin *X, int normalize) {
+    const int64_t N = c->N, G = c->G;
+    int chunks = 1;
+    if (normalize) {
+        const int64_t gx = (G + kTile - 1) / kTile;
+        // enough blocks for ~8 per SM, chunks of at least 256 rows
+        chunks = (int)((8LL * c->num_sms + gx - 1) / gx);
+        const int64_t max_chunks = (N + 255) / 256;
+        if (chunks > max_chunks) chunks = (int)max_chunks;
+        if (chunks < 1) chunks = 1;
+        const int64_t rows_per_chunk = (N + chunks - 1) / chunks;
+        chunks = (int)((N + rows_per_chunk - 1) / rows_per_chunk);
+        if (int e = c->colpart.alloc((size_t)chunks * 2 * G)) return e;
+        dim3 blk(kTile, kRowsPerBlock);
+        dim3 grd((unsigned)gx, (unsigned)chunks);
+        k_colstats_partial<Tin><<<grd, blk, 0, c->stream>>>(X, N, G, rows_per_chunk, c->colpart.p);
+        c->launches++;
+        k_colstats_final<Tin><<<(unsigned)((G + 255) / 256), 256, 0, c->stream>>>(X, N, G, chunks, c->colpart.p,
+                                                                                  c->mean.p, c->sd.p);
+        c->launches++;
+    }
+    dim3 blk(kTile, kRowsPerBlock);
+    dim3 grd((unsigned)((G + kTile - 1) / kTile), (unsigned)((c->n_pad + kTile - 1) / kTile));
+    if (c->storage == PHET_F32)
+        k_normalize_transpose<Tin, float><<<grd, blk, 0, c->stream>>>(X, N, G, c->n_pad, c->rows_grouped.p, c->mean.p,
+                                                                     c->sd.p, normalize, (float *)c->xg.p);
+    else
+        k_normalize_transpose<Tin, double><<<grd, blk, 0, c->stream>>>(X, N, G, c->n_pad, c->rows_grouped.p, c->mean.p,
+                                                                      c->sd.p, normalize, (double *)c->xg.p);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_normalize(phet_ctx *c, const void *Xdev, int dtype, int normalize) {
+    if (dtype == PHET_F32) return run_normalize<float>(c, (const float *)Xdev, normalize);
+    return run_normalize<double>(c, (const double *)Xdev, normalize);
+}
+
+}  // namespace phet

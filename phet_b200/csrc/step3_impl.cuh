@@ -1,0 +1,261 @@
+// Step 3: "discriminative power".  Replaces /root/reference/src/model/phet.py:473-498: for each
+// gene, permute the control column and the case column, cut slices of length m over
+// [0, min(n0, n1)), run a two-sample Kolmogorov-Smirnov test per slice, keep the smallest p.
+//
+// For equal slice lengths n the exact two-sided p-value of scipy.stats.ks_2samp depends only on
+// the INTEGER statistic h = n*D = max_v |#{a <= v} - #{b <= v}| (scipy _stats_py.py:7834-7836),
+// so the device computes h exactly (integer arithmetic on sorted samples, ties evaluated at
+// the end of each tie group like the ECDF) and looks p up in a host-built table.
+//
+// One CTA stages one gene (same SMEM layout as step 1); each warp takes slices: gather the two
+// samples through the permutation, sort both in registers, spill them to a per-warp SMEM
+// scratch, and for every a-value binary-search the b sample: D is non-increasing between
+// consecutive a-values, so its extremes are at a_i (counting a <= a_i, b <= a_i) and just
+// below a_i (counting a < a_i, b < a_i).
+#pragma once
+
+#include "common.cuh"
+#include "warp_prims.cuh"
+
+namespace phet {
+
+constexpr int kThreads3 = 512;
+
+struct Step3Args {
+    const void *xg;
+    int64_t n_pad, G;
+    int64_t n0, n1, min_c, m, n_slices, n_last;
+    int64_t g_begin, g_end;
+    int perm_mode;
+    const uint32_t *perm0, *perm1;  // [G][min_c] class-local positions (host mode)
+    uint64_t seed;
+    const double *tab_full, *tab_last;
+    double *o;
+    int32_t *H;
+};
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Keyed bijection of [0, l): four rounds of (add key, multiply by an odd constant, xor-shift)
+// on the enclosing power-of-two domain, cycle-walked back into range.  Mirrored in
+// phet_b200/perm.py (host) so device-mode permutations can be replayed on the CPU.
+struct PermKey {
+    uint32_t k0, k1, k2, k3, mask, s1, s2, l;
+};
+
+__host__ __device__ __forceinline__ PermKey make_perm_key(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t l) {
+    PermKey k;
+    const uint64_t a = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (2 * gene + cls + 1)));
+    const uint64_t b = splitmix64(a);
+    k.k0 = (uint32_t)a;
+    k.k1 = (uint32_t)(a >> 32);
+    k.k2 = (uint32_t)b;
+    k.k3 = (uint32_t)(b >> 32);
+    uint32_t w = l > 0 ? l - 1 : 0;
+    w |= w >> 1;
+    w |= w >> 2;
+    w |= w >> 4;
+    w |= w >> 8;
+    w |= w >> 16;
+    k.mask = w;
+    int bits = 0;
+    while ((w >> bits) & 1u) ++bits;
+    k.s1 = bits / 2 > 0 ? bits / 2 : 1;
+    k.s2 = bits / 3 > 0 ? bits / 3 : 1;
+    k.l = l;
+    return k;
+}
+
+__host__ __device__ __forceinline__ uint32_t perm_apply(const PermKey &k, uint32_t i) {
+    uint32_t x = i;
+    do {
+        x = (x + k.k0) & k.mask;
+        x = (x * 0x9E3779B1u) & k.mask;
+        x ^= x >> k.s1;
+        x = (x + k.k1) & k.mask;
+        x = (x * 0x85EBCA77u) & k.mask;
+        x ^= x >> k.s2;
+        x = (x + k.k2) & k.mask;
+        x = (x * 0xC2B2AE3Du) & k.mask;
+        x ^= x >> k.s1;
+        x = (x + k.k3) & k.mask;
+        x = (x * 0x27D4EB2Fu) & k.mask;
+        x ^= x >> k.s2;
+    } while (x >= k.l);
+    return x;
+}
+
+template <typename T, int E, bool STAGED>
+__global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+
+    const size_t gene_bytes = STAGED ? (size_t)a.n_pad * sizeof(T) : 0;
+    T *gene_s = reinterpret_cast<T *>(smem_raw);
+    unsigned char *after = smem_raw + ((gene_bytes + 15) & ~(size_t)15);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(after);
+    double *part = reinterpret_cast<double *>(after + 16);
+    T *scratch = reinterpret_cast<T *>(after + 16 + (size_t)nw * sizeof(double));
+    T *sa = scratch + (size_t)warp * (2 * 32 * E);
+    T *sb = sa + 32 * E;
+
+    if (STAGED) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    unsigned phase = 0;
+    const int n0 = (int)a.n0;
+
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const T *gene;
+        if (STAGED) {
+            if (tid == 0) stage_row(gene_s, static_cast<const T *>(a.xg) + g * a.n_pad, gene_bytes, bar);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            gene = gene_s;
+        } else {
+            gene = static_cast<const T *>(a.xg) + g * a.n_pad;
+        }
+        PermKey key0, key1;
+        if (a.perm_mode == PHET_PERM_DEVICE) {
+            key0 = make_perm_key(a.seed, (uint64_t)g, 0u, (uint32_t)a.n0);
+            key1 = make_perm_key(a.seed, (uint64_t)g, 1u, (uint32_t)a.n1);
+        }
+        double omin = CUDART_INF;
+        for (int64_t k = warp; k < a.n_slices; k += nw) {
+            const int n = (k == a.n_slices - 1) ? (int)a.n_last : (int)a.m;
+            const int64_t start = k * a.m;
+            T va[E], vb[E];
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const int p = lane + 32 * r;
+                if (p < n) {
+                    uint32_t qa, qb;
+                    if (a.perm_mode == PHET_PERM_DEVICE) {
+                        qa = perm_apply(key0, (uint32_t)(start + p));
+                        qb = perm_apply(key1, (uint32_t)(start + p));
+                    } else {
+                        qa = __ldg(a.perm0 + g * a.min_c + start + p);
+                        qb = __ldg(a.perm1 + g * a.min_c + start + p);
+                    }
+                    va[r] = STAGED ? gene[qa] : __ldg(gene + qa);
+                    vb[r] = STAGED ? gene[n0 + qb] : __ldg(gene + n0 + qb);
+                } else {
+                    va[r] = Lim<T>::inf();
+                    vb[r] = Lim<T>::inf();
+                }
+            }
+            warp_sort_asc<T, E>(va, lane);
+            warp_sort_asc<T, E>(vb, lane);
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                sa[lane + 32 * r] = va[r];
+                sb[lane + 32 * r] = vb[r];
+            }
+            __syncwarp();
+            int h = 0;
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const int p = lane + 32 * r;
+                if (p < n) {
+                    const T v = va[r];
+                    const bool first = (p == 0) || (sa[p - 1] != v);
+                    const bool last = (p == n - 1) || (sa[p + 1] != v);
+                    // lower and upper bound of v in the sorted b sample, searched together
+                    int lo1 = 0, len1 = n, lo2 = 0, len2 = n;
+                    while ((len1 | len2) > 0) {
+                        const int h1 = len1 >> 1, h2 = len2 >> 1;
+                        const T x1 = sb[min(lo1 + h1, n - 1)];
+                        const T x2 = sb[min(lo2 + h2, n - 1)];
+                        const bool g1 = (len1 > 0) && (x1 < v);
+                        const bool g2 = (len2 > 0) && (x2 <= v);
+                        lo1 = g1 ? lo1 + h1 + 1 : lo1;
+                        len1 = g1 ? len1 - h1 - 1 : h1;
+                        lo2 = g2 ? lo2 + h2 + 1 : lo2;
+                        len2 = g2 ? len2 - h2 - 1 : h2;
+                    }
+                    if (last) h = max(h, abs(p + 1 - lo2));
+                    if (first) h = max(h, abs(p - lo1));
+                }
+            }
+            h = __reduce_max_sync(kFull, h);
+            const double pv = (n == (int)a.m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
+            omin = fmin(omin, pv);
+            if (a.H != nullptr && lane == 0) a.H[g * a.n_slices + k] = h;
+            __syncwarp();
+        }
+        if (lane == 0) part[warp] = omin;
+        __syncthreads();
+        if (tid == 0) {
+            double t = CUDART_INF;
+            for (int w = 0; w < nw; ++w) t = fmin(t, part[w]);
+            a.o[g] = t;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int E, bool STAGED>
+static int launch_step3_inst(phet_ctx *c, const Step3Args &args, size_t smem_gene) {
+    auto kern = k_step3<T, E, STAGED>;
+    const size_t smem = smem_gene + 16 + (size_t)(kThreads3 / 32) * sizeof(double) +
+                        (size_t)(kThreads3 / 32) * 2 * 32 * E * sizeof(T);
+    if (smem > (size_t)kMaxSmemOptin) return 1;  // caller retries without staging
+    PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads3, smem));
+    if (per_sm < 1) {
+        set_error("step3: kernel does not fit on an SM");
+        return PHET_ERR_UNSUPPORTED;
+    }
+    int64_t grid = (int64_t)per_sm * c->num_sms;
+    const int64_t ng = args.g_end - args.g_begin;
+    if (grid > ng) grid = ng;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, kThreads3, smem, c->stream>>>(args);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int E>
+static int launch_step3_E(phet_ctx *c, const Step3Args &args) {
+    const size_t gene = ((size_t)c->n_pad * sizeof(T) + 15) & ~(size_t)15;
+    int rc = launch_step3_inst<T, E, true>(c, args, gene);
+    if (rc == 1) rc = launch_step3_inst<T, E, false>(c, args, 0);
+    if (rc == 1) {
+        set_error("step3: scratch does not fit in shared memory");
+        return PHET_ERR_UNSUPPORTED;
+    }
+    return rc;
+}
+
+template <typename T>
+static int run_step3_T(phet_ctx *c, const Step3Args &args) {
+    const int need = (int)((args.m + 31) / 32);
+    if (need <= 1) return launch_step3_E<T, 1>(c, args);
+    if (need <= 2) return launch_step3_E<T, 2>(c, args);
+    if (need <= 3) return launch_step3_E<T, 3>(c, args);
+    if (need <= 4) return launch_step3_E<T, 4>(c, args);
+    if (need <= 5) return launch_step3_E<T, 5>(c, args);
+    if (need <= 6) return launch_step3_E<T, 6>(c, args);
+    if (need <= 8) return launch_step3_E<T, 8>(c, args);
+    if (need <= 10) return launch_step3_E<T, 10>(c, args);
+    if (need <= 12) return launch_step3_E<T, 12>(c, args);
+    if (need <= 16) return launch_step3_E<T, 16>(c, args);
+    set_error("step3: slice length m > 512 is not supported by the register-resident sort");
+    return PHET_ERR_UNSUPPORTED;
+}
+
+}  // namespace phet

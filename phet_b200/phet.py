@@ -1,0 +1,262 @@
+"""Drop-in ``PHet`` model class whose ``fit_predict`` runs on a B200 through libphet_b200.
+
+Mirrors the reference's operator interface for this path -- constructor
+``/root/reference/src/model/phet.py:33-40`` and ``fit_predict(X, y, sample_ids=None,
+subtypes=None) -> ndarray (G, 1) float64`` (``phet.py:163-518``) -- with the same argument
+names, defaults, error behaviour and RNG consumption, so the caller at ``src/train.py:474-477``
+can switch by changing one import.  Scope is the binary (control/case), ``delta_type="iqr"``,
+non-pseudobulk branch; the other branches raise ``NotImplementedError``.
+
+There is no CPU fallback: every stage of the hot path runs in hand-written sm_100a kernels
+behind the C ABI in ``include/phet_b200.h``; if the library or a B200 is missing,
+``fit_predict`` raises ``phet_b200._capi.PhetError``.
+"""
+from __future__ import annotations
+
+from typing import Literal, Optional
+
+import numpy as np
+
+from . import _capi, hostmath
+
+SEED_VALUE = 0.001  # phet.py:29 (applied on the device, csrc/finalize.cu)
+
+
+class PHet:
+    def __init__(self, normalize: Literal["robust", "zscore", "log"] | None = "zscore",
+                 percentiles: Optional[tuple[int, int]] = (25, 75), num_subsamples: int = 1000,
+                 subsampling_size: Literal["optimum", "sqrt"] | int = "sqrt",
+                 delta_type: Literal["iqr", "hvf"] = "iqr",
+                 group_test: Literal["anova", "kruskal"] = "anova",
+                 multiconditions_strategy: Literal["pairwise", "one_vs_all"] = "one_vs_all",
+                 multiconditions_aggregation: Literal["mean", "max"] = "max",
+                 adjust_pvalue: bool = False, feature_weight: Optional[list[float]] = None,
+                 *, iqr_range: Optional[tuple[int, int]] = None, device: int | None = None,
+                 storage: Literal["auto", "f32", "f64"] = "auto",
+                 permutation: Literal["reference", "device"] = "reference",
+                 distributed: bool | Literal["auto"] = "auto", capture: bool = False):
+        """Same parameters as the reference (phet.py:33-104).  Extra keyword-only arguments:
+
+        iqr_range    alias of ``percentiles`` -- it is the name ``src/train.py:474`` passes.
+        device       CUDA device index (default: LOCAL_RANK if set, else 0).
+        storage      element type of the normalised matrix kept in HBM/SMEM ("auto" = X's dtype).
+        permutation  "reference": Step-3 permutations are drawn from ``np.random`` exactly as the
+                     reference does (phet.py:486-487), bit-compatible for a given seed;
+                     "device": a keyed bijection evaluated on the GPU (no G x N host draws).
+        distributed  shard subsamples (Step 1) and genes (Step 3) over the ranks of an initialised
+                     ``torch.distributed`` group; "auto" = on when world_size > 1.
+        capture      keep per-stage intermediates (P, delta, H, o, bins) as attributes.
+        """
+        if iqr_range is not None:
+            percentiles = iqr_range
+        self.normalize = normalize
+        self.iqr_range = percentiles
+        self.num_subsamples = num_subsamples
+        self.subsampling_size = subsampling_size
+        self.delta_type = delta_type
+        self.group_test = group_test
+        self.multiconditions_strategy = multiconditions_strategy
+        self.multiconditions_aggregation = multiconditions_aggregation
+        self.adjust_pvalue = adjust_pvalue
+        if delta_type == "hvf" and self.normalize is not None:
+            self.normalize = "log"  # phet.py:116-117
+        if feature_weight is None:
+            feature_weight = [0.4, 0.3, 0.2, 0.1]
+        elif len(feature_weight) < 2:
+            raise ValueError("Feature weight list must contain at least two elements.")  # phet.py:122-123
+        self.feature_weight = np.array(feature_weight) / np.sum(feature_weight)  # phet.py:124
+        self.device = device
+        self.storage = storage
+        self.permutation = permutation
+        self.distributed = distributed
+        self.capture = capture
+        self.timings_ = {}
+
+    # ------------------------------------------------------------------------------------
+    def _check_scope(self, num_classes, sample_ids):
+        if num_classes > 2:
+            raise NotImplementedError("phet_b200 covers the two-condition path; the multi-class branch "
+                                      "(phet.py:304-306,348-382) is out of scope")
+        if sample_ids:
+            raise NotImplementedError("pseudobulk branch (phet.py:224-253) is out of scope")
+        if self.delta_type != "iqr":
+            raise NotImplementedError("delta_type='hvf' (phet.py:255-262,403-411) is out of scope")
+        if self.normalize not in ("zscore", None):
+            raise NotImplementedError("normalize must be 'zscore' or None on the B200 path")
+        if self.adjust_pvalue:
+            raise NotImplementedError("adjust_pvalue=True (phet.py:430-431) is out of scope")
+
+    def _resolve_device(self):
+        if self.device is not None:
+            return int(self.device)
+        import os
+        return int(os.environ.get("LOCAL_RANK", "0"))
+
+    def _dist(self):
+        """(rank, world, torch.distributed module or None)."""
+        if self.distributed is False:
+            return 0, 1, None
+        try:
+            import torch.distributed as dist
+        except Exception:
+            return 0, 1, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size(), dist
+        return 0, 1, None
+
+    # ------------------------------------------------------------------------------------
+    def draw_index_sets(self, examples_i, examples_j, m, replace):
+        """Replay of phet.py:397-402 on the legacy global RNG: control draw then case draw."""
+        S = self.num_subsamples
+        idx = np.empty((S, 2, m), dtype=np.int32)
+        for s in range(S):
+            idx[s, 0] = np.random.choice(a=examples_i, size=m, replace=replace)
+            idx[s, 1] = np.random.choice(a=examples_j, size=m, replace=replace)
+        return idx
+
+    @staticmethod
+    def draw_permutations(n0, n1, num_features, min_c):
+        """Replay of phet.py:486-487: per gene, permutation of the control then the case column.
+        ``np.random.permutation(values)`` consumes the stream exactly like ``permutation(len)``."""
+        p0 = np.empty((num_features, min_c), dtype=np.uint32)
+        p1 = np.empty((num_features, min_c), dtype=np.uint32)
+        for g in range(num_features):
+            p0[g] = np.random.permutation(n0)[:min_c]
+            p1[g] = np.random.permutation(n1)[:min_c]
+        return p0, p1
+
+    # ------------------------------------------------------------------------------------
+    def fit_predict(self, X, y, sample_ids: list | None = None, subtypes: list | None = None):
+        """Feature scores, shape (num_features, 1), float64 -- see phet.py:163-209."""
+        import time
+        t_all = time.perf_counter()
+        X = np.asarray(X)
+        num_examples, num_features = X.shape
+        y = np.asarray(y)
+        unique_classes = np.unique(y)
+        num_classes = len(unique_classes)
+        if num_classes < 2:
+            raise Exception("More than two valid groups are allowed!")  # phet.py:216-218
+        if sample_ids:
+            if len(sample_ids) != num_examples:
+                raise Exception("The number of sample IDs provided does not match the number of example!")
+            if subtypes and len(subtypes) != num_examples:
+                raise Exception("The number of subtypes provided does not match the number of examples!")
+        self._check_scope(num_classes, sample_ids)
+        if len(y) != num_examples:
+            raise Exception("The number of labels does not match the number of examples!")
+        y = np.searchsorted(unique_classes, y)  # LabelEncoder, phet.py:220
+
+        examples_i = np.where(y == 0)[0]
+        examples_j = np.where(y == 1)[0]
+        n0, n1 = len(examples_i), len(examples_j)
+        min_c = min(n0, n1)
+        m = hostmath.subsample_size(n0, n1, self.subsampling_size)
+        if m < 1:
+            raise ValueError("subsampling size must be >= 1")
+        replace = bool(m > n0 or m > n1)  # phet.py:393-396
+        S = int(self.num_subsamples)
+        rank, world, dist = self._dist()
+
+        # ---- host draws, in the reference's order (all Step-1 draws, then Step-3 permutations)
+        t0 = time.perf_counter()
+        if dist is None or rank == 0:
+            idx = self.draw_index_sets(examples_i, examples_j, m, replace)
+        else:
+            idx = np.empty((S, 2, m), dtype=np.int32)
+        n_slices, n_last = hostmath.step3_slices(min_c, m)
+        perm0 = perm1 = None
+        seed = 0
+        if self.permutation == "reference":
+            if dist is None or rank == 0:
+                perm0, perm1 = self.draw_permutations(n0, n1, num_features, min_c)
+            else:
+                perm0 = np.empty((num_features, min_c), dtype=np.uint32)
+                perm1 = np.empty((num_features, min_c), dtype=np.uint32)
+        elif self.permutation == "device":
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) if (dist is None or rank == 0) else 0
+        else:
+            raise ValueError("permutation must be 'reference' or 'device'")
+        if dist is not None:
+            from .distributed import broadcast_numpy
+            idx = broadcast_numpy(idx, dist)
+            if perm0 is not None:
+                perm0 = broadcast_numpy(perm0.view(np.int32), dist).view(np.uint32)
+                perm1 = broadcast_numpy(perm1.view(np.int32), dist).view(np.uint32)
+            seed = int(broadcast_numpy(np.array([seed], dtype=np.int64), dist)[0])
+        self.timings_["host_draws_s"] = time.perf_counter() - t0
+
+        # ---- device
+        dev = self._resolve_device()
+        stream = None
+        if dist is not None:
+            import torch
+            torch.cuda.set_device(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        ctx = _capi.Context(dev, stream)
+        try:
+            scores = self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices,
+                                      n_last, rank, world, dist)
+        finally:
+            ctx.close()
+        self.timings_["fit_s"] = time.perf_counter() - t_all
+        return scores
+
+    # ------------------------------------------------------------------------------------
+    def _step1_params(self, X_dtype, m):
+        qdt = np.float32 if X_dtype == np.float32 else np.float64
+        (j0, k0, g0), (j1, k1, g1) = hostmath.quantile_positions(m, self.iqr_range, dtype=qdt)
+        prm = _capi.Step1Params()
+        prm.test = _capi.TEST_T if m < 30 else _capi.TEST_Z  # phet.py:425-428
+        df = 2.0 * m - 2.0
+        prm.ln_beta = hostmath.ln_beta_half(df) if (prm.test == _capi.TEST_T and df > 0) else 0.0
+        # float32 input: scipy's stdtr returns float32, which underflows to 0 below 2^-150
+        prm.p_flush_below = 2.0 ** -150 if (X_dtype == np.float32 and prm.test == _capi.TEST_T) else 0.0
+        prm.q = _capi.QuantilePos(j0, k0, j1, k1, g0, g1)
+        prm.capture_debug = 1 if self.capture else 0
+        return prm
+
+    def _run_device(self, ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
+                    rank, world, dist):
+        G = X.shape[1]
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        storage = {"auto": None, "f32": _capi.PHET_F32, "f64": _capi.PHET_F64}[self.storage]
+        ctx.set_classes(examples_i, examples_j)
+        ctx.load_matrix(X, _capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE, storage)
+        ctx.set_index_sets(idx)
+        prm = self._step1_params(X.dtype, m)
+        from .distributed import shard_range
+        s_lo, s_hi = shard_range(S, rank, world)
+        g_lo, g_hi = shard_range(G, rank, world)
+        ctx.step1(s_lo, s_hi, prm)                                   # phet.py:397-432
+        tab_full = hostmath.ks_exact_table(m)
+        tab_last = hostmath.ks_exact_table(n_last)
+        ctx.step3(g_lo, g_hi, m, tab_full, tab_last, n_last, perm0, perm1, seed)   # phet.py:473-498
+        if dist is not None:
+            from .distributed import allreduce_device_buffer
+            allreduce_device_buffer(ctx, _capi.BUF_ACC, dist)       # sum_s -2 ln p, sum_s delta
+            allreduce_device_buffer(ctx, _capi.BUF_O, dist)         # genes outside a rank's slice are 0
+        ctx.fisher(S)                                                # phet.py:435-462
+        o_min, o_max = ctx.o_minmax()
+        B = len(self.feature_weight)
+        edges = hostmath.uniform_bin_edges(o_min, o_max, B)          # sklearn KBinsDiscretizer 'uniform'
+        counts = ctx.bin(edges)                                      # phet.py:500-504
+        self.bin_counts_ = np.concatenate([counts, np.zeros(B - len(counts), dtype=np.int64)])
+        scores = ctx.combine(self.feature_weight)                    # phet.py:510-516
+        self.m_ = m
+        self.index_sets_ = idx
+        self.launches_ = ctx.launch_count()
+        self.step1_geometry_ = ctx.step1_geometry()
+        if self.capture:
+            self.fsum_, self.rsum_ = ctx.read(_capi.BUF_ACC, np.float64, (2, G))
+            self.f_ = ctx.read(_capi.BUF_F, np.float64, (G,))
+            self.r_ = ctx.read(_capi.BUF_R, np.float64, (G,))
+            self.o_ = ctx.read(_capi.BUF_O, np.float64, (G,))
+            self.H_ = ctx.read(_capi.BUF_H, np.int32, (G, n_slices))
+            self.bins_ = ctx.read(_capi.BUF_BINS, np.int8, (G,))
+            self.edges_ = edges
+            if world == 1:
+                self.P_ = ctx.read(_capi.BUF_P, np.float64, (G, S))
+                self.R_ = ctx.read(_capi.BUF_DELTA, np.float64, (G, S))
+        return np.reshape(scores, (G, 1))

@@ -1,0 +1,146 @@
+"""GPU parity: the CUDA path (through the C ABI / drop-in class) against the committed golden
+vectors (outputs of the unmodified reference) and against the oracle on the same inputs.
+
+Integer outputs (index sets, KS statistics h, bins, bin counts, top-k ranking) must be
+bit-exact.  Floating-point outputs agree within rtol 1e-5 when the matrix is staged in fp64
+(north_star: "rtol 1e-5 in fp64") and rtol 1e-3 when it is staged in fp32.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"f64": 1e-5, "f32": 1e-3}
+NAMES = golden_names()
+
+
+def _run(g, tag, storage="auto", permutation="reference", capture=True):
+    from phet_b200 import PHet
+    dt = np.float64 if tag == "f64" else np.float32
+    X = np.ascontiguousarray(g["X"].astype(dt))
+    np.random.seed(int(g["seed"]))
+    est = PHet(**g["params"], storage=storage, permutation=permutation, capture=capture, distributed=False)
+    scores = est.fit_predict(X, g["y"].astype(np.int64))
+    return est, scores
+
+
+def _topk(s, k):
+    return np.argsort(-s[:, 0], kind="stable")[:k]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_scores_match_reference(name):
+    g = load_golden(name)
+    for tag in g["dtypes"]:
+        est, scores = _run(g, tag)
+        ref = g[f"scores_{tag}"]
+        assert scores.shape == ref.shape and scores.dtype == np.float64
+        # draws: identical consumption of np.random
+        assert np.array_equal(est.index_sets_[:, 0], g["idx_i"]) and np.array_equal(est.index_sets_[:, 1], g["idx_j"])
+        # integer outputs: bit-exact
+        assert np.array_equal(est.H_, g[f"H_{tag}"]), "KS integer statistics differ"
+        assert np.array_equal(est.bins_.astype(np.int64), g[f"bins_{tag}"].astype(np.int64))
+        assert np.array_equal(est.bin_counts_, g[f"bin_counts_{tag}"])
+        assert np.array_equal(est.o_, g[f"o_{tag}"]), "o must be bit-exact (table lookup of exact h)"
+        # floating point
+        rtol = RTOL[tag]
+        ks = g[f"P_head_{tag}"].shape[1]
+        assert np.allclose(est.R_[:, :ks], g[f"R_head_{tag}"], rtol=rtol, atol=1e-7 if tag == "f32" else 1e-12)
+        assert np.allclose(est.P_[:, :ks], g[f"P_head_{tag}"], rtol=rtol, atol=1e-300)
+        assert np.allclose(est.rsum_, g[f"rsum_{tag}"], rtol=rtol, atol=1e-9)
+        assert np.allclose(est.fsum_, g[f"fsum_{tag}"], rtol=rtol, atol=1e-9)
+        assert np.allclose(scores, ref, rtol=rtol, atol=1e-12), float(np.max(np.abs(scores - ref) / np.abs(ref).max()))
+        k = min(100, scores.shape[0] // 4)
+        if tag == "f64":
+            assert np.array_equal(_topk(scores, k), _topk(ref, k)), "top-k ranking differs"
+
+
+@pytest.mark.parametrize("name", ["srbct_s200", "hbecs_like", "cells10k_m70", "unbalanced_2200"])
+def test_f32_staging_of_f64_input(name):
+    """fp64 input staged as fp32 in HBM/SMEM (the fast layout): rtol 1e-3, exact ranking head."""
+    g = load_golden(name)
+    est, scores = _run(g, "f64", storage="f32")
+    ref = g["scores_f64"]
+    assert np.allclose(scores, ref, rtol=1e-3, atol=1e-12)
+    assert np.array_equal(est.bin_counts_, g["bin_counts_f64"])
+    assert np.array_equal(_topk(scores, 20), _topk(ref, 20))
+
+
+@pytest.mark.parametrize("name", ["hbecs_like", "balanced_1200", "cells10k_m70"])
+def test_device_permutation_mode_against_oracle(name):
+    """permutation='device': replay the device's keyed permutations on the host, feed them to the
+    oracle, and require identical integer statistics / bins and matching scores."""
+    from oracle import phet_oracle as po
+    from phet_b200.perm import device_permutation
+    g = load_golden(name)
+    X = g["X"].astype(np.float64)
+    y = g["y"].astype(np.int64)
+    np.random.seed(int(g["seed"]))
+    from phet_b200 import PHet
+    est = PHet(**g["params"], permutation="device", capture=True, distributed=False)
+    scores = est.fit_predict(X, y)
+    # the class draws its device seed from np.random right after the Step-1 draws
+    np.random.seed(int(g["seed"]))
+    idx_i, idx_j, _ = po.draw_index_sets(y, int(g["m"]), g["params"]["num_subsamples"])
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    n0, n1 = int((y == 0).sum()), int((y == 1).sum())
+    G = X.shape[1]
+    perm_i = np.stack([device_permutation(seed, gi, 0, n0) for gi in range(G)]).astype(np.int64)
+    perm_j = np.stack([device_permutation(seed, gi, 1, n1) for gi in range(G)]).astype(np.int64)
+    res = po.fit_predict_oracle(X, y, index_sets=(idx_i, idx_j), perms=(perm_i, perm_j), **g["params"])
+    assert np.array_equal(est.H_, res.H)
+    assert np.array_equal(est.bin_counts_, res.bin_counts)
+    assert np.allclose(scores, res.scores, rtol=1e-5, atol=1e-12)
+
+
+def test_c_abi_one_call_fit_host():
+    """phet_fit_host (the single C entry a non-Python caller would use) == class path."""
+    import ctypes as C
+    from phet_b200 import _capi, hostmath
+    g = load_golden("hbecs_like")
+    X = np.ascontiguousarray(g["X"].astype(np.float64))
+    y = g["y"].astype(np.int64)
+    ctrl = np.where(y == 0)[0].astype(np.int32)
+    case = np.where(y == 1)[0].astype(np.int32)
+    m = int(g["m"])
+    S = g["params"]["num_subsamples"]
+    idx = np.ascontiguousarray(np.stack([g["idx_i"], g["idx_j"]], axis=1).astype(np.int32))
+    min_c = min(len(ctrl), len(case))
+    n_slices, n_last = hostmath.step3_slices(min_c, m)
+    p0 = np.ascontiguousarray(g["perm_i"][:, :min_c].astype(np.uint32))
+    p1 = np.ascontiguousarray(g["perm_j"][:, :min_c].astype(np.uint32))
+    w = np.array([0.4, 0.3, 0.2, 0.1])
+    tf, tl = hostmath.ks_exact_table(m), hostmath.ks_exact_table(n_last)
+    (j0, k0, g0), (j1, k1, g1) = hostmath.quantile_positions(m, (25, 75))
+    prm = _capi.FitParams()
+    prm.normalize, prm.storage = _capi.NORM_ZSCORE, _capi.PHET_F64
+    prm.step1.test = _capi.TEST_Z
+    prm.step1.q = _capi.QuantilePos(j0, k0, j1, k1, g0, g1)
+    prm.m, prm.perm_mode, prm.seed, prm.n_bins, prm.n_last = m, _capi.PERM_HOST, 0, 4, n_last
+    prm.weights = w.ctypes.data_as(C.POINTER(C.c_double))
+    prm.table_full = tf.ctypes.data_as(C.POINTER(C.c_double))
+    prm.table_last = tl.ctypes.data_as(C.POINTER(C.c_double))
+    ctx = _capi.Context(0)
+    scores = np.empty(X.shape[1])
+    counts = np.zeros(4, dtype=np.int64)
+    rc = ctx.lib.phet_fit_host(ctx.h, _capi._ptr(X), _capi.PHET_F64, X.shape[0], X.shape[1], _capi._ptr(ctrl),
+                               len(ctrl), _capi._ptr(case), len(case), _capi._ptr(idx), S, _capi._ptr(p0),
+                               _capi._ptr(p1), C.byref(prm), _capi._ptr(scores), _capi._ptr(counts))
+    assert rc == 0, ctx.lib.phet_last_error()
+    ctx.close()
+    assert np.array_equal(counts, g["bin_counts_f64"])
+    assert np.allclose(scores[:, None], g["scores_f64"], rtol=1e-5, atol=1e-12)
+
+
+def test_errors_are_loud():
+    from phet_b200 import PHet, _capi
+    with pytest.raises(ValueError):
+        PHet(feature_weight=[1.0])
+    with pytest.raises(Exception):
+        PHet().fit_predict(np.zeros((4, 3)), np.zeros(4))
+    ctx = _capi.Context(0)
+    with pytest.raises(_capi.PhetError):
+        ctx.load_matrix(np.zeros((4, 3)))  # classes not set
+    ctx.close()
