@@ -47,7 +47,7 @@ def test_scores_match_reference(name):
         # floating point
         rtol = RTOL[tag]
         ks = g[f"P_head_{tag}"].shape[1]
-        assert np.allclose(est.R_[:, :ks], g[f"R_head_{tag}"], rtol=rtol, atol=1e-7 if tag == "f32" else 1e-12)
+        assert np.allclose(est.R_[:, :ks], g[f"R_head_{tag}"], rtol=rtol, atol=1e-5 if tag == "f32" else 1e-12)
         assert np.allclose(est.P_[:, :ks], g[f"P_head_{tag}"], rtol=rtol, atol=1e-300)
         assert np.allclose(est.rsum_, g[f"rsum_{tag}"], rtol=rtol, atol=1e-9)
         assert np.allclose(est.fsum_, g[f"fsum_{tag}"], rtol=rtol, atol=1e-9)
