@@ -192,7 +192,9 @@ class PHet:
         if dist is not None:
             import torch
             torch.cuda.set_device(dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._torch_stream = torch.cuda.Stream(dev)   # non-default: handle 0 would mean "own stream"
+            torch.cuda.set_stream(self._torch_stream)
+            stream = self._torch_stream.cuda_stream
         ctx = _capi.Context(dev, stream)
         try:
             scores = self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices,
