@@ -120,6 +120,32 @@ int phet_step3(phet_ctx *ctx, int64_t g_begin, int64_t g_end, int64_t m, int per
                const uint32_t *perm_ctrl, const uint32_t *perm_case, uint64_t seed,
                const double *table_full, const double *table_last, int64_t n_last);
 
+/* Stage 0 + Step 1 + Step 3 fused over gene blocks (the end-to-end path).  For a host matrix
+ * (is_device = 0; pinned memory recommended) block b+1 is copied H2D on a second stream while
+ * block b is normalised and processed, so the fit is bounded by max(PCIe, compute) instead of
+ * their sum.  Requires phet_set_classes and phet_set_index_sets.  Genes [g_begin, g_end) are
+ * loaded (only they become resident) and run through Step 1 for subsamples [s_begin, s_end);
+ * Step 3 runs for genes [g3_begin, g3_end), a sub-range of the loaded genes.  Single GPU:
+ * all ranges full.  Subsample sharding (north star): all genes, a slice of s, a slice of g3.
+ * Gene sharding (capacity layout): a slice of genes, all s, g3 = the same slice. */
+typedef struct {
+    int32_t normalize, storage;
+    int64_t g_begin, g_end;
+    int64_t s_begin, s_end;
+    int64_t g3_begin, g3_end;
+    phet_step1_params step1;
+    int64_t m;
+    int32_t perm_mode;
+    uint64_t seed;
+    const uint32_t *perm_ctrl, *perm_case; /* PHET_PERM_HOST: uint32 [G][min_c] for all genes */
+    const double *table_full, *table_last;
+    int64_t n_last;
+    int64_t block_genes;                   /* genes per H2D block; 0 = auto */
+} phet_pipeline_params;
+
+int phet_run_pipeline(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G, int dtype,
+                      const phet_pipeline_params *prm);
+
 /* Replaces phet.py:435-444 and 449-462: r = acc_r / S_total, f = standardised Fisher. */
 int phet_fisher(phet_ctx *ctx, int64_t S_total);
 

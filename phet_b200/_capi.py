@@ -23,7 +23,7 @@ PERM_HOST, PERM_DEVICE = 0, 1
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
-    "phet_step3", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_device_ptr",
+    "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
@@ -41,6 +41,14 @@ class QuantilePos(C.Structure):
 class Step1Params(C.Structure):
     _fields_ = [("test", C.c_int32), ("ln_beta", C.c_double), ("p_flush_below", C.c_double),
                 ("q", QuantilePos), ("capture_debug", C.c_int32)]
+
+
+class PipelineParams(C.Structure):
+    _fields_ = [("normalize", C.c_int32), ("storage", C.c_int32), ("g_begin", C.c_int64), ("g_end", C.c_int64),
+                ("s_begin", C.c_int64), ("s_end", C.c_int64), ("g3_begin", C.c_int64), ("g3_end", C.c_int64),
+                ("step1", Step1Params), ("m", C.c_int64), ("perm_mode", C.c_int32), ("seed", C.c_uint64),
+                ("perm_ctrl", C.c_void_p), ("perm_case", C.c_void_p), ("table_full", C.c_void_p),
+                ("table_last", C.c_void_p), ("n_last", C.c_int64), ("block_genes", C.c_int64)]
 
 
 class FitParams(C.Structure):
@@ -82,6 +90,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_set_index_sets.argtypes = [vp, vp, i64, i64]
     lib.phet_step1.argtypes = [vp, i64, i64, C.POINTER(Step1Params), C.c_int]
     lib.phet_step3.argtypes = [vp, i64, i64, i64, C.c_int, vp, vp, u64, vp, vp, i64]
+    lib.phet_run_pipeline.argtypes = [vp, vp, C.c_int, i64, i64, C.c_int, C.POINTER(PipelineParams)]
     lib.phet_fisher.argtypes = [vp, i64]
     lib.phet_o_minmax.argtypes = [vp, C.POINTER(dbl)]
     lib.phet_bin.argtypes = [vp, vp, i32, vp]
@@ -185,6 +194,35 @@ class Context:
         else:
             _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_DEVICE, None, None, seed, _ptr(tf),
                                        _ptr(tl), n_last))
+
+    def run_pipeline(self, X, N, G, dtype, params: Step1Params, m, table_full, table_last, n_last,
+                     g_range=None, s_range=None, g3_range=None, normalize=NORM_ZSCORE, storage=None,
+                     perm_ctrl=None, perm_case=None, seed=0, is_device=False, block_genes=0):
+        """Stage 0 + Step 1 + Step 3 over gene blocks.  X: C-contiguous host ndarray (N, G) or, with
+        is_device=True, a raw device pointer (int)."""
+        pp = PipelineParams()
+        pp.normalize = normalize
+        pp.storage = dtype if storage is None else storage
+        pp.g_begin, pp.g_end = g_range if g_range is not None else (0, G)
+        pp.s_begin, pp.s_end = s_range if s_range is not None else (0, self.S)
+        pp.g3_begin, pp.g3_end = g3_range if g3_range is not None else (pp.g_begin, pp.g_end)
+        pp.step1 = params
+        pp.m = m
+        tf = np.ascontiguousarray(table_full, dtype=np.float64)
+        tl = np.ascontiguousarray(table_last, dtype=np.float64)
+        pp.table_full, pp.table_last, pp.n_last = tf.ctypes.data, tl.ctypes.data, n_last
+        keep = [tf, tl]
+        if perm_ctrl is not None:
+            pc = np.ascontiguousarray(perm_ctrl, dtype=np.uint32)
+            pk = np.ascontiguousarray(perm_case, dtype=np.uint32)
+            keep += [pc, pk]
+            pp.perm_mode, pp.perm_ctrl, pp.perm_case = PERM_HOST, pc.ctypes.data, pk.ctypes.data
+        else:
+            pp.perm_mode, pp.seed = PERM_DEVICE, seed
+        pp.block_genes = block_genes
+        ptr = C.c_void_p(X) if is_device else _ptr(X)
+        _check(self.lib.phet_run_pipeline(self.h, ptr, 1 if is_device else 0, N, G, dtype, C.byref(pp)))
+        self.N, self.G = N, G
 
     def fisher(self, S_total):
         _check(self.lib.phet_fisher(self.h, S_total))

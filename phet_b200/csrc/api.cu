@@ -44,11 +44,15 @@ __global__ void k_remap_idx(int32_t *__restrict__ idx, int64_t n, const int32_t 
     }
 }
 
-int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate) {
+int launch_step1(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t s_begin, int64_t s_end,
+                 const phet_step1_params *prm, int accumulate) {
     Step1Args a;
     a.xg = c->xg.p;
     a.n_pad = c->n_pad;
     a.G = c->G;
+    a.xg_g0 = c->xg_g0;
+    a.g_begin = g_begin;
+    a.g_end = g_end;
     a.idx = c->idx.p;
     a.m = c->m;
     a.s_begin = s_begin;
@@ -60,10 +64,13 @@ int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_p
     a.dbg_ld = s_end - s_begin;
     if (prm->capture_debug) {
         const size_t need = (size_t)c->G * (size_t)(s_end - s_begin);
+        const bool fresh = c->dbgP.n < need || c->S_local != s_end - s_begin;
         if (int e = c->dbgP.alloc(need)) return e;
         if (int e = c->dbgD.alloc(need)) return e;
-        PHET_CUDA(cudaMemsetAsync(c->dbgP.p, 0, need * sizeof(double), c->stream));
-        PHET_CUDA(cudaMemsetAsync(c->dbgD.p, 0, need * sizeof(double), c->stream));
+        if (fresh) {
+            PHET_CUDA(cudaMemsetAsync(c->dbgP.p, 0, need * sizeof(double), c->stream));
+            PHET_CUDA(cudaMemsetAsync(c->dbgD.p, 0, need * sizeof(double), c->stream));
+        }
         a.dbgP = c->dbgP.p;
         a.dbgD = c->dbgD.p;
         c->S_local = s_end - s_begin;
@@ -74,8 +81,11 @@ int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_p
     a.ln_beta = prm->ln_beta;
     a.p_flush = prm->p_flush_below;
     a.accumulate = accumulate;
-    if (s_end <= s_begin) {
-        if (!accumulate) PHET_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double) * 2 * c->G, c->stream));
+    if (s_end <= s_begin || g_end <= g_begin) {
+        if (!accumulate && g_end > g_begin) {
+            PHET_CUDA(cudaMemsetAsync(c->acc.p + g_begin, 0, sizeof(double) * (g_end - g_begin), c->stream));
+            PHET_CUDA(cudaMemsetAsync(c->acc.p + c->G + g_begin, 0, sizeof(double) * (g_end - g_begin), c->stream));
+        }
         return 0;
     }
     return c->storage == PHET_F32 ? run_step1_f32(c, a) : run_step1_f64(c, a);
@@ -87,6 +97,7 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.xg = c->xg.p;
     a.n_pad = c->n_pad;
     a.G = c->G;
+    a.xg_g0 = c->xg_g0;
     a.n0 = c->n0;
     a.n1 = c->n1;
     a.min_c = c->n0 < c->n1 ? c->n0 : c->n1;
@@ -193,6 +204,13 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->edges.release();
     c->weights.release();
     c->counts.release();
+    c->stage[0].release();
+    c->stage[1].release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return PHET_OK;
@@ -234,26 +252,27 @@ int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const in
     return PHET_OK;
 }
 
-int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype, int normalize,
-                     int storage) {
-    PHET_REQUIRE(c != nullptr, "ctx is NULL");
-    PHET_REQUIRE(X != nullptr, "X is NULL");
-    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called before phet_load_matrix");
+// Allocate the per-fit device buffers for genes [g_begin, g_end) of an N x G problem.
+static int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int normalize, int storage, int64_t g_begin,
+                          int64_t g_end) {
+    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called before loading the matrix");
     PHET_REQUIRE(N == c->n0 + c->n1, "N does not match the class sizes");
     PHET_REQUIRE(G >= 1, "G must be >= 1");
     PHET_REQUIRE(dtype == PHET_F32 || dtype == PHET_F64, "dtype must be PHET_F32 or PHET_F64");
     PHET_REQUIRE(storage == PHET_F32 || storage == PHET_F64, "storage must be PHET_F32 or PHET_F64");
     PHET_REQUIRE(normalize == PHET_NORM_NONE || normalize == PHET_NORM_ZSCORE, "normalize must be none or zscore");
     PHET_REQUIRE(N < (int64_t)1 << 31, "N too large");
+    PHET_REQUIRE(0 <= g_begin && g_begin <= g_end && g_end <= G, "gene range outside [0, G]");
     PHET_CUDA(cudaSetDevice(c->device));
-    const size_t e_in = dtype == PHET_F32 ? 4 : 8;
     const size_t e_st = storage == PHET_F32 ? 4 : 8;
     c->N = N;
     c->G = G;
     c->storage = storage;
     const int64_t per16 = 16 / (int64_t)e_st;
     c->n_pad = (N + per16 - 1) / per16 * per16;
-    if (int e = c->xg.alloc((size_t)G * (size_t)c->n_pad * e_st)) return e;
+    c->xg_g0 = g_begin;
+    c->xg_rows = g_end - g_begin;
+    if (int e = c->xg.alloc((size_t)(c->xg_rows > 0 ? c->xg_rows : 1) * (size_t)c->n_pad * e_st)) return e;
     if (int e = c->mean.alloc((size_t)G)) return e;
     if (int e = c->sd.alloc((size_t)G)) return e;
     if (int e = c->acc.alloc((size_t)2 * G)) return e;
@@ -263,6 +282,19 @@ int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64
     if (int e = c->fw.alloc((size_t)G)) return e;
     if (int e = c->scores.alloc((size_t)G)) return e;
     if (int e = c->bins.alloc((size_t)G)) return e;
+    PHET_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double) * 2 * G, c->stream));
+    PHET_CUDA(cudaMemsetAsync(c->o.p, 0, sizeof(double) * G, c->stream));
+    PHET_CUDA(cudaMemsetAsync(c->mean.p, 0, sizeof(double) * G, c->stream));
+    PHET_CUDA(cudaMemsetAsync(c->sd.p, 0, sizeof(double) * G, c->stream));
+    return PHET_OK;
+}
+
+int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype, int normalize,
+                     int storage) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(X != nullptr, "X is NULL");
+    if (int e = prepare_matrix(c, N, G, dtype, normalize, storage, 0, G)) return e;
+    const size_t e_in = dtype == PHET_F32 ? 4 : 8;
     const void *Xdev = X;
     if (!is_device) {
         const size_t bytes = (size_t)N * (size_t)G * e_in;
@@ -270,9 +302,7 @@ int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64
         PHET_CUDA(cudaMemcpyAsync(c->xraw.p, X, bytes, cudaMemcpyHostToDevice, c->stream));
         Xdev = c->xraw.p;
     }
-    if (int e = launch_normalize(c, Xdev, dtype, normalize)) return e;
-    PHET_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double) * 2 * G, c->stream));
-    PHET_CUDA(cudaMemsetAsync(c->o.p, 0, sizeof(double) * G, c->stream));
+    if (int e = launch_normalize(c, Xdev, G, 0, G, dtype, normalize)) return e;
     if (!is_device) {
         PHET_CUDA(cudaStreamSynchronize(c->stream));
         c->xraw.release();  // the normalised gene-major copy is all later steps need
@@ -314,19 +344,15 @@ int phet_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_par
     PHET_REQUIRE(q.j_lo >= 0 && q.k_lo < c->m && q.j_hi >= 0 && q.k_hi < c->m && q.j_lo <= q.k_lo && q.j_hi <= q.k_hi,
                  "quantile positions outside [0, m)");
     PHET_CUDA(cudaSetDevice(c->device));
-    return launch_step1(c, s_begin, s_end, prm, accumulate);
+    return launch_step1(c, c->xg_g0, c->xg_g0 + c->xg_rows, s_begin, s_end, prm, accumulate);
 }
 
-int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, const uint32_t *perm_ctrl,
-               const uint32_t *perm_case, uint64_t seed, const double *table_full, const double *table_last,
-               int64_t n_last) {
-    PHET_REQUIRE(c != nullptr, "ctx is NULL");
-    PHET_REQUIRE(c->matrix_set, "load the matrix before phet_step3");
-    PHET_REQUIRE(0 <= g_begin && g_begin <= g_end && g_end <= c->G, "gene range outside [0, G]");
+// Allocations, table/permutation uploads and zeroing shared by every Step-3 launch of a fit.
+static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,
+                         const double *table_full, const double *table_last, int64_t n_last) {
     PHET_REQUIRE(m >= 1 && m <= 512, "slice length m must be in [1, 512]");
     PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE, "bad perm_mode");
     PHET_REQUIRE(table_full && table_last, "KS tables are NULL");
-    PHET_CUDA(cudaSetDevice(c->device));
     const int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
     const int64_t n_slices = (min_c + m - 1) / m;
     PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");
@@ -347,10 +373,96 @@ int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_
         PHET_CUDA(cudaMemcpyAsync(c->perm0.p, perm_ctrl, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
         PHET_CUDA(cudaMemcpyAsync(c->perm1.p, perm_case, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
     }
+    return PHET_OK;
+}
+
+int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, const uint32_t *perm_ctrl,
+               const uint32_t *perm_case, uint64_t seed, const double *table_full, const double *table_last,
+               int64_t n_last) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(c->matrix_set, "load the matrix before phet_step3");
+    PHET_REQUIRE(c->xg_g0 <= g_begin && g_begin <= g_end && g_end <= c->xg_g0 + c->xg_rows,
+                 "gene range outside the resident genes");
+    PHET_CUDA(cudaSetDevice(c->device));
+    if (int e = step3_prepare(c, m, perm_mode, perm_ctrl, perm_case, table_full, table_last, n_last)) return e;
     int rc = launch_step3(c, g_begin, g_end, m, perm_mode, seed, n_last);
     if (rc) return rc;
     // tables and permutations are host buffers owned by the caller: finish the copies before returning
     PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+// Gene-block pipeline: H2D copy of block b+1 (copy stream, cudaMemcpy2DAsync out of the caller's
+// row-major matrix) overlaps normalise + Step 1 + Step 3 of block b (compute stream).
+int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype,
+                      const phet_pipeline_params *p) {
+    PHET_REQUIRE(c != nullptr && X != nullptr && p != nullptr, "NULL argument");
+    PHET_REQUIRE(c->idx_set, "phet_set_index_sets must precede phet_run_pipeline");
+    PHET_REQUIRE(p->m == c->m, "m does not match the uploaded index sets");
+    PHET_REQUIRE(0 <= p->s_begin && p->s_begin <= p->s_end && p->s_end <= c->S, "subsample range outside [0, S]");
+    PHET_REQUIRE(p->g_begin <= p->g3_begin && p->g3_begin <= p->g3_end && p->g3_end <= p->g_end,
+                 "Step-3 gene range must lie inside the loaded gene range");
+    if (int e = prepare_matrix(c, N, G, dtype, p->normalize, p->storage, p->g_begin, p->g_end)) return e;
+    const phet_quantile_pos &q = p->step1.q;
+    PHET_REQUIRE(q.j_lo >= 0 && q.k_lo < c->m && q.j_hi >= 0 && q.k_hi < c->m && q.j_lo <= q.k_lo && q.j_hi <= q.k_hi,
+                 "quantile positions outside [0, m)");
+    if (int e = step3_prepare(c, p->m, p->perm_mode, p->perm_ctrl, p->perm_case, p->table_full, p->table_last,
+                              p->n_last))
+        return e;
+    const size_t e_in = dtype == PHET_F32 ? 4 : 8;
+    const int64_t gcount = p->g_end - p->g_begin;
+    auto compute_block = [&](const void *Xblock, int64_t ldx, int64_t g0, int64_t gc) -> int {
+        if (int e = launch_normalize(c, Xblock, ldx, g0, gc, dtype, p->normalize)) return e;
+        return 0;
+    };
+    auto steps_block = [&](int64_t g0, int64_t gc) -> int {
+        if (int e = launch_step1(c, g0, g0 + gc, p->s_begin, p->s_end, &p->step1, 0)) return e;
+        const int64_t a = g0 > p->g3_begin ? g0 : p->g3_begin;
+        const int64_t b = (g0 + gc) < p->g3_end ? (g0 + gc) : p->g3_end;
+        if (b > a)
+            if (int e = launch_step3(c, a, b, p->m, p->perm_mode, p->seed, p->n_last)) return e;
+        return 0;
+    };
+    if (gcount > 0) {
+        if (is_device) {
+            const unsigned char *Xb = static_cast<const unsigned char *>(X) + (size_t)p->g_begin * e_in;
+            if (int e = compute_block(Xb, G, p->g_begin, gcount)) return e;
+            if (int e = steps_block(p->g_begin, gcount)) return e;
+        } else {
+            if (!c->copy_stream) PHET_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                if (!c->ev_copied[i]) PHET_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+                if (!c->ev_consumed[i]) PHET_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+            }
+            int64_t gb = p->block_genes;
+            if (gb <= 0) {  // ~128 MB per staging buffer, a multiple of the persistent grid (one CTA per SM)
+                gb = (int64_t)((128u << 20) / ((size_t)N * e_in));
+                gb = gb / c->num_sms * c->num_sms;
+                if (gb < c->num_sms) gb = c->num_sms;
+            }
+            if (gb > gcount) gb = gcount;
+            const size_t stage_bytes = (size_t)N * (size_t)gb * e_in;
+            if (int e = c->stage[0].alloc(stage_bytes)) return e;
+            if (gcount > gb)
+                if (int e = c->stage[1].alloc(stage_bytes)) return e;
+            int b = 0;
+            for (int64_t g0 = p->g_begin; g0 < p->g_end; g0 += gb, ++b) {
+                const int64_t gc = (g0 + gb <= p->g_end) ? gb : (p->g_end - g0);
+                const int buf = b & 1;
+                if (b >= 2) PHET_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[buf], 0));
+                PHET_CUDA(cudaMemcpy2DAsync(c->stage[buf].p, (size_t)gc * e_in,
+                                            static_cast<const unsigned char *>(X) + (size_t)g0 * e_in, (size_t)G * e_in,
+                                            (size_t)gc * e_in, (size_t)N, cudaMemcpyHostToDevice, c->copy_stream));
+                PHET_CUDA(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
+                PHET_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
+                if (int e = compute_block(c->stage[buf].p, gc, g0, gc)) return e;
+                PHET_CUDA(cudaEventRecord(c->ev_consumed[buf], c->stream));
+                if (int e = steps_block(g0, gc)) return e;
+            }
+        }
+    }
+    PHET_CUDA(cudaStreamSynchronize(c->stream));  // X, tables and permutations are caller-owned host memory
+    c->matrix_set = true;
     return PHET_OK;
 }
 
@@ -475,12 +587,28 @@ int phet_fit_host(phet_ctx *c, const void *X, int dtype, int64_t N, int64_t G, c
     PHET_REQUIRE(c != nullptr && prm != nullptr && scores_out != nullptr, "NULL argument");
     PHET_REQUIRE(prm->n_bins >= 2 && prm->weights, "need at least two feature weights");  // phet.py:122-123
     if (int e = phet_set_classes(c, ctrl_rows, n0, case_rows, n1)) return e;
-    if (int e = phet_load_matrix(c, X, 0, N, G, dtype, prm->normalize, prm->storage)) return e;
     if (int e = phet_set_index_sets(c, idx, S, prm->m)) return e;
-    if (int e = phet_step1(c, 0, S, &prm->step1, 0)) return e;
-    if (int e = phet_step3(c, 0, G, prm->m, prm->perm_mode, perm_ctrl, perm_case, prm->seed, prm->table_full,
-                           prm->table_last, prm->n_last))
-        return e;
+    phet_pipeline_params pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.normalize = prm->normalize;
+    pp.storage = prm->storage;
+    pp.g_begin = 0;
+    pp.g_end = G;
+    pp.s_begin = 0;
+    pp.s_end = S;
+    pp.g3_begin = 0;
+    pp.g3_end = G;
+    pp.step1 = prm->step1;
+    pp.m = prm->m;
+    pp.perm_mode = prm->perm_mode;
+    pp.seed = prm->seed;
+    pp.perm_ctrl = perm_ctrl;
+    pp.perm_case = perm_case;
+    pp.table_full = prm->table_full;
+    pp.table_last = prm->table_last;
+    pp.n_last = prm->n_last;
+    pp.block_genes = 0;
+    if (int e = phet_run_pipeline(c, X, 0, N, G, dtype, &pp)) return e;
     if (int e = phet_fisher(c, S)) return e;
     double mm[2];
     if (int e = phet_o_minmax(c, mm)) return e;

@@ -62,10 +62,14 @@ struct phet_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // H2D staging for the pipelined host path
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    phet::DevBuf<unsigned char> stage[2];
     int64_t launches = 0;
 
     // problem
     int64_t N = 0, G = 0, n_pad = 0;   // cells, genes, padded row length of the gene-major copy
+    int64_t xg_g0 = 0, xg_rows = 0;    // genes [xg_g0, xg_g0 + xg_rows) are resident in xg
     int64_t n0 = 0, n1 = 0;            // class sizes
     int storage = PHET_F32;
     bool classes_set = false, matrix_set = false, idx_set = false;
@@ -99,8 +103,10 @@ struct phet_ctx {
 namespace phet {
 
 // kernels' host launchers (defined in the .cu files)
-int launch_normalize(phet_ctx *c, const void *Xdev, int dtype, int normalize);
-int launch_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate);
+int launch_normalize(phet_ctx *c, const void *Xblock, int64_t ldx, int64_t g0, int64_t gcount, int dtype,
+                     int normalize);
+int launch_step1(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t s_begin, int64_t s_end,
+                 const phet_step1_params *prm, int accumulate);
 int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, uint64_t seed,
                  int64_t n_last);
 int launch_fisher(phet_ctx *c, int64_t S_total);

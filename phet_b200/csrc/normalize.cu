@@ -16,7 +16,7 @@ constexpr int kRowsPerBlock = 8;
 // fp64 accumulation; the shift removes the cancellation of the one-pass variance formula.
 template <typename Tin>
 __global__ void __launch_bounds__(kTile *kRowsPerBlock)
-    k_colstats_partial(const Tin *__restrict__ X, int64_t N, int64_t G, int64_t rows_per_chunk,
+    k_colstats_partial(const Tin *__restrict__ X, int64_t ldx, int64_t N, int64_t G, int64_t rows_per_chunk,
                        double *__restrict__ part) {
     __shared__ double sm_s[kRowsPerBlock][kTile + 1];
     __shared__ double sm_q[kRowsPerBlock][kTile + 1];
@@ -29,17 +29,17 @@ __global__ void __launch_bounds__(kTile *kRowsPerBlock)
         const double K = (double)X[g];
         int64_t r = r0 + ty;
         for (; r + 3 * kRowsPerBlock < r1; r += 4 * kRowsPerBlock) {
-            const double d0 = (double)X[r * G + g] - K;
-            const double d1 = (double)X[(r + kRowsPerBlock) * G + g] - K;
-            const double d2 = (double)X[(r + 2 * kRowsPerBlock) * G + g] - K;
-            const double d3 = (double)X[(r + 3 * kRowsPerBlock) * G + g] - K;
+            const double d0 = (double)X[r * ldx + g] - K;
+            const double d1 = (double)X[(r + kRowsPerBlock) * ldx + g] - K;
+            const double d2 = (double)X[(r + 2 * kRowsPerBlock) * ldx + g] - K;
+            const double d3 = (double)X[(r + 3 * kRowsPerBlock) * ldx + g] - K;
             s += d0; q += d0 * d0;
             s += d1; q += d1 * d1;
             s += d2; q += d2 * d2;
             s += d3; q += d3 * d3;
         }
         for (; r < r1; r += kRowsPerBlock) {
-            const double d = (double)X[r * G + g] - K;
+            const double d = (double)X[r * ldx + g] - K;
             s += d;
             q += d * d;
         }
@@ -80,7 +80,7 @@ __global__ void k_colstats_final(const Tin *__restrict__ X, int64_t N, int64_t G
 
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(kTile *kRowsPerBlock)
-    k_normalize_transpose(const Tin *__restrict__ X, int64_t N, int64_t G, int64_t n_pad,
+    k_normalize_transpose(const Tin *__restrict__ X, int64_t ldx, int64_t N, int64_t G, int64_t n_pad,
                           const int32_t *__restrict__ rows_grouped, const double *__restrict__ mean,
                           const double *__restrict__ sd, int normalize, Tout *__restrict__ xg) {
     __shared__ Tout tile[kTile][kTile + 1];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kTile *kRowsPerBlock)
             double z = 0.0;
             if (q < N && g < G) {
                 const int64_t row = rows_grouped[q];
-                const double x = (double)X[row * G + g];
+                const double x = (double)X[row * ldx + g];
                 z = normalize ? (x - mu) / sg : x;
                 if (!isfinite(z)) z = 0.0;  // nan_to_num(nan=0, posinf=0, neginf=0), phet.py:299
             }
@@ -116,9 +116,12 @@ __global__ void __launch_bounds__(kTile *kRowsPerBlock)
     }
 }
 
+// X points at the first gene of the block; ldx = row pitch of X in elements; the block covers
+// genes [g0, g0 + gcount) and is written to rows (g0 - xg_g0 ...) of the gene-major buffer.
 template <typename Tin>
-static int run_normalize(phet_ctx *c, const Tin *X, int normalize) {
-    const int64_t N = c->N, G = c->G;
+static int run_normalize(phet_ctx *c, const Tin *X, int64_t ldx, int64_t g0, int64_t gcount, int normalize) {
+    const int64_t N = c->N, G = gcount;
+    double *mean = c->mean.p + g0, *sd = c->sd.p + g0;
     int chunks = 1;
     if (normalize) {
         const int64_t gx = (G + kTile - 1) / kTile;
@@ -132,28 +135,31 @@ static int run_normalize(phet_ctx *c, const Tin *X, int normalize) {
         if (int e = c->colpart.alloc((size_t)chunks * 2 * G)) return e;
         dim3 blk(kTile, kRowsPerBlock);
         dim3 grd((unsigned)gx, (unsigned)chunks);
-        k_colstats_partial<Tin><<<grd, blk, 0, c->stream>>>(X, N, G, rows_per_chunk, c->colpart.p);
+        k_colstats_partial<Tin><<<grd, blk, 0, c->stream>>>(X, ldx, N, G, rows_per_chunk, c->colpart.p);
         c->launches++;
-        k_colstats_final<Tin><<<(unsigned)((G + 255) / 256), 256, 0, c->stream>>>(X, N, G, chunks, c->colpart.p,
-                                                                                  c->mean.p, c->sd.p);
+        k_colstats_final<Tin><<<(unsigned)((G + 255) / 256), 256, 0, c->stream>>>(X, N, G, chunks, c->colpart.p, mean,
+                                                                                  sd);
         c->launches++;
     }
     dim3 blk(kTile, kRowsPerBlock);
     dim3 grd((unsigned)((G + kTile - 1) / kTile), (unsigned)((c->n_pad + kTile - 1) / kTile));
+    const size_t e_st = c->storage == PHET_F32 ? 4 : 8;
+    unsigned char *out = c->xg.p + (size_t)(g0 - c->xg_g0) * (size_t)c->n_pad * e_st;
     if (c->storage == PHET_F32)
-        k_normalize_transpose<Tin, float><<<grd, blk, 0, c->stream>>>(X, N, G, c->n_pad, c->rows_grouped.p, c->mean.p,
-                                                                     c->sd.p, normalize, (float *)c->xg.p);
+        k_normalize_transpose<Tin, float><<<grd, blk, 0, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean,
+                                                                     sd, normalize, (float *)out);
     else
-        k_normalize_transpose<Tin, double><<<grd, blk, 0, c->stream>>>(X, N, G, c->n_pad, c->rows_grouped.p, c->mean.p,
-                                                                      c->sd.p, normalize, (double *)c->xg.p);
+        k_normalize_transpose<Tin, double><<<grd, blk, 0, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean,
+                                                                      sd, normalize, (double *)out);
     c->launches++;
     PHET_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_normalize(phet_ctx *c, const void *Xdev, int dtype, int normalize) {
-    if (dtype == PHET_F32) return run_normalize<float>(c, (const float *)Xdev, normalize);
-    return run_normalize<double>(c, (const double *)Xdev, normalize);
+int launch_normalize(phet_ctx *c, const void *Xblock, int64_t ldx, int64_t g0, int64_t gcount, int dtype,
+                     int normalize) {
+    if (dtype == PHET_F32) return run_normalize<float>(c, (const float *)Xblock, ldx, g0, gcount, normalize);
+    return run_normalize<double>(c, (const double *)Xblock, ldx, g0, gcount, normalize);
 }
 
 }  // namespace phet

@@ -26,8 +26,9 @@ namespace phet {
 constexpr int kThreads1 = 512;
 
 struct Step1Args {
-    const void *xg;
-    int64_t n_pad, G;
+    const void *xg;      // row of gene g starts at xg + (g - xg_g0) * n_pad elements
+    int64_t n_pad, G, xg_g0;
+    int64_t g_begin, g_end;
     const int32_t *idx;  // [S][2][m] grouped positions
     int64_t m;
     int64_t s_begin, s_end;
@@ -78,15 +79,15 @@ __global__ void __launch_bounds__(kThreads1, 1) k_step1(const Step1Args a) {
     const double n = (double)m;
     const double inv_pair = 1.0 / n + 1.0 / n;
 
-    for (int64_t g = blockIdx.x; g < a.G; g += gridDim.x) {
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
         const T *gene;
         if (STAGED) {
-            if (tid == 0) stage_row(gene_s, static_cast<const T *>(a.xg) + g * a.n_pad, gene_bytes, bar);
+            if (tid == 0) stage_row(gene_s, static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad, gene_bytes, bar);
             mbar_wait(bar, phase);
             phase ^= 1u;
             gene = gene_s;
         } else {
-            gene = static_cast<const T *>(a.xg) + g * a.n_pad;
+            gene = static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad;
         }
 
         double facc = 0.0;  // per lane: sum of Fisher terms this lane evaluated
@@ -219,7 +220,8 @@ static int launch_step1_inst(phet_ctx *c, const Step1Args &args, size_t smem) {
         return PHET_ERR_UNSUPPORTED;
     }
     int64_t grid = (int64_t)per_sm * c->num_sms;
-    if (grid > args.G) grid = args.G;
+    if (grid > args.g_end - args.g_begin) grid = args.g_end - args.g_begin;
+    if (grid < 1) return 0;
     c->step1_geom[0] = (int32_t)grid;
     c->step1_geom[1] = kThreads1;
     c->step1_geom[2] = (int32_t)smem;

