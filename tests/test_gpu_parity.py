@@ -144,3 +144,33 @@ def test_errors_are_loud():
     with pytest.raises(_capi.PhetError):
         ctx.load_matrix(np.zeros((4, 3)))  # classes not set
     ctx.close()
+
+
+def test_cli_main_srbct(tmp_path):
+    """python -m phet_b200.main --methods phet on SRBCT (BASELINE config 0 shape) against the
+    reference pipeline's output (float32 load, seed 12345, gamma selection, descending sort)."""
+    import os
+    from scipy.io import mmwrite
+    from scipy.sparse import coo_matrix
+    from conftest import GOLDEN_DIR
+    from phet_b200.main import main
+    g = load_golden("srbct_full")
+    z = np.load(os.path.join(GOLDEN_DIR, "cli_srbct.npz"))
+    mmwrite(str(tmp_path / "srbct_matrix.mtx"), coo_matrix(g["X"].astype(np.float64)), precision=6)
+    with open(tmp_path / "srbct_classes.csv", "w") as fh:
+        fh.write("classes\n" + "\n".join(str(int(v)) for v in g["y"]) + "\n")
+    with open(tmp_path / "srbct_feature_names.csv", "w") as fh:
+        fh.write("features\n" + "\n".join(z["names"].tolist()) + "\n")
+    main(["--file-name", "srbct", "--dspath", str(tmp_path), "--rspath", str(tmp_path / "out"), "--methods", "phet",
+          "--num-subsamples", str(int(z["S"]))])
+    import pandas as pd
+    df = pd.read_csv(tmp_path / "out" / "srbct_phet_br_features.csv")
+    ref = z["sig_features"].tolist()
+    got = df["features"].to_list()
+    assert got[:10] == ref[:10]
+    jac = len(set(got) & set(ref)) / len(set(got) | set(ref))
+    assert jac >= 0.97, jac
+    ref_scores = dict(zip(ref, z["sig_scores"]))
+    common = [f for f in got if f in ref_scores]
+    assert np.allclose(df.set_index("features").loc[common, "score"].to_numpy(), [ref_scores[f] for f in common],
+                       rtol=1e-3)
