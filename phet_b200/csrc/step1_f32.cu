@@ -1,4 +1,4 @@
-#include "step1_impl.cuh"
+#include "step1h_impl.cuh"
 namespace phet {
-int run_step1_f32(phet_ctx *c, const Step1Args &a) { return run_step1_T<float>(c, a); }
+int run_step1_f32(phet_ctx *c, const Step1Args &a) { return run_step1_any<float>(c, a); }
 }  // namespace phet

@@ -1,4 +1,4 @@
-#include "step1_impl.cuh"
+#include "step1h_impl.cuh"
 namespace phet {
-int run_step1_f64(phet_ctx *c, const Step1Args &a) { return run_step1_T<double>(c, a); }
+int run_step1_f64(phet_ctx *c, const Step1Args &a) { return run_step1_any<double>(c, a); }
 }  // namespace phet

@@ -236,13 +236,7 @@ static int launch_step1_inst(phet_ctx *c, const Step1Args &args, size_t smem) {
 template <typename T, bool STAGED>
 static int dispatch_step1_E(phet_ctx *c, const Step1Args &args, size_t smem) {
     const int need = (int)((args.m + 31) / 32);
-    if (need <= 1) return launch_step1_inst<T, 1, STAGED>(c, args, smem);
-    if (need <= 2) return launch_step1_inst<T, 2, STAGED>(c, args, smem);
-    if (need <= 3) return launch_step1_inst<T, 3, STAGED>(c, args, smem);
-    if (need <= 4) return launch_step1_inst<T, 4, STAGED>(c, args, smem);
-    if (need <= 5) return launch_step1_inst<T, 5, STAGED>(c, args, smem);
-    if (need <= 6) return launch_step1_inst<T, 6, STAGED>(c, args, smem);
-    if (need <= 8) return launch_step1_inst<T, 8, STAGED>(c, args, smem);
+    // m <= 256 is served by the half-warp path (step1h_impl.cuh); this network covers 257..512
     if (need <= 10) return launch_step1_inst<T, 10, STAGED>(c, args, smem);
     if (need <= 12) return launch_step1_inst<T, 12, STAGED>(c, args, smem);
     if (need <= 16) return launch_step1_inst<T, 16, STAGED>(c, args, smem);

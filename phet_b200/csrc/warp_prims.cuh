@@ -166,4 +166,171 @@ __device__ __forceinline__ void stage_row(void *smem_dst, const void *gmem_src, 
     }
 }
 
+// =================================================================================================
+// Half-warp merge-split sorter (the fast path for m <= 256).
+//
+// Each half-warp (16 lanes) sorts its own 16*E values; the two groups of a unit (control, case)
+// are sorted at the same time by the two halves of one warp.  Every lane first sorts its E
+// values in registers (Batcher merge-exchange network, arbitrary E), then the 16 lanes run a
+// flip-form bitonic network of 10 stages whose "comparator" is a merge-split of two sorted
+// E-blocks: the lower lane keeps the E smallest of the 2E, the upper lane the E largest.
+//
+// To make that step branch- and predicate-free the blocks are kept in "x-space": a lane whose
+// role in the coming stage is "upper" stores the NEGATED block, ascending.  Then for both roles
+//     w[i] = min(x[i], -partner_x[i])          (one SHFL + one FMNMX per element, same index i)
+// is the kept half, and in both roles w is an increasing-then-decreasing sequence, so one
+// pruned half-cleaner network (virtual -inf pads in front) re-sorts it.  Changing role between
+// stages is x'[i] = -x[E-1-i], done arithmetically as alpha*x[i] + beta*x[E-1-i] with
+// (alpha, beta) in {(1,0),(0,-1)} on the otherwise idle FMA pipe.  Missing elements are +BIG
+// sentinels (finite, so 0*BIG == 0).  Versus the full-warp network this needs ~45 % of the
+// shuffles and ~70 % of the min/max instructions per unit.
+// =================================================================================================
+
+template <typename T> struct Big;
+template <> struct Big<float> {
+    static __host__ __device__ __forceinline__ float v() { return 3.402823466e+38f; }
+};
+template <> struct Big<double> {
+    static __host__ __device__ __forceinline__ double v() { return 1.7976931348623157e+308; }
+};
+
+template <typename T>
+__device__ __forceinline__ void cmpex(T &a, T &b) {
+    const T lo = tmin(a, b);
+    const T hi = tmax(a, b);
+    a = lo;
+    b = hi;
+}
+
+// Batcher's merge-exchange sort (Knuth 5.2.2 Algorithm M) as a compile-time network, any E.
+template <typename T, int E>
+__device__ __forceinline__ void local_sort_asc(T (&x)[E]) {
+#pragma unroll
+    for (int p = 1; p < E; p <<= 1) {
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1) {
+#pragma unroll
+            for (int j = k % p; j <= E - 1 - k; j += 2 * k) {
+#pragma unroll
+                for (int i = 0; i <= k - 1; ++i) {
+                    if (i <= E - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) cmpex(x[i + j], x[i + j + k]);
+                }
+            }
+        }
+    }
+}
+
+// Sort an increasing-then-decreasing block ascending: half-cleaner network on next_pow2(E)
+// positions with the E real values at the top and virtual -inf pads (no-op comparators) below.
+template <typename T, int E>
+__device__ __forceinline__ void bitonic_cleanup_asc(T (&w)[E]) {
+    constexpr int EP = next_pow2(E);
+    constexpr int OFF = EP - E;
+#pragma unroll
+    for (int d = EP / 2; d >= 1; d >>= 1) {
+#pragma unroll
+        for (int pos = OFF; pos < EP; ++pos) {
+            if ((pos & d) == 0) cmpex(w[pos - OFF], w[pos + d - OFF]);
+        }
+    }
+}
+
+// x'[i] = alpha*x[i] + beta*x[E-1-i]  ((1,0): unchanged; (0,-1): negate and reverse).
+template <typename T, int E>
+__device__ __forceinline__ void role_flip(T (&x)[E], const T alpha, const T beta) {
+    T y[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) y[i] = fma(beta, x[E - 1 - i], alpha * x[i]);
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = y[i];
+}
+
+// Per-lane role-change coefficients of the 11 transitions of the 16-lane network; only six are
+// distinct.  alpha = 1 keeps the block, alpha = 0 (beta = -1) negates and reverses it.
+template <typename T>
+struct HalfSortCoef {
+    T a_1, a_12, a_14, a_42, a_18, a_84;  // alpha for (init|final <-> bit1), (1<->2), (1->4), (4->2), (1->8), (8->4)
+    __device__ __forceinline__ explicit HalfSortCoef(int h) {
+        const int b1 = h & 1, b2 = (h >> 1) & 1, b4 = (h >> 2) & 1, b8 = (h >> 3) & 1;
+        a_1 = b1 ? T(0) : T(1);
+        a_12 = (b1 ^ b2) ? T(0) : T(1);
+        a_14 = (b1 ^ b4) ? T(0) : T(1);
+        a_42 = (b4 ^ b2) ? T(0) : T(1);
+        a_18 = (b1 ^ b8) ? T(0) : T(1);
+        a_84 = (b8 ^ b4) ? T(0) : T(1);
+    }
+};
+
+template <typename T, int E>
+__device__ __forceinline__ void merge_split_stage(T (&x)[E], const int mask) {
+    T w[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const T o = __shfl_xor_sync(kFull, x[i], mask);
+        w[i] = tmin(x[i], -o);
+    }
+    bitonic_cleanup_asc<T, E>(w);
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = w[i];
+}
+
+// In: E unsorted values per lane (pads = Big<T>::v()).  Out: ascending over the half-warp in
+// blocked layout, sorted position p = (lane & 15) * E + r.
+template <typename T, int E>
+__device__ __forceinline__ void halfwarp_sort_asc(T (&x)[E], const HalfSortCoef<T> &c) {
+    local_sort_asc<T, E>(x);
+#define PHET_STAGE(ALPHA, MASK)                 \
+    role_flip<T, E>(x, (ALPHA), (ALPHA)-T(1));  \
+    merge_split_stage<T, E>(x, (MASK));
+    PHET_STAGE(c.a_1, 1)     // k = 2 : flip  (role bit 1)
+    PHET_STAGE(c.a_12, 3)    // k = 4 : flip  (role bit 2)
+    PHET_STAGE(c.a_12, 1)    //         j = 1 (role bit 1)
+    PHET_STAGE(c.a_14, 7)    // k = 8 : flip  (role bit 4)
+    PHET_STAGE(c.a_42, 2)    //         j = 2
+    PHET_STAGE(c.a_12, 1)    //         j = 1
+    PHET_STAGE(c.a_18, 15)   // k = 16: flip  (role bit 8)
+    PHET_STAGE(c.a_84, 4)    //         j = 4
+    PHET_STAGE(c.a_42, 2)    //         j = 2
+    PHET_STAGE(c.a_12, 1)    //         j = 1
+#undef PHET_STAGE
+    role_flip<T, E>(x, c.a_1, c.a_1 - T(1));  // back to true values, ascending
+}
+
+// Value at sorted position p (uniform) of a half-warp-sorted blocked array: lane hp = p / E of
+// each half, register rp = p % E.  Both halves pick at once (shuffle width 16).
+// The register is chosen with a binary select tree on the bits of rp (E-1 SEL, log2 E predicates).
+template <typename T, int E>
+__device__ __forceinline__ T halfwarp_pick(const T (&x)[E], const int hp, const int rp) {
+    constexpr int EP = next_pow2(E);
+    T t[EP];
+#pragma unroll
+    for (int i = 0; i < EP; ++i) t[i] = x[i < E ? i : E - 1];
+#pragma unroll
+    for (int step = 1; step < EP; step <<= 1) {
+        const bool b = (rp & step) != 0;
+#pragma unroll
+        for (int i = 0; i + step < EP; i += 2 * step) t[i] = b ? t[i + step] : t[i];
+    }
+    return __shfl_sync(kFull, t[0], hp, 16);
+}
+
+// Explicit shared-window loads: one address add + LDS (the generic-pointer path re-derives the
+// shared window base for every access).
+__device__ __forceinline__ float lds_at(uint32_t base, int idx, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * (uint32_t)idx));
+    return v;
+}
+__device__ __forceinline__ double lds_at(uint32_t base, int idx, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 8u * (uint32_t)idx));
+    return v;
+}
+
+__device__ __forceinline__ double half_sum(double x) {
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+    return x;
+}
+
 }  // namespace phet
