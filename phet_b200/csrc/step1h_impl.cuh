@@ -5,6 +5,7 @@
 #pragma once
 
 #include "step1_impl.cuh"
+#include <cstdlib>
 
 namespace phet {
 
@@ -15,8 +16,8 @@ struct StaticValid {
     static constexpr int value = (E <= 10) ? (E - 1) : 10;
 };
 
-template <typename T, int E, bool STAGED>
-__global__ void __launch_bounds__(kThreads1, 1) k_step1h(const Step1Args a) {
+template <typename T, int E, bool STAGED, int THREADS = kThreads1>
+__global__ void __launch_bounds__(THREADS, 1) k_step1h(const Step1Args a) {
     constexpr int EV = StaticValid<E>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -32,6 +33,10 @@ __global__ void __launch_bounds__(kThreads1, 1) k_step1h(const Step1Args a) {
     const uint32_t gene_sa = smem_u32(gene_s);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + ((gene_bytes + 15) & ~(size_t)15));
     double *part = reinterpret_cast<double *>(bar + 2);
+    // per-warp scratch for the sorted blocks: the order statistics are read back from SMEM
+    // (4 broadcast LDS) instead of a register-select tree; the second half is skewed by one
+    // word so the two half-warps do not hit the same banks
+    T *sorted_s = reinterpret_cast<T *>(part + 2 * (THREADS / 32)) + (size_t)warp * (32 * E + 2) + grp * (16 * E + 1);
 
     if (STAGED) {
         if (tid == 0) {
@@ -45,9 +50,6 @@ __global__ void __launch_bounds__(kThreads1, 1) k_step1h(const Step1Args a) {
     const double inv_df = 1.0 / a.df;  // df == 0 (m == 1) -> inf -> NaN statistic, like the reference
     const double inv_pair = inv_n + inv_n;
     const HalfSortCoef<T> coef(h);
-    // sorted position p of a half-warp-sorted block lives in lane p / E, register p % E
-    const int jl_h = a.q.j_lo / E, jl_r = a.q.j_lo % E, kl_h = a.q.k_lo / E, kl_r = a.q.k_lo % E;
-    const int jh_h = a.q.j_hi / E, jh_r = a.q.j_hi % E, kh_h = a.q.k_hi / E, kh_r = a.q.k_hi % E;
     const double w_lo0 = 1.0 - a.q.g_lo, w_hi0 = 1.0 - a.q.g_hi;
 
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
@@ -112,10 +114,14 @@ __global__ void __launch_bounds__(kThreads1, 1) k_step1h(const Step1Args a) {
             const double stat = dmean * rsqrt(svar * inv_pair);   // 0 * inf = NaN and x * inf = +-inf like x / 0
 
             halfwarp_sort_asc<T, E>(x, coef);
-            const double y_jl = (double)halfwarp_pick<T, E>(x, jl_h, jl_r);
-            const double y_kl = (double)halfwarp_pick<T, E>(x, kl_h, kl_r);
-            const double y_jh = (double)halfwarp_pick<T, E>(x, jh_h, jh_r);
-            const double y_kh = (double)halfwarp_pick<T, E>(x, kh_h, kh_r);
+#pragma unroll
+            for (int r = 0; r < E; ++r) sorted_s[h * E + r] = x[r];  // blocked layout == ascending array
+            __syncwarp();
+            const double y_jl = (double)sorted_s[a.q.j_lo];
+            const double y_kl = (double)sorted_s[a.q.k_lo];
+            const double y_jh = (double)sorted_s[a.q.j_hi];
+            const double y_kh = (double)sorted_s[a.q.k_hi];
+            __syncwarp();
             const double q_lo = __dadd_rn(__dmul_rn(w_lo0, y_jl), __dmul_rn(a.q.g_lo, y_kl));
             const double q_hi = __dadd_rn(__dmul_rn(w_hi0, y_jh), __dmul_rn(a.q.g_hi, y_kh));
             const double iq = q_hi - q_lo;
@@ -174,12 +180,14 @@ __global__ void __launch_bounds__(kThreads1, 1) k_step1h(const Step1Args a) {
     }
 }
 
-template <typename T, int E, bool STAGED>
-static int launch_step1h_inst(phet_ctx *c, const Step1Args &args, size_t smem) {
-    auto kern = k_step1h<T, E, STAGED>;
+template <typename T, int E, bool STAGED, int THREADS = kThreads1>
+static int launch_step1h_inst(phet_ctx *c, const Step1Args &args, size_t smem_in) {
+    auto kern = k_step1h<T, E, STAGED, THREADS>;
+    const size_t smem = smem_in + (size_t)(THREADS - kThreads1) / 32 * 2 * sizeof(double) +
+                        (size_t)(THREADS / 32) * (32 * E + 2) * sizeof(T);
     PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads1, smem));
+    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
     if (per_sm < 1) {
         set_error("step1: kernel does not fit on an SM");
         return PHET_ERR_UNSUPPORTED;
@@ -188,11 +196,11 @@ static int launch_step1h_inst(phet_ctx *c, const Step1Args &args, size_t smem) {
     if (grid > args.g_end - args.g_begin) grid = args.g_end - args.g_begin;
     if (grid < 1) return 0;
     c->step1_geom[0] = (int32_t)grid;
-    c->step1_geom[1] = kThreads1;
+    c->step1_geom[1] = THREADS;
     c->step1_geom[2] = (int32_t)smem;
     c->step1_geom[3] = E;
     c->step1_geom[4] = (STAGED ? 1 : 0) | 2;  // bit 1: half-warp merge-split path
-    kern<<<(unsigned)grid, kThreads1, smem, c->stream>>>(args);
+    kern<<<(unsigned)grid, THREADS, smem, c->stream>>>(args);
     c->launches++;
     PHET_CUDA(cudaGetLastError());
     return 0;
@@ -210,7 +218,18 @@ static int dispatch_step1h_E(phet_ctx *c, const Step1Args &args, size_t smem) {
     if (need <= 7) return launch_step1h_inst<T, 7, STAGED>(c, args, smem);
     if (need <= 8) return launch_step1h_inst<T, 8, STAGED>(c, args, smem);
     if (need <= 9) return launch_step1h_inst<T, 9, STAGED>(c, args, smem);
-    if (need <= 10) return launch_step1h_inst<T, 10, STAGED>(c, args, smem);
+    if (need <= 10) {
+#ifdef PHET_EXPERIMENT_THREADS
+        if (sizeof(T) == 4 && STAGED) {
+            const char *e = getenv("PHET_STEP1_THREADS");
+            const int t = e ? atoi(e) : 512;
+            if (t == 640) return launch_step1h_inst<T, 10, STAGED, 640>(c, args, smem);
+            if (t == 768) return launch_step1h_inst<T, 10, STAGED, 768>(c, args, smem);
+            if (t == 1024) return launch_step1h_inst<T, 10, STAGED, 1024>(c, args, smem);
+        }
+#endif
+        return launch_step1h_inst<T, 10, STAGED>(c, args, smem);
+    }
     if (need <= 12) return launch_step1h_inst<T, 12, STAGED>(c, args, smem);
     return launch_step1h_inst<T, 16, STAGED>(c, args, smem);
 }
@@ -220,7 +239,10 @@ template <typename T>
 static int run_step1_any(phet_ctx *c, const Step1Args &args) {
     const size_t tail = 16 + 16 + (size_t)(kThreads1 / 32) * 2 * sizeof(double);
     const size_t staged = (((size_t)c->n_pad * sizeof(T) + 15) & ~(size_t)15) + tail;
-    const bool fits = staged <= (size_t)kMaxSmemOptin;
+    const int need = (int)((args.m + 15) / 16);
+    const int e_pick = need <= 10 ? need : (need <= 12 ? 12 : 16);
+    const size_t scratch = (size_t)(kThreads1 / 32) * (32 * e_pick + 2) * sizeof(T);
+    const bool fits = staged + scratch <= (size_t)kMaxSmemOptin;
     if (args.m <= 256) {
         if (fits) return dispatch_step1h_E<T, true>(c, args, staged);
         return dispatch_step1h_E<T, false>(c, args, tail);

@@ -1,4 +1,4 @@
-#include "step3_impl.cuh"
+#include "step3h_impl.cuh"
 namespace phet {
-int run_step3_f64(phet_ctx *c, const Step3Args &a) { return run_step3_T<double>(c, a); }
+int run_step3_f64(phet_ctx *c, const Step3Args &a) { return run_step3_any<double>(c, a); }
 }  // namespace phet

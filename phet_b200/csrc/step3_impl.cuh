@@ -244,13 +244,7 @@ static int launch_step3_E(phet_ctx *c, const Step3Args &args) {
 template <typename T>
 static int run_step3_T(phet_ctx *c, const Step3Args &args) {
     const int need = (int)((args.m + 31) / 32);
-    if (need <= 1) return launch_step3_E<T, 1>(c, args);
-    if (need <= 2) return launch_step3_E<T, 2>(c, args);
-    if (need <= 3) return launch_step3_E<T, 3>(c, args);
-    if (need <= 4) return launch_step3_E<T, 4>(c, args);
-    if (need <= 5) return launch_step3_E<T, 5>(c, args);
-    if (need <= 6) return launch_step3_E<T, 6>(c, args);
-    if (need <= 8) return launch_step3_E<T, 8>(c, args);
+    // slices of length <= 256 are served by the half-warp path (step3h_impl.cuh)
     if (need <= 10) return launch_step3_E<T, 10>(c, args);
     if (need <= 12) return launch_step3_E<T, 12>(c, args);
     if (need <= 16) return launch_step3_E<T, 16>(c, args);

@@ -298,22 +298,6 @@ __device__ __forceinline__ void halfwarp_sort_asc(T (&x)[E], const HalfSortCoef<
 
 // Value at sorted position p (uniform) of a half-warp-sorted blocked array: lane hp = p / E of
 // each half, register rp = p % E.  Both halves pick at once (shuffle width 16).
-// The register is chosen with a binary select tree on the bits of rp (E-1 SEL, log2 E predicates).
-template <typename T, int E>
-__device__ __forceinline__ T halfwarp_pick(const T (&x)[E], const int hp, const int rp) {
-    constexpr int EP = next_pow2(E);
-    T t[EP];
-#pragma unroll
-    for (int i = 0; i < EP; ++i) t[i] = x[i < E ? i : E - 1];
-#pragma unroll
-    for (int step = 1; step < EP; step <<= 1) {
-        const bool b = (rp & step) != 0;
-#pragma unroll
-        for (int i = 0; i + step < EP; i += 2 * step) t[i] = b ? t[i + step] : t[i];
-    }
-    return __shfl_sync(kFull, t[0], hp, 16);
-}
-
 // Explicit shared-window loads: one address add + LDS (the generic-pointer path re-derives the
 // shared window base for every access).
 __device__ __forceinline__ float lds_at(uint32_t base, int idx, float) {
