@@ -55,7 +55,8 @@ typedef enum {
     PHET_BUF_SCORES = 8,   /* double[G]: final scores (phet.py:510-516)                                      */
     PHET_BUF_XG = 9,       /* normalised gene-major matrix, storage dtype, [G][n_pad], class-grouped cells   */
     PHET_BUF_MEAN = 10,    /* double[G] column mean  */
-    PHET_BUF_STD = 11      /* double[G] column population sd */
+    PHET_BUF_STD = 11,     /* double[G] column population sd */
+    PHET_BUF_ROWS = 12     /* int32[N]: original row held at each position of a gene-major row (the layout) */
 } phet_buffer;
 
 /* Order-statistic positions and lerp weights of the two percentiles, computed on the host
@@ -112,8 +113,10 @@ int phet_step1(phet_ctx *ctx, int64_t s_begin, int64_t s_end, const phet_step1_p
  * cut slices of length m over [0, min(n0,n1)), two-sample KS per slice, o = min p.
  * perm_mode HOST: perm_ctrl / perm_case are host uint32 [G][min_c] class-local positions (the
  *   first min_c entries of np.random.permutation(n_class), phet.py:486-487) for ALL genes.
- * perm_mode DEVICE: permutations come from a keyed bijection on the device (seed); the
- *   pointers are ignored.  Same distribution, not the reference's MT19937 stream.
+ * perm_mode DEVICE: the cells of each class sit in a fixed pseudo-random order in HBM (see
+ *   PHET_BUF_ROWS) and gene g walks them with its own affine bijection t -> (a_g t + b_g) mod n
+ *   keyed by `seed`; the pointers are ignored.  Pseudo-random slice membership per gene, not
+ *   the reference's MT19937 stream.
  * table_full[0..m] / table_last[0..n_last]: exact two-sided p-value of ks_2samp for equal
  * sizes as a function of the integer statistic h (host-built, scipy semantics). */
 int phet_step3(phet_ctx *ctx, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode,

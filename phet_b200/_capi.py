@@ -18,7 +18,7 @@ NORM_NONE, NORM_ZSCORE = 0, 1
 TEST_T, TEST_Z = 0, 1
 PERM_HOST, PERM_DEVICE = 0, 1
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
- BUF_STD) = range(12)
+ BUF_STD, BUF_ROWS) = range(13)
 
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",

@@ -44,6 +44,39 @@ __global__ void k_remap_idx(int32_t *__restrict__ idx, int64_t n, const int32_t 
     }
 }
 
+// host-mode permutations: class-local index (ascending row order) -> class-relative grouped position
+__global__ void k_remap_perm(uint32_t *__restrict__ perm, int64_t n, const int32_t *__restrict__ cls_pos, uint32_t ncls,
+                             int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = perm[i];
+    if (t >= ncls) {
+        *bad = 1;
+        perm[i] = 0;
+    } else {
+        perm[i] = (uint32_t)cls_pos[t];
+    }
+}
+
+static uint64_t gcd_u64(uint64_t a, uint64_t b) {
+    while (b) {
+        const uint64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// kCoprimeCount multipliers in [1, n) coprime to n (n == 1: all ones).  Mirrored in phet_b200/perm.py.
+static void coprime_list(uint32_t n, uint32_t *out) {
+    uint64_t j = 0;
+    for (int k = 0; k < kCoprimeCount;) {
+        const uint64_t z = splitmix64(0xC0FFEE123456789ull ^ ((uint64_t)n * 0x9E3779B97F4A7C15ull) ^ (j++));
+        const uint32_t cand = n > 2 ? (uint32_t)(1 + z % (uint64_t)(n - 1)) : 1u;
+        if (gcd_u64(cand, n) == 1) out[k++] = cand;
+    }
+}
+
 int launch_step1(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t s_begin, int64_t s_end,
                  const phet_step1_params *prm, int accumulate) {
     Step1Args a;
@@ -109,6 +142,8 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.perm_mode = perm_mode;
     a.perm0 = c->perm0.p;
     a.perm1 = c->perm1.p;
+    a.coprime0 = c->coprime.p;
+    a.coprime1 = c->coprime.p ? c->coprime.p + kCoprimeCount : nullptr;
     a.seed = seed;
     a.tab_full = c->tab_full.p;
     a.tab_last = c->tab_last.p;
@@ -195,6 +230,8 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->perm1.release();
     c->tab_full.release();
     c->tab_last.release();
+    c->cls_pos.release();
+    c->coprime.release();
     c->f.release();
     c->r.release();
     c->fw.release();
@@ -229,20 +266,39 @@ int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const in
     PHET_REQUIRE(n0 >= 1 && n1 >= 1, "both classes need at least one cell");
     PHET_CUDA(cudaSetDevice(c->device));
     const int64_t N = n0 + n1;
-    std::vector<int32_t> grouped((size_t)N), pos((size_t)N, -1);
-    for (int64_t i = 0; i < N; ++i) {
-        const int32_t r = i < n0 ? ctrl_rows[i] : case_rows[i - n0];
-        if (r < 0 || r >= N || pos[(size_t)r] != -1) {
-            set_error("invalid: class row lists must partition [0, n0+n1)");
-            return PHET_ERR_INVALID;
+    // Layout: the cells of each class are placed in a fixed pseudo-random order (seeded
+    // Fisher-Yates), so that cheap per-gene affine walks over positions (Step 3, device mode)
+    // visit pseudo-random cells.  order[q] = class-local index held at class-relative position q.
+    std::vector<int32_t> grouped((size_t)N), pos((size_t)N, -1), cls_pos((size_t)N);
+    for (int cls = 0; cls < 2; ++cls) {
+        const int64_t n = cls ? n1 : n0, off = cls ? n0 : 0;
+        const int32_t *rows = cls ? case_rows : ctrl_rows;
+        std::vector<int32_t> order((size_t)n);
+        for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int32_t)i;
+        uint64_t st = 0x5EEDC0DEull + (uint64_t)cls;
+        for (int64_t i = n - 1; i > 0; --i) {
+            st = splitmix64(st);
+            const int64_t j = (int64_t)(st % (uint64_t)(i + 1));
+            std::swap(order[(size_t)i], order[(size_t)j]);
         }
-        grouped[(size_t)i] = r;
-        pos[(size_t)r] = (int32_t)i;
+        for (int64_t q = 0; q < n; ++q) {
+            const int32_t t = order[(size_t)q];
+            const int32_t r = rows[t];
+            if (r < 0 || r >= N || pos[(size_t)r] != -1) {
+                set_error("invalid: class row lists must partition [0, n0+n1)");
+                return PHET_ERR_INVALID;
+            }
+            grouped[(size_t)(off + q)] = r;
+            pos[(size_t)r] = (int32_t)(off + q);
+            cls_pos[(size_t)(off + t)] = (int32_t)q;
+        }
     }
     if (int e = c->rows_grouped.alloc((size_t)N)) return e;
     if (int e = c->pos_of_row.alloc((size_t)N)) return e;
+    if (int e = c->cls_pos.alloc((size_t)N)) return e;
     PHET_CUDA(cudaMemcpyAsync(c->rows_grouped.p, grouped.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
     PHET_CUDA(cudaMemcpyAsync(c->pos_of_row.p, pos.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(cudaMemcpyAsync(c->cls_pos.p, cls_pos.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
     PHET_CUDA(cudaStreamSynchronize(c->stream));
     c->n0 = n0;
     c->n1 = n1;
@@ -372,6 +428,29 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
         if (int e = c->perm1.alloc(n)) return e;
         PHET_CUDA(cudaMemcpyAsync(c->perm0.p, perm_ctrl, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
         PHET_CUDA(cudaMemcpyAsync(c->perm1.p, perm_case, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        int *bad = reinterpret_cast<int *>(c->scalars.p + 12);
+        PHET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        k_remap_perm<<<blocks, 256, 0, c->stream>>>(c->perm0.p, (int64_t)n, c->cls_pos.p, (uint32_t)c->n0, bad);
+        k_remap_perm<<<blocks, 256, 0, c->stream>>>(c->perm1.p, (int64_t)n, c->cls_pos.p + c->n0, (uint32_t)c->n1, bad);
+        c->launches += 2;
+        PHET_CUDA(cudaGetLastError());
+        int hbad = 0;
+        PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PHET_CUDA(cudaStreamSynchronize(c->stream));
+        PHET_REQUIRE(hbad == 0, "host permutations contain a position outside its class");
+    } else {
+        if (c->coprime.p == nullptr || c->coprime_n0 != c->n0 || c->coprime_n1 != c->n1) {
+            std::vector<uint32_t> cp(2 * kCoprimeCount);
+            coprime_list((uint32_t)c->n0, cp.data());
+            coprime_list((uint32_t)c->n1, cp.data() + kCoprimeCount);
+            if (int e = c->coprime.alloc(2 * kCoprimeCount)) return e;
+            PHET_CUDA(cudaMemcpyAsync(c->coprime.p, cp.data(), sizeof(uint32_t) * cp.size(), cudaMemcpyHostToDevice,
+                                      c->stream));
+            PHET_CUDA(cudaStreamSynchronize(c->stream));  // cp is a stack-lifetime host buffer
+            c->coprime_n0 = c->n0;
+            c->coprime_n1 = c->n1;
+        }
     }
     return PHET_OK;
 }
@@ -519,6 +598,7 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_XG: *p = c->xg.p; *bytes = c->G * c->n_pad * (c->storage == PHET_F32 ? 4 : 8); break;
         case PHET_BUF_MEAN: *p = c->mean.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
+        case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;
         default:
             set_error("invalid: unknown buffer id");
             return PHET_ERR_INVALID;
@@ -633,7 +713,14 @@ int phet_fit_host(phet_ctx *c, const void *X, int dtype, int64_t N, int64_t G, c
 double phet_host_p_two_sided_t(double t, double df, double ln_beta) { return p_two_sided_t(t, df, ln_beta); }
 double phet_host_p_two_sided_z(double z) { return p_two_sided_z(z); }
 uint32_t phet_host_perm_apply(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t l, uint32_t i) {
-    return perm_apply(make_perm_key(seed, gene, cls, l), i);
+    static thread_local uint32_t cached_n = 0;
+    static thread_local std::vector<uint32_t> cp;
+    if (cached_n != l) {
+        cp.resize(kCoprimeCount);
+        coprime_list(l, cp.data());
+        cached_n = l;
+    }
+    return affine_at(make_affine(seed, gene, cls, l, cp.data()), i);
 }
 
 }  // extern "C"

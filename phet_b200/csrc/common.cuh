@@ -10,7 +10,8 @@
 namespace phet {
 
 constexpr int kWarp = 32;
-constexpr int kMaxSmemOptin = 232448;  // 227 KB: per-CTA dynamic shared memory limit on sm_100
+constexpr int kMaxSmemOptin = 232448;
+constexpr int kCoprimeCount = 1024;    // per class; power of two  // 227 KB: per-CTA dynamic shared memory limit on sm_100
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -76,10 +77,13 @@ struct phet_ctx {
     int64_t S = 0, m = 0;              // uploaded index sets
     int64_t S_local = 0;               // subsamples covered by the debug buffers
     int64_t n_slices = 0;
+    int64_t coprime_n0 = -1, coprime_n1 = -1;
     int32_t n_bins = 0;
 
     phet::DevBuf<int32_t> rows_grouped;  // [N]: source row of grouped position q (controls, then cases)
     phet::DevBuf<int32_t> pos_of_row;    // [N]: grouped position of original row
+    phet::DevBuf<int32_t> cls_pos;       // [N]: class-relative grouped position of class-local index t (ctrl, then case)
+    phet::DevBuf<uint32_t> coprime;      // [2][kCoprimeCount]: affine multipliers coprime to n0 / n1
     phet::DevBuf<unsigned char> xg;      // [G][n_pad] storage dtype
     phet::DevBuf<double> mean, sd;       // [G]
     phet::DevBuf<double> colpart;        // scratch for column statistics

@@ -27,7 +27,8 @@ struct Step3Args {
     int64_t n0, n1, min_c, m, n_slices, n_last;
     int64_t g_begin, g_end;
     int perm_mode;
-    const uint32_t *perm0, *perm1;  // [G][min_c] class-local positions (host mode)
+    const uint32_t *perm0, *perm1;  // [G][min_c] class-relative grouped positions (host mode, remapped at upload)
+    const uint32_t *coprime0, *coprime1;  // [kCoprimeCount] multipliers coprime to n0 / n1 (device mode)
     uint64_t seed;
     const double *tab_full, *tab_last;
     double *o;
@@ -41,53 +42,33 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-// Keyed bijection of [0, l): four rounds of (add key, multiply by an odd constant, xor-shift)
-// on the enclosing power-of-two domain, cycle-walked back into range.  Mirrored in
-// phet_b200/perm.py (host) so device-mode permutations can be replayed on the CPU.
-struct PermKey {
-    uint32_t k0, k1, k2, k3, mask, s1, s2, l;
+// Device-mode permutation.  phet_set_classes lays the cells of each class out in a fixed
+// pseudo-random order (a seeded Fisher-Yates shuffle on the host), so a per-gene AFFINE bijection
+// of the class-relative positions,  t -> (a_g * t + b_g) mod n  with gcd(a_g, n) = 1, already
+// yields a pseudo-random slice membership per gene, and consecutive t cost one add and one
+// unsigned min.  a_g is drawn from a host-built list of multipliers coprime to n, b_g from a hash.
+// Mirrored on the host in phet_b200/perm.py.
+struct AffinePerm {
+    uint32_t a, b, n;
 };
 
-__host__ __device__ __forceinline__ PermKey make_perm_key(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t l) {
-    PermKey k;
-    const uint64_t a = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (2 * gene + cls + 1)));
-    const uint64_t b = splitmix64(a);
-    k.k0 = (uint32_t)a;
-    k.k1 = (uint32_t)(a >> 32);
-    k.k2 = (uint32_t)b;
-    k.k3 = (uint32_t)(b >> 32);
-    uint32_t w = l > 0 ? l - 1 : 0;
-    w |= w >> 1;
-    w |= w >> 2;
-    w |= w >> 4;
-    w |= w >> 8;
-    w |= w >> 16;
-    k.mask = w;
-    int bits = 0;
-    while ((w >> bits) & 1u) ++bits;
-    k.s1 = bits / 2 > 0 ? bits / 2 : 1;
-    k.s2 = bits / 3 > 0 ? bits / 3 : 1;
-    k.l = l;
-    return k;
+__host__ __device__ __forceinline__ AffinePerm make_affine(uint64_t seed, uint64_t gene, uint32_t cls, uint32_t n,
+                                                           const uint32_t *coprime) {
+    const uint64_t z = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (2 * gene + cls + 1)));
+    AffinePerm p;
+    p.a = coprime[(uint32_t)z & (uint32_t)(kCoprimeCount - 1)];
+    p.b = (uint32_t)(z >> 32) % n;
+    p.n = n;
+    return p;
 }
 
-__host__ __device__ __forceinline__ uint32_t perm_apply(const PermKey &k, uint32_t i) {
-    uint32_t x = i;
-    do {
-        x = (x + k.k0) & k.mask;
-        x = (x * 0x9E3779B1u) & k.mask;
-        x ^= x >> k.s1;
-        x = (x + k.k1) & k.mask;
-        x = (x * 0x85EBCA77u) & k.mask;
-        x ^= x >> k.s2;
-        x = (x + k.k2) & k.mask;
-        x = (x * 0xC2B2AE3Du) & k.mask;
-        x ^= x >> k.s1;
-        x = (x + k.k3) & k.mask;
-        x = (x * 0x27D4EB2Fu) & k.mask;
-        x ^= x >> k.s2;
-    } while (x >= k.l);
-    return x;
+__host__ __device__ __forceinline__ uint32_t affine_at(const AffinePerm &p, uint64_t t) {
+    return (uint32_t)(((uint64_t)p.a * t + p.b) % p.n);
+}
+
+__device__ __forceinline__ uint32_t add_mod(uint32_t x, uint32_t step, uint32_t n) {  // x, step < n < 2^31
+    x += step;
+    return min(x, x - n);
 }
 
 template <typename T, int E, bool STAGED>
@@ -127,10 +108,10 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
         } else {
             gene = static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad;
         }
-        PermKey key0, key1;
+        AffinePerm ap0 = {1u, 0u, 1u}, ap1 = {1u, 0u, 1u};
         if (a.perm_mode == PHET_PERM_DEVICE) {
-            key0 = make_perm_key(a.seed, (uint64_t)g, 0u, (uint32_t)a.n0);
-            key1 = make_perm_key(a.seed, (uint64_t)g, 1u, (uint32_t)a.n1);
+            ap0 = make_affine(a.seed, (uint64_t)g, 0u, (uint32_t)a.n0, a.coprime0);
+            ap1 = make_affine(a.seed, (uint64_t)g, 1u, (uint32_t)a.n1, a.coprime1);
         }
         double omin = CUDART_INF;
         for (int64_t k = warp; k < a.n_slices; k += nw) {
@@ -143,8 +124,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
                 if (p < n) {
                     uint32_t qa, qb;
                     if (a.perm_mode == PHET_PERM_DEVICE) {
-                        qa = perm_apply(key0, (uint32_t)(start + p));
-                        qb = perm_apply(key1, (uint32_t)(start + p));
+                        qa = affine_at(ap0, (uint64_t)(start + p));
+                        qb = affine_at(ap1, (uint64_t)(start + p));
                     } else {
                         qa = __ldg(a.perm0 + g * a.min_c + start + p);
                         qb = __ldg(a.perm1 + g * a.min_c + start + p);

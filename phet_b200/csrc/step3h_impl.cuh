@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
     unsigned phase = 0;
     const HalfSortCoef<T> coef(h);
     const int base = grp ? (int)a.n0 : 0;  // class-grouped row: controls first, then cases
+    const uint32_t ncls = (uint32_t)(grp ? a.n1 : a.n0);
     constexpr int RA = (16 * E + 31) / 32;  // a-values per lane in the evaluation phase
 
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
@@ -52,28 +53,34 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
         } else {
             gene = static_cast<const T *>(a.xg) + (g - a.xg_g0) * a.n_pad;
         }
-        PermKey key;
         const uint32_t *perm = nullptr;
-        if (a.perm_mode == PHET_PERM_DEVICE)
-            key = make_perm_key(a.seed, (uint64_t)g, (uint32_t)grp, (uint32_t)(grp ? a.n1 : a.n0));
-        else
+        uint32_t x0 = 0, step_r = 0, step_s = 0;   // device mode: affine walk over class-relative positions
+        if (a.perm_mode == PHET_PERM_DEVICE) {
+            const AffinePerm ap = make_affine(a.seed, (uint64_t)g, (uint32_t)grp, ncls, grp ? a.coprime1 : a.coprime0);
+            x0 = affine_at(ap, (uint64_t)warp * (uint64_t)a.m + (uint64_t)h);          // first slice of this warp
+            step_r = (uint32_t)((16ull * ap.a) % ncls);                                  // next register: t += 16
+            step_s = (uint32_t)(((uint64_t)ap.a * ((uint64_t)nw * (uint64_t)a.m)) % ncls);  // next slice of this warp
+        } else {
             perm = (grp ? a.perm1 : a.perm0) + g * a.min_c;
+        }
         double omin = CUDART_INF;
         for (int64_t k = warp; k < a.n_slices; k += nw) {
             const int n = (k == a.n_slices - 1) ? (int)a.n_last : (int)a.m;
             const int64_t start = k * a.m;
             T x[E];
+            uint32_t xr = x0;
 #pragma unroll
             for (int r = 0; r < E; ++r) {
                 const int p = h + 16 * r;
                 if (p < n) {
-                    const uint32_t q = (a.perm_mode == PHET_PERM_DEVICE) ? perm_apply(key, (uint32_t)(start + p))
-                                                                         : __ldg(perm + start + p);
+                    const uint32_t q = (a.perm_mode == PHET_PERM_DEVICE) ? xr : __ldg(perm + start + p);
                     x[r] = STAGED ? lds_at(gene_sa, base + (int)q, T(0)) : __ldg(gene + base + q);
                 } else {
                     x[r] = Big<T>::v();
                 }
+                xr = add_mod(xr, step_r, ncls);
             }
+            x0 = add_mod(x0, step_s, ncls);
             halfwarp_sort_asc<T, E>(x, coef);
 #pragma unroll
             for (int r = 0; r < E; ++r) mine[h * E + r] = x[r];
@@ -86,17 +93,24 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
                     const T v = sa[p];
                     const bool first = (p == 0) || (sa[p - 1] != v);
                     const bool last = (p == n - 1) || (sa[p + 1] != v);
-                    int lo1 = 0, len1 = n, lo2 = 0, len2 = n;  // lower / upper bound of v in b, searched together
-                    while ((len1 | len2) > 0) {
-                        const int h1 = len1 >> 1, h2 = len2 >> 1;
-                        const T x1 = sb[min(lo1 + h1, n - 1)];
-                        const T x2 = sb[min(lo2 + h2, n - 1)];
-                        const bool g1 = (len1 > 0) && (x1 < v);
-                        const bool g2 = (len2 > 0) && (x2 <= v);
-                        lo1 = g1 ? lo1 + h1 + 1 : lo1;
-                        len1 = g1 ? len1 - h1 - 1 : h1;
-                        lo2 = g2 ? lo2 + h2 + 1 : lo2;
-                        len2 = g2 ? len2 - h2 - 1 : h2;
+                    // lower bound of v in b: #{b < v}.  b is padded with +BIG up to 16*E entries, so probing
+                    // with power-of-two steps never needs a bounds check (pads compare >= v).
+                    int lo1 = 0;
+#pragma unroll
+                    for (int step = next_pow2(16 * E + 1) / 2; step >= 1; step >>= 1) {
+                        const int mid = lo1 + step;
+                        if (mid <= 16 * E && sb[mid - 1] < v) lo1 = mid;
+                    }
+                    // upper bound #{b <= v}: equals the lower bound unless b holds v itself (ties)
+                    int lo2 = lo1;
+                    if (lo1 < n && sb[lo1] == v) {
+                        lo2 = 0;
+#pragma unroll
+                        for (int step = next_pow2(16 * E + 1) / 2; step >= 1; step >>= 1) {
+                            const int mid = lo2 + step;
+                            if (mid <= 16 * E && sb[mid - 1] <= v) lo2 = mid;
+                        }
+                        lo2 = min(lo2, n);
                     }
                     if (last) hmax = max(hmax, abs(p + 1 - lo2));
                     if (first) hmax = max(hmax, abs(p - lo1));

@@ -1,10 +1,19 @@
-"""Host replica of the device's keyed permutation (csrc/step3_impl.cuh ``perm_apply``), so that
-``perm_mode='device'`` runs can be replayed on the CPU (tests feed these to the oracle)."""
+"""Host replica of the device-mode Step-3 permutation (csrc/step3_impl.cuh ``make_affine`` /
+``affine_at`` and csrc/api.cu ``coprime_list``), so ``permutation="device"`` runs can be replayed
+on the CPU: tests feed the replayed permutations to the oracle.
+
+Device mode = a fixed pseudo-random layout of each class's cells in HBM (chosen by
+``phet_set_classes``; readable as ``PHET_BUF_ROWS``) composed with a per-gene affine bijection of
+the class-relative positions, ``t -> (a_g * t + b_g) mod n``.
+"""
 from __future__ import annotations
+
+import math
 
 import numpy as np
 
 _M64 = (1 << 64) - 1
+COPRIME_COUNT = 1024
 
 
 def _splitmix64(z: int) -> int:
@@ -14,28 +23,44 @@ def _splitmix64(z: int) -> int:
     return z ^ (z >> 31)
 
 
-def device_permutation(seed: int, gene: int, cls: int, l: int, count: int | None = None) -> np.ndarray:
-    """First ``count`` entries of the class-local permutation the device uses for (gene, cls)."""
-    count = l if count is None else count
-    a = _splitmix64((seed ^ ((0xD1B54A32D192ED03 * (2 * gene + cls + 1)) & _M64)) & _M64)
-    b = _splitmix64(a)
-    k = [a & 0xFFFFFFFF, a >> 32, b & 0xFFFFFFFF, b >> 32]
-    w = max(l - 1, 0)
-    for s in (1, 2, 4, 8, 16):
-        w |= w >> s
-    bits = int(w).bit_length()
-    s1 = max(bits // 2, 1)
-    s2 = max(bits // 3, 1)
-    mul = [0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F]
-    sh = [s1, s2, s1, s2]
-    x = np.arange(count, dtype=np.uint64)
-    todo = np.ones(count, dtype=bool)
-    while todo.any():
-        v = x[todo]
-        for r in range(4):
-            v = (v + np.uint64(k[r])) & np.uint64(w)
-            v = (v * np.uint64(mul[r])) & np.uint64(w)
-            v ^= v >> np.uint64(sh[r])
-        x[todo] = v
-        todo[todo] = v >= l
-    return x.astype(np.uint32)
+_COPRIME_CACHE: dict[int, list[int]] = {}
+
+
+def coprime_list(n: int) -> list[int]:
+    if n in _COPRIME_CACHE:
+        return _COPRIME_CACHE[n]
+    out, j = [], 0
+    while len(out) < COPRIME_COUNT:
+        z = _splitmix64((0xC0FFEE123456789 ^ ((n * 0x9E3779B97F4A7C15) & _M64) ^ j) & _M64)
+        j += 1
+        cand = 1 + z % (n - 1) if n > 2 else 1
+        if math.gcd(cand, n) == 1:
+            out.append(cand)
+    _COPRIME_CACHE[n] = out
+    return out
+
+
+def affine_params(seed: int, gene: int, cls: int, n: int):
+    z = _splitmix64((seed ^ ((0xD1B54A32D192ED03 * (2 * gene + cls + 1)) & _M64)) & _M64)
+    a = coprime_list(n)[z & (COPRIME_COUNT - 1)]
+    b = (z >> 32) % n
+    return a, b
+
+
+def device_positions(seed: int, gene: int, cls: int, n: int, count: int | None = None) -> np.ndarray:
+    """Class-relative grouped positions visited by gene ``gene`` for t = 0..count-1."""
+    count = n if count is None else count
+    a, b = affine_params(seed, gene, cls, n)
+    t = np.arange(count, dtype=np.uint64)
+    return ((np.uint64(a) * t + np.uint64(b)) % np.uint64(n)).astype(np.int64)
+
+
+def device_permutation(seed: int, gene: int, cls: int, class_rows: np.ndarray, rows_grouped: np.ndarray,
+                       offset: int, count: int | None = None) -> np.ndarray:
+    """The permutation in the reference's terms: for t = 0..count-1 the CLASS-LOCAL index (into the
+    ascending ``class_rows``) of the cell gene ``gene`` puts at permuted position t.
+    ``rows_grouped`` is the device layout (PHET_BUF_ROWS); ``offset`` = 0 for controls, n0 for cases."""
+    n = len(class_rows)
+    pos = device_positions(seed, gene, cls, n, count)
+    rows = np.asarray(rows_grouped)[offset + pos]
+    return np.searchsorted(class_rows, rows)

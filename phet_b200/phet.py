@@ -264,6 +264,8 @@ class PHet:
         self.launches_ = ctx.launch_count()
         self.step1_geometry_ = ctx.step1_geometry()
         if self.capture:
+            self.layout_rows_ = ctx.read(_capi.BUF_ROWS, np.int32, (N,))
+            self.device_seed_ = seed
             self.fsum_, self.rsum_ = ctx.read(_capi.BUF_ACC, np.float64, (2, G))
             self.f_ = ctx.read(_capi.BUF_F, np.float64, (G,))
             self.r_ = ctx.read(_capi.BUF_R, np.float64, (G,))

@@ -61,13 +61,15 @@ def test_device_pvalue_routines_on_host_match_scipy():
 
 def test_device_permutation_replica_is_a_permutation_and_matches_c():
     from phet_b200 import _capi
-    from phet_b200.perm import device_permutation
+    from phet_b200.perm import device_positions
     lib = _capi.load_library()
-    for l in (1, 2, 3, 29, 54, 252, 5000):
-        pm = device_permutation(12345, 7, 1, l)
+    for l in (1, 2, 3, 29, 54, 252, 5000, 25000):
+        pm = device_positions(12345, 7, 1, l)
         assert sorted(pm.tolist()) == list(range(l))
         dv = [lib.phet_host_perm_apply(12345, 7, 1, l, i) for i in range(min(l, 100))]
         assert dv == pm[:len(dv)].tolist()
+    # different genes walk the class differently
+    assert not np.array_equal(device_positions(1, 0, 0, 5000, 64), device_positions(1, 1, 0, 5000, 64))
 
 
 def test_constructor_mirrors_reference():

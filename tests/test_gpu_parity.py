@@ -85,10 +85,14 @@ def test_device_permutation_mode_against_oracle(name):
     np.random.seed(int(g["seed"]))
     idx_i, idx_j, _ = po.draw_index_sets(y, int(g["m"]), g["params"]["num_subsamples"])
     seed = int(np.random.randint(0, 2 ** 31 - 1))
-    n0, n1 = int((y == 0).sum()), int((y == 1).sum())
+    assert seed == est.device_seed_
+    ctrl, case = np.where(y == 0)[0], np.where(y == 1)[0]
     G = X.shape[1]
-    perm_i = np.stack([device_permutation(seed, gi, 0, n0) for gi in range(G)]).astype(np.int64)
-    perm_j = np.stack([device_permutation(seed, gi, 1, n1) for gi in range(G)]).astype(np.int64)
+    rows = est.layout_rows_
+    assert sorted(rows[:len(ctrl)].tolist()) == ctrl.tolist() and sorted(rows[len(ctrl):].tolist()) == case.tolist()
+    perm_i = np.stack([device_permutation(seed, gi, 0, ctrl, rows, 0) for gi in range(G)]).astype(np.int64)
+    perm_j = np.stack([device_permutation(seed, gi, 1, case, rows, len(ctrl)) for gi in range(G)]).astype(np.int64)
+    assert all(sorted(p.tolist()) == list(range(len(ctrl))) for p in perm_i[:5])
     res = po.fit_predict_oracle(X, y, index_sets=(idx_i, idx_j), perms=(perm_i, perm_j), **g["params"])
     assert np.array_equal(est.H_, res.H)
     assert np.array_equal(est.bin_counts_, res.bin_counts)
