@@ -3,10 +3,12 @@
 #include "common.cuh"
 #include "pvalue.cuh"
 #include "step1_impl.cuh"
+#include "step1p_impl.cuh"
 #include "step3_impl.cuh"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -56,6 +58,19 @@ __global__ void k_remap_perm(uint32_t *__restrict__ perm, int64_t n, const int32
     } else {
         perm[i] = (uint32_t)cls_pos[t];
     }
+}
+
+// [S][2][m] grouped positions -> [2][nblk][m][32] class-local positions, 16 bits each: the 32
+// subsamples of a block are adjacent, so a warp of k_step1p reads 64 contiguous bytes per element
+__global__ void k_build_idxT(const int32_t *__restrict__ idx, int64_t S, int64_t m, int64_t n0, int64_t nblk,
+                             uint16_t *__restrict__ idxT) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk][m][32]
+    if (o >= 2 * nblk * m * 32) return;
+    const int64_t sl = o & 31;
+    const int64_t j = (o >> 5) % m;
+    const int64_t cb = (o >> 5) / m;  // c * nblk + blk
+    const int64_t c = cb / nblk, s = (cb % nblk) * 32 + sl;
+    idxT[o] = (s < S) ? (uint16_t)(idx[(s * 2 + c) * m + j] - (c ? n0 : 0)) : (uint16_t)0;
 }
 
 static uint64_t gcd_u64(uint64_t a, uint64_t b) {
@@ -190,6 +205,7 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
     }
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
+    if (const char *impl = getenv("PHET_STEP1_IMPL")) c->step1_impl = (strcmp(impl, "warp") == 0) ? 1 : 0;
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;
@@ -221,6 +237,9 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->colpart.release();
     c->xraw.release();
     c->idx.release();
+    c->idxT.release();
+    c->win.release();
+    c->pair_scratch.release();
     c->acc.release();
     c->dbgP.release();
     c->dbgD.release();
@@ -385,6 +404,16 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
     PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PHET_CUDA(cudaStreamSynchronize(c->stream));
     PHET_REQUIRE(hbad == 0, "index sets contain a row number outside [0, N)");
+    c->idxT_ok = false;
+    if (c->n0 <= 65536 && c->n1 <= 65536 && m <= 255) {  // transposed 16-bit copy for the pair-per-thread Step 1
+        const int64_t nblk = (S + 31) / 32;
+        const int64_t nT = 2 * nblk * m * 32;
+        if (int e = c->idxT.alloc((size_t)nT)) return e;
+        k_build_idxT<<<(unsigned)((nT + 255) / 256), 256, 0, c->stream>>>(c->idx.p, S, m, c->n0, nblk, c->idxT.p);
+        c->launches++;
+        PHET_CUDA(cudaGetLastError());
+        c->idxT_ok = true;
+    }
     c->S = S;
     c->m = m;
     c->idx_set = true;

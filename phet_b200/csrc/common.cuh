@@ -89,6 +89,11 @@ struct phet_ctx {
     phet::DevBuf<double> colpart;        // scratch for column statistics
     phet::DevBuf<unsigned char> xraw;    // staging copy of a host matrix
     phet::DevBuf<int32_t> idx;           // [S][2][m] grouped positions
+    phet::DevBuf<uint16_t> idxT;         // [2][m][S] class-local positions (pair-per-thread Step 1)
+    bool idxT_ok = false;
+    int step1_impl = 0;                  // 0 auto, 1 warp sorters only (env PHET_STEP1_IMPL=warp)
+    phet::DevBuf<float2> win;            // [G][2] bucket map (scale, offset) per (gene, class)
+    phet::DevBuf<double> pair_scratch;   // [grid][3][slots] control-class results awaiting the case sample
     phet::DevBuf<double> acc;            // [2][G]
     phet::DevBuf<double> dbgP, dbgD;     // [G][S_local]
     phet::DevBuf<double> o;              // [G]

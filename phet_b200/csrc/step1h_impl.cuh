@@ -5,6 +5,7 @@
 #pragma once
 
 #include "step1_impl.cuh"
+#include "step1p_impl.cuh"
 #include <cstdlib>
 
 namespace phet {
@@ -234,9 +235,14 @@ static int dispatch_step1h_E(phet_ctx *c, const Step1Args &args, size_t smem) {
     return launch_step1h_inst<T, 16, STAGED>(c, args, smem);
 }
 
-// m <= 256: half-warp path; larger m: full-warp network (step1_impl.cuh, E = 10, 12, 16 per lane).
+// Pair-per-thread bucket selection when it applies (step1p_impl.cuh); else m <= 256: half-warp
+// sorter; larger m: full-warp network (step1_impl.cuh, E = 10, 12, 16 per lane).
 template <typename T>
 static int run_step1_any(phet_ctx *c, const Step1Args &args) {
+    {
+        const int rc = run_step1_pair<T>(c, args);
+        if (rc != 1) return rc;
+    }
     const size_t tail = 16 + 16 + (size_t)(kThreads1 / 32) * 2 * sizeof(double);
     const size_t staged = (((size_t)c->n_pad * sizeof(T) + 15) & ~(size_t)15) + tail;
     const int need = (int)((args.m + 15) / 16);

@@ -1,0 +1,597 @@
+// Step 1, pair-per-thread path (m <= 255, both classes <= 65536 cells, one class vector fits in
+// shared memory).  Same contract as k_step1 (step1_impl.cuh); replaces phet.py:397-432 + 435,
+// 449-451.
+//
+// Why a third formulation: the warp-cooperative sorters are bound by the ALU pipe (FMNMX at one
+// warp-instruction per two cycles per scheduler, ~470 of them per unit) although only four order
+// statistics per sample are needed.  Here ONE THREAD owns one (subsample, class) sample and finds
+// those order statistics by EXACT bucket selection instead of sorting:
+//
+//   pass A   gather the m values from the class vector staged in SMEM; accumulate sum / sum of
+//            squares in fp64; map every value through a per-(gene, class) monotone affine map
+//            to one of 127 buckets (FFMA + saturating F2I: no ALU-pipe work); count the bucket in
+//            a thread-private byte histogram (bank = lane: conflict-free) and remember the bucket
+//            id in a thread-private list.
+//   locate   walk the 127 counters once: for each of the four sorted positions (y[j], y[j+1] of
+//            the low and the high percentile) the bucket that holds it and its rank inside.
+//   select   per percentile, the few elements (typically 2-5) of the bucket range that holds
+//            its two positions are re-gathered (SIMD-in-register range test over the bucket
+//            list, 4 ids per word), sorted with a tiny register network, and the two ranks read
+//            off.  Because the map is monotone, bucket order is value order: the result is the
+//            exact order statistic, bit-identical to a full sort.
+//   rescue   a range with more than 16 (fp64: 8) elements is either one big tie group (all
+//            equal: answer known) or is handed to a warp-cooperative full sort of that sample.
+//
+// The bucket map comes from k_windows: it brackets the two percentiles of the class with a
+// margin of z = 4 standard errors of a subsample quantile (estimated on 512 cells of the class;
+// the class-grouped layout is a fixed pseudo-random shuffle, so the first cells are a sample), so
+// the interior buckets see ~1 element each.  A bad map can only cost time, never exactness.
+//
+// One class vector is resident at a time (class-at-a-time staging with 1-D TMA bulk copies):
+// control results (sum, sum of squares, IQR) of a thread's subsamples are parked in a
+// thread-private global scratch line and combined when the same thread finishes the case sample.
+#pragma once
+
+#include "step1_impl.cuh"
+
+namespace phet {
+
+constexpr int kPairMaxThreads = 512;
+constexpr int kPairHistBytes = 128;   // per thread: 127 one-byte counters (+1 unused)
+constexpr float kPairTopBucket = 126.5f;
+constexpr uint32_t kPairPadId = 127u; // bucket-list filler of the last chunk (never a target)
+constexpr int kWinSample = 512;       // cells per class sampled by k_windows
+
+struct Step1PairArgs {
+    Step1Args a;
+    const uint16_t *idxT;  // [2][nblk][m][32]: class-local grouped position of element j of subsample 32*blk + lane
+    int64_t nblk;          // ceil(S_total / 32)
+    const float2 *win;     // [G][2]: (scale, offset) of the bucket map of (gene, class)
+    double *scratch;       // [grid][3][slots]
+    int32_t slots;         // rounds * blockDim.x
+    int32_t rounds;
+    int32_t bl_stride;     // bytes per thread of the bucket list (16 * odd)
+    int32_t vals_bytes;    // SMEM bytes reserved for one class vector (multiple of 128)
+    int64_t n0, n1;
+};
+
+// ---- explicit shared-window accesses (the scratch areas are addressed by byte arithmetic) ----
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
+}
+__device__ __forceinline__ void sts_val(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+}
+__device__ __forceinline__ void sts_val(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+}
+__device__ __forceinline__ float lds_val(uint32_t addr, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_val(uint32_t addr, double) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Monotone non-decreasing in v (fma with scale >= 0, min, truncation and saturation all are);
+// below the window and NaN -> 0, above -> 126.
+__device__ __forceinline__ uint32_t pair_bucket(float v, float scale, float off) {
+    const float t = fminf(fmaf(v, scale, off), kPairTopBucket);
+    uint32_t b;
+    asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(b) : "f"(t));
+    return b;
+}
+
+// Bytes of w are bucket ids < 128.  Bit 7 of byte i of the result is set iff lo <= byte i <= hi
+// (lo4 = lo * 0x01010101, hi4h = hi * 0x01010101 | 0x80808080; no borrow crosses a byte).
+__device__ __forceinline__ uint32_t range_flags(uint32_t w, uint32_t lo4, uint32_t hi4h) {
+    return ((w | 0x80808080u) - lo4) & (hi4h - w) & 0x80808080u;
+}
+
+// vals[pos] with the address formed by one IMAD (FMA pipe) instead of LEA (ALU pipe)
+__device__ __forceinline__ float lds_pos(uint32_t base, uint32_t pos, float) {
+    float v;
+    asm volatile("{\n.reg .u32 a;\nmad.lo.u32 a, %1, 4, %2;\nld.shared.f32 %0, [a];\n}" : "=f"(v) : "r"(pos), "r"(base));
+    return v;
+}
+__device__ __forceinline__ double lds_pos(uint32_t base, uint32_t pos, double) {
+    double v;
+    asm volatile("{\n.reg .u32 a;\nmad.lo.u32 a, %1, 8, %2;\nld.shared.f64 %0, [a];\n}" : "=d"(v) : "r"(pos), "r"(base));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
+    return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
+}
+
+// One 16-element chunk of pass A.  TAIL: elements j >= m are fillers.
+template <typename T, bool TAIL>
+__device__ __forceinline__ void pair_chunk(const uint16_t *__restrict__ ip, int j0, int m, uint32_t vals_sa, uint32_t hbase,
+                                           uint32_t blbase, float scale, float off, double &sx, double &qx) {
+    const uint16_t *ipc = ip + j0 * 32;  // element j of this thread's subsample sits at ip[32 * j]
+    uint32_t pos[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) pos[u] = (!TAIL || j0 + u < m) ? (uint32_t)__ldg(ipc + u * 32) : 0u;
+    T v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        uint32_t b = kPairPadId;
+        if (!TAIL || j0 + u < m) {
+            const double vd = (double)v[u];
+            sx += vd;
+            qx = fma(vd, vd, qx);
+            b = pair_bucket((float)v[u], scale, off);
+            const uint32_t ad = hist_addr(hbase, b);
+            sts_u8(ad, lds_u8(ad) + 1u);
+        }
+        pk[u >> 2] = b * (1u << (8 * (u & 3))) + pk[u >> 2];  // IMAD: ids are < 128, bytes do not overlap
+    }
+    sts_v4(blbase + (uint32_t)j0, pk[0], pk[1], pk[2], pk[3]);
+}
+
+// Ascending bitonic network on N = 2^k registers: every index is a compile-time constant.
+template <typename T, int N>
+__device__ __forceinline__ void sort_pow2_asc(T (&x)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const T lo = tmin(x[i], x[l]), hi = tmax(x[i], x[l]);
+                    const bool up = (i & k) == 0;
+                    x[i] = up ? lo : hi;
+                    x[l] = up ? hi : lo;
+                }
+            }
+        }
+    }
+}
+
+// x[r] for a runtime r < N without dynamic register indexing
+template <typename T, int N>
+__device__ __forceinline__ T pick_reg(const T (&x)[N], int r) {
+    T y = x[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i)
+        if (r == i) y = x[i];
+    return y;
+}
+
+template <typename T>
+struct PairCand {
+    static constexpr int kMax = 64 / (int)sizeof(T);  // candidates per range held in the 16 upper histogram words
+};
+
+// Exact order statistics at ranks ra <= rb (0-based) among the cnt elements of the sample whose
+// bucket lies in [blo, bhi].  Returns false if the range must be rescued by a full sort.
+template <typename T>
+__device__ __forceinline__ bool pair_select(const uint16_t *__restrict__ ip, int m, uint32_t vals_sa,
+                                            uint32_t hbase, uint32_t blbase, uint32_t blo, uint32_t bhi, int cnt, int ra,
+                                            int rb, T &ya, T &yb) {
+    constexpr int CM = PairCand<T>::kMax;
+    const uint32_t lo4 = blo * 0x01010101u;
+    const uint32_t hi4h = (bhi * 0x01010101u) | 0x80808080u;
+    const int nchunk = (m + 15) >> 4;
+    if (cnt <= CM) {
+        // flagged words of the bucket list -> records (word index | flag bits) in histogram words 0..15
+        int nrec = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
+            const uint32_t f0 = range_flags(q.x, lo4, hi4h), f1 = range_flags(q.y, lo4, hi4h);
+            const uint32_t f2 = range_flags(q.z, lo4, hi4h), f3 = range_flags(q.w, lo4, hi4h);
+            if (f0) { sts_u32(hbase + 128u * (uint32_t)nrec, f0 | (uint32_t)(4 * c + 0)); ++nrec; }
+            if (f1) { sts_u32(hbase + 128u * (uint32_t)nrec, f1 | (uint32_t)(4 * c + 1)); ++nrec; }
+            if (f2) { sts_u32(hbase + 128u * (uint32_t)nrec, f2 | (uint32_t)(4 * c + 2)); ++nrec; }
+            if (f3) { sts_u32(hbase + 128u * (uint32_t)nrec, f3 | (uint32_t)(4 * c + 3)); ++nrec; }
+        }
+        // re-gather the candidates into histogram words 16..31
+        const uint32_t cbase = hbase + 128u * 16u;
+        constexpr uint32_t kSlot = (sizeof(T) == 4) ? 128u : 256u;  // a double takes two interleaved words
+        int nc = 0;
+        for (int i = 0; i < nrec; ++i) {
+            const uint32_t r = lds_u32(hbase + 128u * (uint32_t)i);
+            const int wj = (int)(r & 63u);
+            uint32_t f = r & 0x80808080u;
+            while (f) {
+                const int bit = __ffs((int)f) - 1;
+                f &= f - 1u;
+                const int j = wj * 4 + (bit >> 3);
+                const uint32_t pos = (uint32_t)__ldg(ip + j * 32);
+                const T v = lds_pos(vals_sa, pos, T(0));
+                if (nc < CM) {
+                    if (sizeof(T) == 4) {
+                        sts_val(cbase + kSlot * (uint32_t)nc, v);
+                    } else {
+                        const long long bits = __double_as_longlong((double)v);
+                        sts_u32(cbase + kSlot * (uint32_t)nc, (uint32_t)bits);
+                        sts_u32(cbase + kSlot * (uint32_t)nc + 128u, (uint32_t)((unsigned long long)bits >> 32));
+                    }
+                }
+                ++nc;
+            }
+        }
+        auto load_cand = [&](int i) -> T {
+            if (sizeof(T) == 4) return lds_val(cbase + kSlot * (uint32_t)i, T(0));
+            const uint32_t lo = lds_u32(cbase + kSlot * (uint32_t)i), hi = lds_u32(cbase + kSlot * (uint32_t)i + 128u);
+            return (T)__longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        };
+        if (nc <= 8) {
+            T c[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? load_cand(i) : Big<T>::v();
+            sort_pow2_asc<T, 8>(c);
+            ya = pick_reg<T, 8>(c, ra);
+            yb = pick_reg<T, 8>(c, rb);
+        } else if (CM > 8) {
+            T c[CM];
+#pragma unroll
+            for (int i = 0; i < CM; ++i) c[i] = (i < nc) ? load_cand(i) : Big<T>::v();
+            sort_pow2_asc<T, CM>(c);
+            ya = pick_reg<T, CM>(c, ra);
+            yb = pick_reg<T, CM>(c, rb);
+        }
+        return nc == cnt;
+    }
+    // big range: exact only if it is a single tie group
+    T vmin = Big<T>::v(), vmax = -Big<T>::v();
+    for (int c = 0; c < nchunk; ++c) {
+        const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t f = range_flags(k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)), lo4, hi4h);
+            while (f) {
+                const int bit = __ffs((int)f) - 1;
+                f &= f - 1u;
+                const int j = c * 16 + k * 4 + (bit >> 3);
+                const uint32_t pos = (uint32_t)__ldg(ip + j * 32);
+                const T v = lds_pos(vals_sa, pos, T(0));
+                vmin = tmin(vmin, v);
+                vmax = tmax(vmax, v);
+            }
+        }
+    }
+    ya = vmin;
+    yb = vmin;
+    return vmin == vmax;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairArgs pa) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Step1Args &a = pa.a;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const int m = (int)a.m;
+
+    // shared memory: [class vector | mbarrier | per-warp partials | histograms (4 KB per warp) | bucket lists]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + pa.vals_bytes);
+    double *part = reinterpret_cast<double *>(bar + 2);
+    unsigned char *hist_raw = reinterpret_cast<unsigned char *>(part + 2 * (kPairMaxThreads / 32));
+    const uint32_t hbase = smem_u32(hist_raw) + (uint32_t)warp * (32u * kPairHistBytes) + (uint32_t)lane * 4u;
+    const uint32_t blbase = smem_u32(hist_raw) + (uint32_t)nw * (32u * kPairHistBytes) + (uint32_t)tid * (uint32_t)pa.bl_stride;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
+    __syncthreads();
+
+    unsigned phase = 0;
+    const double inv_n = 1.0 / (double)m;
+    const double inv_df = 1.0 / a.df;
+    const double inv_pair = inv_n + inv_n;
+    const double w_lo0 = 1.0 - a.q.g_lo, w_hi0 = 1.0 - a.q.g_hi;
+    const int P0 = a.q.j_lo, P1 = a.q.k_lo, P2 = a.q.j_hi, P3 = a.q.k_hi;
+    double *scr = pa.scratch + (size_t)blockIdx.x * 3u * (size_t)pa.slots;
+    const int m_full = m & ~15;
+
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        double facc = 0.0, racc = 0.0;
+        const unsigned char *row = static_cast<const unsigned char *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad * sizeof(T);
+        for (int cls = 0; cls < 2; ++cls) {
+            const int64_t e0 = cls ? pa.n0 : 0;
+            const int64_t ncls = cls ? pa.n1 : pa.n0;
+            const size_t b0 = ((size_t)e0 * sizeof(T)) & ~(size_t)15;
+            const size_t b1 = (((size_t)(e0 + ncls) * sizeof(T)) + 15) & ~(size_t)15;
+            __syncthreads();  // every read of the previous class vector is done
+            if (tid == 0) stage_row(smem_raw, row + b0, b1 - b0, bar);
+            const uint32_t vals_sa = smem_u32(smem_raw) + (uint32_t)((size_t)e0 * sizeof(T) - b0);
+            const float2 wn = __ldg(pa.win + (size_t)g * 2 + cls);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+
+            for (int r = 0; r < pa.rounds; ++r) {
+                const int slot = r * (int)blockDim.x + tid;
+                const int64_t s = a.s_begin + slot;
+                const bool active = s < a.s_end;
+                const int64_t sa = active ? s : a.s_begin;
+                const uint16_t *ip = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sa >> 5)) * (size_t)m) * 32u + (size_t)(sa & 31);
+                double sx = 0.0, qx = 0.0, iq = 0.0;
+                bool rescue = false;
+                if (active) {
+                    // ---- pass A
+                    for (int j0 = 0; j0 < m_full; j0 += 16)
+                        pair_chunk<T, false>(ip, j0, m, vals_sa, hbase, blbase, wn.x, wn.y, sx, qx);
+                    if (m_full < m) pair_chunk<T, true>(ip, m_full, m, vals_sa, hbase, blbase, wn.x, wn.y, sx, qx);
+                    // ---- locate the four sorted positions in the histogram
+                    uint32_t wi = 0, x = lds_u32(hbase), s4 = (x * 0x01010101u) >> 24;
+                    int cum = 0;
+                    int B[4], E[4], C[4];
+                    const int P[4] = {P0, P1, P2, P3};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        while (cum + (int)s4 <= P[t] && wi < 31u) {
+                            cum += (int)s4;
+                            ++wi;
+                            x = lds_u32(hbase + 128u * wi);
+                            s4 = (x * 0x01010101u) >> 24;
+                        }
+                        int run = cum;
+                        uint32_t q = 0, c = x & 255u;
+                        while (run + (int)c <= P[t] && q < 3u) {
+                            run += (int)c;
+                            ++q;
+                            c = (x >> (8u * q)) & 255u;
+                        }
+                        B[t] = (int)(wi * 4u + q);
+                        E[t] = run;
+                        C[t] = (int)c;
+                    }
+                    // ---- select inside the two bucket ranges
+                    T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const int Ba = h ? B[2] : B[0], Bb = h ? B[3] : B[1];
+                        const int Ea = h ? E[2] : E[0], Eb = h ? E[3] : E[1], Cb = h ? C[3] : C[1];
+                        const int Pa = h ? P2 : P0, Pb = h ? P3 : P1;
+                        T ya, yb;
+                        const bool ok = pair_select<T>(ip, m, vals_sa, hbase, blbase, (uint32_t)Ba, (uint32_t)Bb,
+                                                       Eb + Cb - Ea, Pa - Ea, Pb - Ea, ya, yb);
+                        rescue = rescue || !ok;
+                        if (h) {
+                            y2 = ya;
+                            y3 = yb;
+                        } else {
+                            y0 = ya;
+                            y1 = yb;
+                        }
+                    }
+                    const double q_lo = __dadd_rn(__dmul_rn(w_lo0, (double)y0), __dmul_rn(a.q.g_lo, (double)y1));
+                    const double q_hi = __dadd_rn(__dmul_rn(w_hi0, (double)y2), __dmul_rn(a.q.g_hi, (double)y3));
+                    iq = q_hi - q_lo;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
+                }
+                // ---- rescue: warp-cooperative full sort of the samples that could not be bucket-selected
+                unsigned todo = __ballot_sync(kFull, rescue);
+                while (todo) {
+                    const int L = __ffs((int)todo) - 1;
+                    todo &= todo - 1u;
+                    const int64_t sL = __shfl_sync(kFull, s, L);
+                    const uint16_t *ipL = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sL >> 5)) * (size_t)m) * 32u + (size_t)(sL & 31);
+                    T v[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int j = lane + 32 * rr;
+                        v[rr] = (j < m) ? lds_pos(vals_sa, (uint32_t)__ldg(ipL + j * 32), T(0)) : Lim<T>::inf();
+                    }
+                    warp_sort_asc<T, 8>(v, lane);
+                    const double iqL = iqr_of_sorted<T, 8>(v, a.q);
+                    if (lane == L) iq = iqL;
+                }
+                if (active) {
+                    if (cls == 0) {
+                        scr[slot] = sx;
+                        scr[pa.slots + slot] = qx;
+                        scr[2 * pa.slots + slot] = iq;
+                    } else {
+                        const double sx0 = scr[slot], qx0 = scr[pa.slots + slot], iq0 = scr[2 * pa.slots + slot];
+                        double ss0 = qx0 - sx0 * sx0 * inv_n;
+                        if (fabs(ss0) <= 1e-15 * qx0) ss0 = 0.0;
+                        double ss1 = qx - sx * sx * inv_n;
+                        if (fabs(ss1) <= 1e-15 * qx) ss1 = 0.0;
+                        const double svar = (ss0 + ss1) * inv_df;
+                        const double dmean = (sx0 - sx) * inv_n;
+                        const double stat = dmean * rsqrt(svar * inv_pair);
+                        double delta = fabs(iq0 - iq);
+                        if (!isfinite(delta)) delta = 0.0;  // phet.py:416
+                        racc += delta;
+                        double p = (a.test == PHET_TEST_Z) ? p_two_sided_z(stat) : p_two_sided_t(stat, a.df, a.ln_beta);
+                        if (p <= a.p_flush) p = 0.0;
+                        facc += fisher_term(p);
+                        if (a.dbgD != nullptr) a.dbgD[g * a.dbg_ld + (s - a.s_begin)] = delta;
+                        if (a.dbgP != nullptr) a.dbgP[g * a.dbg_ld + (s - a.s_begin)] = (p == p && !isinf(p)) ? p : 0.0;
+                    }
+                }
+            }
+        }
+        facc = warp_sum(facc);
+        racc = warp_sum(racc);
+        if (lane == 0) {
+            part[warp * 2 + 0] = facc;
+            part[warp * 2 + 1] = racc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tf = 0.0, tr = 0.0;
+            for (int w = 0; w < nw; ++w) {  // fixed order: reproducible for a given launch shape
+                tf += part[w * 2 + 0];
+                tr += part[w * 2 + 1];
+            }
+            if (a.accumulate) {
+                tf += a.acc_f[g];
+                tr += a.acc_r[g];
+            }
+            a.acc_f[g] = tf;
+            a.acc_r[g] = tr;
+        }
+    }
+}
+
+// Bucket map per (gene, class): one warp sorts a sample of the class and brackets the two
+// percentiles.  fa / fb: lower / upper probability positions before the sampling margin.
+template <typename T>
+__global__ void __launch_bounds__(256) k_windows(const void *__restrict__ xg, int64_t n_pad, int64_t xg_g0, int64_t g_begin,
+                                                 int64_t g_end, int64_t n0, int64_t n1, float p_lo, float p_hi, float m,
+                                                 float z, float2 *__restrict__ win) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t g = g_begin + (wid >> 1);
+    const int cls = (int)(wid & 1);
+    if (g >= g_end) return;
+    const int64_t ncls = cls ? n1 : n0;
+    const int ns = (int)(ncls < kWinSample ? ncls : kWinSample);
+    const T *gene = static_cast<const T *>(xg) + (g - xg_g0) * n_pad + (cls ? n0 : 0);
+    T v[kWinSample / 32];
+#pragma unroll
+    for (int r = 0; r < kWinSample / 32; ++r) {
+        const int k = lane + 32 * r;
+        v[r] = (k < ns) ? __ldg(gene + k) : Lim<T>::inf();
+    }
+    warp_sort_asc<T, kWinSample / 32>(v, lane);
+    const float fns = (float)ns;
+    const float var = 1.0f / m + 1.0f / fns;
+    const float fa = p_lo - z * sqrtf(fmaxf(p_lo * (1.0f - p_lo), 0.0f) * var) - 1.0f / fns;
+    const float fb = p_hi + z * sqrtf(fmaxf(p_hi * (1.0f - p_hi), 0.0f) * var) + 1.0f / fns;
+    int ra = (int)floorf(fa * fns), rb = (int)ceilf(fb * fns);
+    ra = max(0, min(ra, ns - 1));
+    rb = max(0, min(rb, ns - 1));
+    float lo = (float)warp_pick<T, kWinSample / 32>(v, ra);
+    float hi = (float)warp_pick<T, kWinSample / 32>(v, rb);
+    if (!(hi > lo)) {  // the bracket collapsed onto a tie group: fall back to the sample's range
+        lo = (float)warp_pick<T, kWinSample / 32>(v, 0);
+        hi = (float)warp_pick<T, kWinSample / 32>(v, ns - 1);
+    }
+    float scale = 0.0f, off = 1.0f;
+    if (hi > lo) {
+        scale = 125.0f / (hi - lo);
+        off = 1.0f - lo * scale;
+        if (!isfinite(scale) || !isfinite(off)) {
+            scale = 0.0f;
+            off = 1.0f;
+        }
+    }
+    if (lane == 0) win[(size_t)g * 2 + cls] = make_float2(scale, off);
+}
+
+struct PairGeometry {
+    int threads = 0, rounds = 0, bl_stride = 0, vals_bytes = 0;
+    size_t smem = 0;
+};
+
+// Shared-memory budget and thread count for S_local subsamples.  threads == 0: not eligible.
+template <typename T>
+static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_local) {
+    PairGeometry ge;
+    if (m < 1 || m > 255 || n0 > 65536 || n1 > 65536 || S_local < 1) return ge;
+    const int64_t nmax = n0 > n1 ? n0 : n1;
+    ge.vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
+    int chunks = (int)((m + 15) / 16);
+    if ((chunks & 1) == 0) ++chunks;  // stride = 16 bytes * odd: 128-bit bucket-list accesses are conflict-free
+    ge.bl_stride = 16 * chunks;
+    const size_t fixed = (size_t)ge.vals_bytes + 16 + 2 * (kPairMaxThreads / 32) * sizeof(double);
+    const size_t per_thread = (size_t)kPairHistBytes + (size_t)ge.bl_stride;
+    if (fixed + 64 * per_thread > (size_t)kMaxSmemOptin) return ge;
+    int tmax = (int)(((size_t)kMaxSmemOptin - fixed) / per_thread) / 32 * 32;
+    if (tmax > kPairMaxThreads) tmax = kPairMaxThreads;
+    const int rounds = (int)((S_local + tmax - 1) / tmax);
+    int t = (int)((S_local + rounds - 1) / rounds);
+    t = (t + 31) / 32 * 32;
+    ge.threads = t;
+    ge.rounds = rounds;
+    ge.smem = fixed + (size_t)t * per_thread;
+    return ge;
+}
+
+}  // namespace phet
+
+namespace phet {
+
+// Returns 1 when the pair-per-thread path does not apply (caller falls back to the warp sorters).
+template <typename T>
+static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
+    if (!c->idxT_ok || c->step1_impl == 1) return 1;
+    const int64_t S_local = args.s_end - args.s_begin;
+    const PairGeometry ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local);
+    if (ge.threads == 0) return 1;
+    auto kern = k_step1p<T>;
+    PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
+    int per_sm = 0;
+    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ge.threads, ge.smem));
+    if (per_sm < 1) return 1;
+    const int64_t ng = args.g_end - args.g_begin;
+    int64_t grid = (int64_t)per_sm * c->num_sms;
+    if (grid > ng) grid = ng;
+    if (grid < 1) return 0;
+
+    if (int e = c->win.alloc((size_t)c->G * 2)) return e;
+    const int32_t slots = ge.rounds * ge.threads;
+    if (int e = c->pair_scratch.alloc((size_t)grid * 3 * (size_t)slots)) return e;
+
+    {   // bucket maps of the genes of this launch
+        const int64_t warps = ng * 2;
+        const unsigned blocks = (unsigned)((warps + 7) / 8);
+        const float mf = (float)args.m;
+        k_windows<T><<<blocks, 256, 0, c->stream>>>(args.xg, args.n_pad, args.xg_g0, args.g_begin, args.g_end, c->n0, c->n1,
+                                                   (float)args.q.j_lo / mf, (float)(args.q.k_hi + 1) / mf, mf, 4.0f,
+                                                   c->win.p);
+        c->launches++;
+    }
+    Step1PairArgs pa;
+    pa.a = args;
+    pa.idxT = c->idxT.p;
+    pa.nblk = (c->S + 31) / 32;
+    pa.win = c->win.p;
+    pa.scratch = c->pair_scratch.p;
+    pa.slots = slots;
+    pa.rounds = ge.rounds;
+    pa.bl_stride = ge.bl_stride;
+    pa.vals_bytes = ge.vals_bytes;
+    pa.n0 = c->n0;
+    pa.n1 = c->n1;
+    c->step1_geom[0] = (int32_t)grid;
+    c->step1_geom[1] = ge.threads;
+    c->step1_geom[2] = (int32_t)ge.smem;
+    c->step1_geom[3] = 0;
+    c->step1_geom[4] = 1 | 4;  // staged; bit 2: pair-per-thread bucket-select path
+    kern<<<(unsigned)grid, ge.threads, ge.smem, c->stream>>>(pa);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace phet
