@@ -378,7 +378,9 @@ def main():
     hbm_bytes = G * n_pad * 4 + 16 * G + s_local * 2 * m * 4           # gene rows staged once + accumulators + idx
     smem_bytes = G * s_local * 2 * m * 4                                 # gathered values
     step1_s = phase[1] * 1e-3
-    roofline = {"bound": "hbm", "kernel": "k_step1<float,E=%d,staged=%s>" % (geom["E"], geom["staged"]),
+    kname = {"pair-per-thread": "k_step1p<float>", "half-warp": "k_step1h<float,E=%d>" % geom["E"],
+             "full-warp": "k_step1<float,E=%d>" % geom["E"]}[geom["path"]]
+    roofline = {"bound": "hbm", "kernel": "%s (staged=%s)" % (kname, geom["staged"]),
                 "achieved": hbm_bytes / step1_s / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": hbm_bytes / step1_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                 "launch_ms": phase[1], "algorithmic_hbm_bytes_per_launch": int(hbm_bytes),

@@ -266,4 +266,5 @@ class Context:
     def step1_geometry(self):
         out = (C.c_int32 * 5)()
         _check(self.lib.phet_step1_geometry(self.h, out))
-        return dict(grid=out[0], block=out[1], smem=out[2], E=out[3], staged=bool(out[4]))
+        path = "pair-per-thread" if out[4] & 4 else ("half-warp" if out[4] & 2 else "full-warp")
+        return dict(grid=out[0], block=out[1], smem=out[2], E=out[3], staged=bool(out[4] & 1), path=path)

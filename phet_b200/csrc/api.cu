@@ -60,17 +60,18 @@ __global__ void k_remap_perm(uint32_t *__restrict__ perm, int64_t n, const int32
     }
 }
 
-// [S][2][m] grouped positions -> [2][nblk][m][32] class-local positions, 16 bits each: the 32
-// subsamples of a block are adjacent, so a warp of k_step1p reads 64 contiguous bytes per element
-__global__ void k_build_idxT(const int32_t *__restrict__ idx, int64_t S, int64_t m, int64_t n0, int64_t nblk,
+// [S][2][m] grouped positions -> [2][nblk][mp][32] class-local positions, 16 bits each (mp = m rounded
+// up to 16, rows >= m are 0): the 32 subsamples of a block are adjacent, so a warp of k_step1p reads 64
+// contiguous bytes per element, and whole 16-element chunks can be loaded without bounds checks
+__global__ void k_build_idxT(const int32_t *__restrict__ idx, int64_t S, int64_t m, int64_t mp, int64_t n0, int64_t nblk,
                              uint16_t *__restrict__ idxT) {
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk][m][32]
-    if (o >= 2 * nblk * m * 32) return;
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk][mp][32]
+    if (o >= 2 * nblk * mp * 32) return;
     const int64_t sl = o & 31;
-    const int64_t j = (o >> 5) % m;
-    const int64_t cb = (o >> 5) / m;  // c * nblk + blk
+    const int64_t j = (o >> 5) % mp;
+    const int64_t cb = (o >> 5) / mp;  // c * nblk + blk
     const int64_t c = cb / nblk, s = (cb % nblk) * 32 + sl;
-    idxT[o] = (s < S) ? (uint16_t)(idx[(s * 2 + c) * m + j] - (c ? n0 : 0)) : (uint16_t)0;
+    idxT[o] = (s < S && j < m) ? (uint16_t)(idx[(s * 2 + c) * m + j] - (c ? n0 : 0)) : (uint16_t)0;
 }
 
 static uint64_t gcd_u64(uint64_t a, uint64_t b) {
@@ -407,9 +408,10 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
     c->idxT_ok = false;
     if (c->n0 <= 65536 && c->n1 <= 65536 && m <= 255) {  // transposed 16-bit copy for the pair-per-thread Step 1
         const int64_t nblk = (S + 31) / 32;
-        const int64_t nT = 2 * nblk * m * 32;
+        const int64_t mp = (m + 15) / 16 * 16;
+        const int64_t nT = 2 * nblk * mp * 32;
         if (int e = c->idxT.alloc((size_t)nT)) return e;
-        k_build_idxT<<<(unsigned)((nT + 255) / 256), 256, 0, c->stream>>>(c->idx.p, S, m, c->n0, nblk, c->idxT.p);
+        k_build_idxT<<<(unsigned)((nT + 255) / 256), 256, 0, c->stream>>>(c->idx.p, S, m, mp, c->n0, nblk, c->idxT.p);
         c->launches++;
         PHET_CUDA(cudaGetLastError());
         c->idxT_ok = true;

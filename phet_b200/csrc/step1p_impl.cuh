@@ -128,30 +128,54 @@ __device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
     return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
 }
 
-// One 16-element chunk of pass A.  TAIL: elements j >= m are fillers.
-template <typename T, bool TAIL>
-__device__ __forceinline__ void pair_chunk(const uint16_t *__restrict__ ip, int j0, int m, uint32_t vals_sa, uint32_t hbase,
-                                           uint32_t blbase, float scale, float off, double &sx, double &qx) {
+// Indices of one 16-element chunk.  The index table is zero-padded to a multiple of 16 rows, so the
+// loads (and the gathers they feed) need no bounds predicate.
+__device__ __forceinline__ void pair_load_pos(const uint16_t *__restrict__ ip, int j0, uint32_t (&pos)[16]) {
     const uint16_t *ipc = ip + j0 * 32;  // element j of this thread's subsample sits at ip[32 * j]
-    uint32_t pos[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) pos[u] = (!TAIL || j0 + u < m) ? (uint32_t)__ldg(ipc + u * 32) : 0u;
-    T v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+    for (int u = 0; u < 16; ++u) pos[u] = (uint32_t)__ldg(ipc + u * 32);
+}
+
+// One 16-element chunk of pass A on gathered values.  TAIL: elements j >= m are fillers.
+template <typename T, bool TAIL>
+__device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint32_t hbase, uint32_t blbase, float scale,
+                                           float off, double &sx, double &qx) {
     uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        uint32_t b = kPairPadId;
-        if (!TAIL || j0 + u < m) {
+    for (int u = 0; u < 16; u += 2) {
+        // two histogram updates in flight: both counters are read before either is written, and
+        // the second write accounts for the first when the two elements share a bucket
+        uint32_t b0 = kPairPadId, b1 = kPairPadId;
+        const bool ok0 = !TAIL || j0 + u < m, ok1 = !TAIL || j0 + u + 1 < m;
+        if (ok0) {
             const double vd = (double)v[u];
             sx += vd;
             qx = fma(vd, vd, qx);
-            b = pair_bucket((float)v[u], scale, off);
-            const uint32_t ad = hist_addr(hbase, b);
-            sts_u8(ad, lds_u8(ad) + 1u);
+            b0 = pair_bucket((float)v[u], scale, off);
         }
-        pk[u >> 2] = b * (1u << (8 * (u & 3))) + pk[u >> 2];  // IMAD: ids are < 128, bytes do not overlap
+        if (ok1) {
+            const double vd = (double)v[u + 1];
+            sx += vd;
+            qx = fma(vd, vd, qx);
+            b1 = pair_bucket((float)v[u + 1], scale, off);
+        }
+        if (!TAIL) {
+            const uint32_t a0 = hist_addr(hbase, b0), a1 = hist_addr(hbase, b1);
+            const uint32_t c0 = lds_u8(a0), c1 = lds_u8(a1);
+            sts_u8(a0, c0 + 1u);
+            sts_u8(a1, c1 + (a0 == a1 ? 2u : 1u));
+        } else {
+            if (ok0) {
+                const uint32_t a0 = hist_addr(hbase, b0);
+                sts_u8(a0, lds_u8(a0) + 1u);
+            }
+            if (ok1) {
+                const uint32_t a1 = hist_addr(hbase, b1);
+                sts_u8(a1, lds_u8(a1) + 1u);
+            }
+        }
+        pk[u >> 2] = b0 * (1u << (8 * (u & 3))) + pk[u >> 2];  // IMAD: ids are < 128, bytes do not overlap
+        pk[u >> 2] = b1 * (1u << (8 * ((u + 1) & 3))) + pk[u >> 2];
     }
     sts_v4(blbase + (uint32_t)j0, pk[0], pk[1], pk[2], pk[3]);
 }
@@ -189,80 +213,16 @@ __device__ __forceinline__ T pick_reg(const T (&x)[N], int r) {
 
 template <typename T>
 struct PairCand {
-    static constexpr int kMax = 64 / (int)sizeof(T);  // candidates per range held in the 16 upper histogram words
+    static constexpr int kMax = 64 / (int)sizeof(T);  // candidates per bucket range (64 bytes of the bucket-list area each)
 };
 
-// Exact order statistics at ranks ra <= rb (0-based) among the cnt elements of the sample whose
-// bucket lies in [blo, bhi].  Returns false if the range must be rescued by a full sort.
+// A bucket range with more than kMax elements: exact only if it is one tie group.
 template <typename T>
-__device__ __forceinline__ bool pair_select(const uint16_t *__restrict__ ip, int m, uint32_t vals_sa,
-                                            uint32_t hbase, uint32_t blbase, uint32_t blo, uint32_t bhi, int cnt, int ra,
-                                            int rb, T &ya, T &yb) {
-    constexpr int CM = PairCand<T>::kMax;
+__device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int m, uint32_t vals_sa, uint32_t blbase,
+                                            uint32_t blo, uint32_t bhi, T &y) {
     const uint32_t lo4 = blo * 0x01010101u;
     const uint32_t hi4h = (bhi * 0x01010101u) | 0x80808080u;
     const int nchunk = (m + 15) >> 4;
-    if (cnt <= CM) {
-        // flagged words of the bucket list -> records (word index | flag bits) in histogram words 0..15
-        int nrec = 0;
-        for (int c = 0; c < nchunk; ++c) {
-            const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
-            const uint32_t f0 = range_flags(q.x, lo4, hi4h), f1 = range_flags(q.y, lo4, hi4h);
-            const uint32_t f2 = range_flags(q.z, lo4, hi4h), f3 = range_flags(q.w, lo4, hi4h);
-            if (f0) { sts_u32(hbase + 128u * (uint32_t)nrec, f0 | (uint32_t)(4 * c + 0)); ++nrec; }
-            if (f1) { sts_u32(hbase + 128u * (uint32_t)nrec, f1 | (uint32_t)(4 * c + 1)); ++nrec; }
-            if (f2) { sts_u32(hbase + 128u * (uint32_t)nrec, f2 | (uint32_t)(4 * c + 2)); ++nrec; }
-            if (f3) { sts_u32(hbase + 128u * (uint32_t)nrec, f3 | (uint32_t)(4 * c + 3)); ++nrec; }
-        }
-        // re-gather the candidates into histogram words 16..31
-        const uint32_t cbase = hbase + 128u * 16u;
-        constexpr uint32_t kSlot = (sizeof(T) == 4) ? 128u : 256u;  // a double takes two interleaved words
-        int nc = 0;
-        for (int i = 0; i < nrec; ++i) {
-            const uint32_t r = lds_u32(hbase + 128u * (uint32_t)i);
-            const int wj = (int)(r & 63u);
-            uint32_t f = r & 0x80808080u;
-            while (f) {
-                const int bit = __ffs((int)f) - 1;
-                f &= f - 1u;
-                const int j = wj * 4 + (bit >> 3);
-                const uint32_t pos = (uint32_t)__ldg(ip + j * 32);
-                const T v = lds_pos(vals_sa, pos, T(0));
-                if (nc < CM) {
-                    if (sizeof(T) == 4) {
-                        sts_val(cbase + kSlot * (uint32_t)nc, v);
-                    } else {
-                        const long long bits = __double_as_longlong((double)v);
-                        sts_u32(cbase + kSlot * (uint32_t)nc, (uint32_t)bits);
-                        sts_u32(cbase + kSlot * (uint32_t)nc + 128u, (uint32_t)((unsigned long long)bits >> 32));
-                    }
-                }
-                ++nc;
-            }
-        }
-        auto load_cand = [&](int i) -> T {
-            if (sizeof(T) == 4) return lds_val(cbase + kSlot * (uint32_t)i, T(0));
-            const uint32_t lo = lds_u32(cbase + kSlot * (uint32_t)i), hi = lds_u32(cbase + kSlot * (uint32_t)i + 128u);
-            return (T)__longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-        };
-        if (nc <= 8) {
-            T c[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? load_cand(i) : Big<T>::v();
-            sort_pow2_asc<T, 8>(c);
-            ya = pick_reg<T, 8>(c, ra);
-            yb = pick_reg<T, 8>(c, rb);
-        } else if (CM > 8) {
-            T c[CM];
-#pragma unroll
-            for (int i = 0; i < CM; ++i) c[i] = (i < nc) ? load_cand(i) : Big<T>::v();
-            sort_pow2_asc<T, CM>(c);
-            ya = pick_reg<T, CM>(c, ra);
-            yb = pick_reg<T, CM>(c, rb);
-        }
-        return nc == cnt;
-    }
-    // big range: exact only if it is a single tie group
     T vmin = Big<T>::v(), vmax = -Big<T>::v();
     for (int c = 0; c < nchunk; ++c) {
         const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
@@ -273,21 +233,22 @@ __device__ __forceinline__ bool pair_select(const uint16_t *__restrict__ ip, int
                 const int bit = __ffs((int)f) - 1;
                 f &= f - 1u;
                 const int j = c * 16 + k * 4 + (bit >> 3);
-                const uint32_t pos = (uint32_t)__ldg(ip + j * 32);
-                const T v = lds_pos(vals_sa, pos, T(0));
-                vmin = tmin(vmin, v);
-                vmax = tmax(vmax, v);
+                if (j < m) {
+                    const T v = lds_pos(vals_sa, (uint32_t)__ldg(ip + j * 32), T(0));
+                    vmin = tmin(vmin, v);
+                    vmax = tmax(vmax, v);
+                }
             }
         }
     }
-    ya = vmin;
-    yb = vmin;
+    y = vmin;
     return vmin == vmax;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int CM = PairCand<T>::kMax;
     const Step1Args &a = pa.a;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -318,6 +279,8 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
     const int P0 = a.q.j_lo, P1 = a.q.k_lo, P2 = a.q.j_hi, P3 = a.q.k_hi;
     double *scr = pa.scratch + (size_t)blockIdx.x * 3u * (size_t)pa.slots;
     const int m_full = m & ~15;
+    const int nchunk = (m + 15) >> 4;
+    const size_t idx_rows = (size_t)nchunk * 16u;  // rows per block of the zero-padded index table
 
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
         double facc = 0.0, racc = 0.0;
@@ -339,14 +302,30 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                 const int64_t s = a.s_begin + slot;
                 const bool active = s < a.s_end;
                 const int64_t sa = active ? s : a.s_begin;
-                const uint16_t *ip = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sa >> 5)) * (size_t)m) * 32u + (size_t)(sa & 31);
+                const uint16_t *ip = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sa >> 5)) * idx_rows) * 32u + (size_t)(sa & 31);
                 double sx = 0.0, qx = 0.0, iq = 0.0;
                 bool rescue = false;
                 if (active) {
-                    // ---- pass A
-                    for (int j0 = 0; j0 < m_full; j0 += 16)
-                        pair_chunk<T, false>(ip, j0, m, vals_sa, hbase, blbase, wn.x, wn.y, sx, qx);
-                    if (m_full < m) pair_chunk<T, true>(ip, m_full, m, vals_sa, hbase, blbase, wn.x, wn.y, sx, qx);
+                    // ---- pass A, software-pipelined: the index loads of chunk c+1 are in flight while chunk c is processed
+                    {
+                        uint32_t pos[16], nxt[16];
+                        pair_load_pos(ip, 0, pos);
+                        for (int j0 = 0; j0 < m_full; j0 += 16) {
+                            if (j0 + 16 < m) pair_load_pos(ip, j0 + 16, nxt);
+                            T v[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                            pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, sx, qx);
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) pos[u] = nxt[u];
+                        }
+                        if (m_full < m) {
+                            T v[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                            pair_chunk<T, true>(v, m_full, m, hbase, blbase, wn.x, wn.y, sx, qx);
+                        }
+                    }
                     // ---- locate the four sorted positions in the histogram
                     uint32_t wi = 0, x = lds_u32(hbase), s4 = (x * 0x01010101u) >> 24;
                     int cum = 0;
@@ -371,17 +350,118 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         E[t] = run;
                         C[t] = (int)c;
                     }
-                    // ---- select inside the two bucket ranges
+                    const int cntL = E[1] + C[1] - E[0], cntH = E[3] + C[3] - E[2];
+                    const bool smallL = cntL <= CM, smallH = cntH <= CM;
+                    // ---- a range too big to enumerate is exact only if it is one tie group (needs the intact bucket list)
+                    T tieL = T(0), tieH = T(0);
+                    if (!smallL) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[0], (uint32_t)B[1], tieL);
+                    if (!smallH) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[2], (uint32_t)B[3], tieH) || rescue;
+                    // ---- one pass over the bucket list: words holding an element of either bucket range become
+                    //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
+                    //      bits 0-5), compacted in place over the part of the list already consumed
+                    int nrec = 0;
+                    {
+                        // a range that is too big is matched by nothing here (lo > hi) and handled below
+                        const uint32_t lo4L = (smallL ? (uint32_t)B[0] : 1u) * 0x01010101u;
+                        const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
+                        const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
+                        const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
+                        for (int c = 0; c < nchunk; ++c) {
+                            const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t w = (k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
+                                const uint32_t wh = w | 0x80808080u;
+                                const uint32_t fl = (wh - lo4L) & (hi4L - w) & 0x80808080u;
+                                const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
+                                const uint32_t f = fl | (fh >> 1);
+                                if (f) {
+                                    sts_u32(blbase + 4u * (uint32_t)nrec, f | (uint32_t)(4 * c + k));
+                                    ++nrec;
+                                }
+                            }
+                        }
+                    }
+                    // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
+                    int nL = 0, nH = 0;
+                    for (int i = 0; i < nrec; ++i) {
+                        const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
+                        const int wj = (int)(rec & 63u) * 4;
+                        uint32_t fl = rec & 0x80808080u, fh = (rec << 1) & 0x80808080u;
+                        while (fl) {
+                            const int bit = __ffs((int)fl) - 1;
+                            fl &= fl - 1u;
+                            if (nL < CM) sts_u8(hist_addr(hbase, (uint32_t)nL), (uint32_t)(wj + (bit >> 3)));
+                            ++nL;
+                        }
+                        while (fh) {
+                            const int bit = __ffs((int)fh) - 1;
+                            fh &= fh - 1u;
+                            if (nH < CM) sts_u8(hist_addr(hbase, 16u + (uint32_t)nH), (uint32_t)(wj + (bit >> 3)));
+                            ++nH;
+                        }
+                    }
+                    rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
+                    // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
+                    //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
+                    {
+                        const int nLc = nL < CM ? nL : CM, nHc = nH < CM ? nH : CM;
+                        const int nmax = nLc > nHc ? nLc : nHc;
+                        for (int i0 = 0; i0 < nmax; i0 += 4) {
+                            uint32_t pl[4], ph[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
+                                const uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
+                                const uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
+                                pl[u] = (uint32_t)__ldg(ip + jl * 32u);
+                                ph[u] = (uint32_t)__ldg(ip + jh * 32u);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const T vl = lds_pos(vals_sa, pl[u], T(0)), vh = lds_pos(vals_sa, ph[u], T(0));
+                                if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
+                                if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
+                            }
+                        }
+                    }
+                    // ---- sort the candidates of each range and read off the two ranks
                     T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
-                        const int Ba = h ? B[2] : B[0], Bb = h ? B[3] : B[1];
-                        const int Ea = h ? E[2] : E[0], Eb = h ? E[3] : E[1], Cb = h ? C[3] : C[1];
-                        const int Pa = h ? P2 : P0, Pb = h ? P3 : P1;
+                        const int nc = h ? nH : nL;
+                        const bool small = h ? smallH : smallL;
+                        const int ra = h ? P2 - E[2] : P0 - E[0], rb = h ? P3 - E[2] : P1 - E[0];
+                        const uint32_t cb = blbase + (h ? 64u : 0u);
                         T ya, yb;
-                        const bool ok = pair_select<T>(ip, m, vals_sa, hbase, blbase, (uint32_t)Ba, (uint32_t)Bb,
-                                                       Eb + Cb - Ea, Pa - Ea, Pb - Ea, ya, yb);
-                        rescue = rescue || !ok;
+                        if (!small) {
+                            ya = h ? tieH : tieL;
+                            yb = ya;
+                        } else if (nc <= 8 || CM <= 8) {
+                            T c[8];
+                            if (sizeof(T) == 4) {
+                                const uint4 q0 = lds_v4(cb), q1 = lds_v4(cb + 16u);
+                                c[0] = (T)__uint_as_float(q0.x); c[1] = (T)__uint_as_float(q0.y);
+                                c[2] = (T)__uint_as_float(q0.z); c[3] = (T)__uint_as_float(q0.w);
+                                c[4] = (T)__uint_as_float(q1.x); c[5] = (T)__uint_as_float(q1.y);
+                                c[6] = (T)__uint_as_float(q1.z); c[7] = (T)__uint_as_float(q1.w);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) c[i] = lds_val(cb + 8u * (uint32_t)i, T(0));
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? c[i] : Big<T>::v();
+                            sort_pow2_asc<T, 8>(c);
+                            ya = pick_reg<T, 8>(c, ra);
+                            yb = pick_reg<T, 8>(c, rb);
+                        } else {
+                            T c[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) c[i] = (i < nc) ? lds_val(cb + (uint32_t)(i * (int)sizeof(T)), T(0)) : Big<T>::v();
+                            sort_pow2_asc<T, 16>(c);
+                            ya = pick_reg<T, 16>(c, ra);
+                            yb = pick_reg<T, 16>(c, rb);
+                        }
                         if (h) {
                             y2 = ya;
                             y3 = yb;
@@ -402,7 +482,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     const int L = __ffs((int)todo) - 1;
                     todo &= todo - 1u;
                     const int64_t sL = __shfl_sync(kFull, s, L);
-                    const uint16_t *ipL = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sL >> 5)) * (size_t)m) * 32u + (size_t)(sL & 31);
+                    const uint16_t *ipL = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sL >> 5)) * idx_rows) * 32u + (size_t)(sL & 31);
                     T v[8];
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
@@ -521,6 +601,7 @@ static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_l
     const int64_t nmax = n0 > n1 ? n0 : n1;
     ge.vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
     int chunks = (int)((m + 15) / 16);
+    if (chunks < 9) chunks = 9;       // the first 128 bytes double as the candidate-value area
     if ((chunks & 1) == 0) ++chunks;  // stride = 16 bytes * odd: 128-bit bucket-list accesses are conflict-free
     ge.bl_stride = 16 * chunks;
     const size_t fixed = (size_t)ge.vals_bytes + 16 + 2 * (kPairMaxThreads / 32) * sizeof(double);

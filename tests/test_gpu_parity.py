@@ -178,3 +178,48 @@ def test_cli_main_srbct(tmp_path):
     common = [f for f in got if f in ref_scores]
     assert np.allclose(df.set_index("features").loc[common, "score"].to_numpy(), [ref_scores[f] for f in common],
                        rtol=1e-3)
+
+
+def _adversarial_cases():
+    rng = np.random.default_rng(7)
+    cases = {}
+    # zero-inflated counts: one huge tie group that the percentiles fall into for most subsamples
+    X = rng.poisson(0.15, (900, 40)).astype(np.float64)
+    cases["zero_inflated"] = (X, 450, dict(num_subsamples=40))
+    # a few distinct values only (every bucket is a tie group), plus constant genes
+    X = rng.integers(0, 4, (700, 30)).astype(np.float64)
+    X[:, :3] = 2.0
+    cases["few_levels"] = (X, 300, dict(num_subsamples=30))
+    # heavy tails: the sampled window is a poor fit for some genes
+    X = rng.standard_cauchy((1000, 30))
+    cases["cauchy"] = (X, 500, dict(num_subsamples=30))
+    # m not a multiple of 16, wide and narrow percentiles, replace=True (m > class size)
+    X = rng.gamma(2.0, 1.0, (600, 24))
+    cases["m_37"] = (X, 300, dict(num_subsamples=25, subsampling_size=37, percentiles=(5, 95)))
+    cases["m_250"] = (X, 300, dict(num_subsamples=12, subsampling_size=250, percentiles=(40, 60)))
+    cases["replace_true"] = (X[:130], 60, dict(num_subsamples=20, subsampling_size=100))
+    # bimodal: the two percentiles sit in different modes with a gap between them
+    X = np.where(rng.random((800, 20)) < 0.5, rng.normal(-5, 0.1, (800, 20)), rng.normal(5, 0.1, (800, 20)))
+    cases["bimodal"] = (X, 400, dict(num_subsamples=30))
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_adversarial_cases()))
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_step1_pair_path_equals_sort_path(name, dt, monkeypatch):
+    """The bucket-select kernel (k_step1p) must reproduce the sorting kernels exactly: identical
+    order statistics (delta-IQR bit for bit) and the same p-values up to fp64 summation order."""
+    from phet_b200 import PHet
+    X, n0, kw = _adversarial_cases()[name]
+    X = np.ascontiguousarray(X.astype(dt))
+    y = np.r_[np.zeros(n0, dtype=np.int64), np.ones(X.shape[0] - n0, dtype=np.int64)]
+    out = {}
+    for impl in ("auto", "warp"):
+        monkeypatch.setenv("PHET_STEP1_IMPL", impl)
+        np.random.seed(99)
+        est = PHet(**kw, capture=True, distributed=False, permutation="device")
+        est.fit_predict(X, y)
+        out[impl] = (est.R_.copy(), est.P_.copy(), est.step1_geometry_["path"])
+    assert out["auto"][2] == "pair-per-thread" and out["warp"][2] != "pair-per-thread"
+    assert np.array_equal(out["auto"][0], out["warp"][0]), "delta-IQR differs between the select and the sort path"
+    assert np.allclose(out["auto"][1], out["warp"][1], rtol=1e-11, atol=1e-300)
