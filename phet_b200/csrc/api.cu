@@ -207,6 +207,7 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (const char *impl = getenv("PHET_STEP1_IMPL")) c->step1_impl = (strcmp(impl, "warp") == 0) ? 1 : 0;
+    if (const char *nbw = getenv("PHET_STEP1_NBW")) c->pair_nbw = (atoi(nbw) == 16) ? 16 : (atoi(nbw) == 32 ? 32 : 0);
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;

@@ -37,8 +37,9 @@
 namespace phet {
 
 constexpr int kPairMaxThreads = 512;
-constexpr int kPairHistBytes = 128;   // per thread: 127 one-byte counters (+1 unused)
-constexpr float kPairTopBucket = 126.5f;
+// Per thread: NBW histogram words = 4*NBW one-byte counters; buckets 0 .. 4*NBW-2 are used.  NBW = 32 when
+// shared memory allows, 16 when that buys more resident threads (latency hiding matters more than
+// bucket resolution: coarser buckets only add a few candidates per range).
 constexpr uint32_t kPairPadId = 127u; // bucket-list filler of the last chunk (never a target)
 constexpr int kWinSample = 512;       // cells per class sampled by k_windows
 
@@ -97,12 +98,21 @@ __device__ __forceinline__ double lds_val(uint32_t addr, double) {
     return v;
 }
 
-// Monotone non-decreasing in v (fma with scale >= 0, min, truncation and saturation all are);
-// below the window and NaN -> 0, above -> 126.
-__device__ __forceinline__ uint32_t pair_bucket(float v, float scale, float off) {
-    const float t = fminf(fmaf(v, scale, off), kPairTopBucket);
+__device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
+    return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
+}
+
+// Bucket of v and the shared-memory address of its counter.  t = v*scale + off, clamped to
+// top = 4*NBW - 1.5, is monotone non-decreasing in v (fma with scale >= 0, min, truncation and the
+// saturation of the conversion all are); below the window and NaN -> 0.  The counter of bucket b is
+// byte b%4 of word b/4, and the words of a thread sit 128 bytes apart (bank == lane: conflict-free).
+// (One conversion only: F2I runs on the quarter-rate XU pipe, which the fp64 conversions also use.)
+__device__ __forceinline__ uint32_t pair_bucket(float v, float scale, float off, float top, uint32_t hbase,
+                                                uint32_t &addr) {
+    const float t = fminf(fmaf(v, scale, off), top);
     uint32_t b;
     asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(b) : "f"(t));
+    addr = hist_addr(hbase, b);
     return b;
 }
 
@@ -124,9 +134,6 @@ __device__ __forceinline__ double lds_pos(uint32_t base, uint32_t pos, double) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
-    return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
-}
 
 // Indices of one 16-element chunk.  The index table is zero-padded to a multiple of 16 rows, so the
 // loads (and the gathers they feed) need no bounds predicate.
@@ -139,44 +146,36 @@ __device__ __forceinline__ void pair_load_pos(const uint16_t *__restrict__ ip, i
 // One 16-element chunk of pass A on gathered values.  TAIL: elements j >= m are fillers.
 template <typename T, bool TAIL>
 __device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint32_t hbase, uint32_t blbase, float scale,
-                                           float off, double &sx, double &qx) {
-    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                                           float off, float top, double (&sx)[2], double (&qx)[2]) {
+    uint32_t b[16], ad[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        b[u] = kPairPadId;
+        ad[u] = hbase;
+        if (!TAIL || j0 + u < m) {
+            const double vd = (double)v[u];
+            sx[u & 1] += vd;
+            qx[u & 1] = fma(vd, vd, qx[u & 1]);
+            b[u] = pair_bucket((float)v[u], scale, off, top, hbase, ad[u]);
+        }
+    }
 #pragma unroll
     for (int u = 0; u < 16; u += 2) {
         // two histogram updates in flight: both counters are read before either is written, and
         // the second write accounts for the first when the two elements share a bucket
-        uint32_t b0 = kPairPadId, b1 = kPairPadId;
-        const bool ok0 = !TAIL || j0 + u < m, ok1 = !TAIL || j0 + u + 1 < m;
-        if (ok0) {
-            const double vd = (double)v[u];
-            sx += vd;
-            qx = fma(vd, vd, qx);
-            b0 = pair_bucket((float)v[u], scale, off);
-        }
-        if (ok1) {
-            const double vd = (double)v[u + 1];
-            sx += vd;
-            qx = fma(vd, vd, qx);
-            b1 = pair_bucket((float)v[u + 1], scale, off);
-        }
         if (!TAIL) {
-            const uint32_t a0 = hist_addr(hbase, b0), a1 = hist_addr(hbase, b1);
-            const uint32_t c0 = lds_u8(a0), c1 = lds_u8(a1);
-            sts_u8(a0, c0 + 1u);
-            sts_u8(a1, c1 + (a0 == a1 ? 2u : 1u));
+            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]);
+            sts_u8(ad[u], c0 + 1u);
+            sts_u8(ad[u + 1], c1 + 1u + (ad[u] == ad[u + 1] ? 1u : 0u));
         } else {
-            if (ok0) {
-                const uint32_t a0 = hist_addr(hbase, b0);
-                sts_u8(a0, lds_u8(a0) + 1u);
-            }
-            if (ok1) {
-                const uint32_t a1 = hist_addr(hbase, b1);
-                sts_u8(a1, lds_u8(a1) + 1u);
-            }
+            if (j0 + u < m) sts_u8(ad[u], lds_u8(ad[u]) + 1u);
+            if (j0 + u + 1 < m) sts_u8(ad[u + 1], lds_u8(ad[u + 1]) + 1u);
         }
-        pk[u >> 2] = b0 * (1u << (8 * (u & 3))) + pk[u >> 2];  // IMAD: ids are < 128, bytes do not overlap
-        pk[u >> 2] = b1 * (1u << (8 * ((u + 1) & 3))) + pk[u >> 2];
     }
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // IMAD chain: ids are < 128, bytes do not overlap
+        pk[k] = ((b[4 * k + 3] * 256u + b[4 * k + 2]) * 256u + b[4 * k + 1]) * 256u + b[4 * k];
     sts_v4(blbase + (uint32_t)j0, pk[0], pk[1], pk[2], pk[3]);
 }
 
@@ -245,7 +244,7 @@ __device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int
     return vmin == vmax;
 }
 
-template <typename T>
+template <typename T, int NBW>
 __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int CM = PairCand<T>::kMax;
@@ -255,20 +254,22 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
     const int warp = tid >> 5;
     const int nw = blockDim.x >> 5;
     const int m = (int)a.m;
+    constexpr uint32_t kHistWarpBytes = 32u * 4u * NBW;
+    constexpr float kTop = 4.0f * NBW - 1.5f;
 
-    // shared memory: [class vector | mbarrier | per-warp partials | histograms (4 KB per warp) | bucket lists]
+    // shared memory: [class vector | mbarrier | per-warp partials | histograms (128*NBW bytes per warp) | bucket lists]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + pa.vals_bytes);
     double *part = reinterpret_cast<double *>(bar + 2);
     unsigned char *hist_raw = reinterpret_cast<unsigned char *>(part + 2 * (kPairMaxThreads / 32));
-    const uint32_t hbase = smem_u32(hist_raw) + (uint32_t)warp * (32u * kPairHistBytes) + (uint32_t)lane * 4u;
-    const uint32_t blbase = smem_u32(hist_raw) + (uint32_t)nw * (32u * kPairHistBytes) + (uint32_t)tid * (uint32_t)pa.bl_stride;
+    const uint32_t hbase = smem_u32(hist_raw) + (uint32_t)warp * kHistWarpBytes + (uint32_t)lane * 4u;
+    const uint32_t blbase = smem_u32(hist_raw) + (uint32_t)nw * kHistWarpBytes + (uint32_t)tid * (uint32_t)pa.bl_stride;
 
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
+    for (int i = 0; i < NBW; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
     __syncthreads();
 
     unsigned phase = 0;
@@ -306,16 +307,34 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                 double sx = 0.0, qx = 0.0, iq = 0.0;
                 bool rescue = false;
                 if (active) {
+                    double sxp[2] = {0.0, 0.0}, qxp[2] = {0.0, 0.0};
                     // ---- pass A, software-pipelined: the index loads of chunk c+1 are in flight while chunk c is processed
                     {
                         uint32_t pos[16], nxt[16];
                         pair_load_pos(ip, 0, pos);
-                        for (int j0 = 0; j0 < m_full; j0 += 16) {
+                        int j0 = 0;
+                        for (; j0 + 32 <= m_full; j0 += 32) {  // two chunks per trip: the index buffers swap roles
+                            pair_load_pos(ip, j0 + 16, nxt);
+                            {
+                                T v[16];
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                                pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                            }
+                            if (j0 + 32 < m) pair_load_pos(ip, j0 + 32, pos);
+                            {
+                                T v[16];
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, nxt[u], T(0));
+                                pair_chunk<T, false>(v, j0 + 16, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                            }
+                        }
+                        if (j0 < m_full) {  // one more full chunk
                             if (j0 + 16 < m) pair_load_pos(ip, j0 + 16, nxt);
                             T v[16];
 #pragma unroll
                             for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
-                            pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, sx, qx);
+                            pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
 #pragma unroll
                             for (int u = 0; u < 16; ++u) pos[u] = nxt[u];
                         }
@@ -323,8 +342,10 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             T v[16];
 #pragma unroll
                             for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
-                            pair_chunk<T, true>(v, m_full, m, hbase, blbase, wn.x, wn.y, sx, qx);
+                            pair_chunk<T, true>(v, m_full, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
                         }
+                        sx = sxp[0] + sxp[1];
+                        qx = qxp[0] + qxp[1];
                     }
                     // ---- locate the four sorted positions in the histogram
                     uint32_t wi = 0, x = lds_u32(hbase), s4 = (x * 0x01010101u) >> 24;
@@ -333,7 +354,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     const int P[4] = {P0, P1, P2, P3};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        while (cum + (int)s4 <= P[t] && wi < 31u) {
+                        while (cum + (int)s4 <= P[t] && wi < (uint32_t)(NBW - 1)) {
                             cum += (int)s4;
                             ++wi;
                             x = lds_u32(hbase + 128u * wi);
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         while (fl) {
                             const int bit = __ffs((int)fl) - 1;
                             fl &= fl - 1u;
-                            if (nL < CM) sts_u8(hist_addr(hbase, (uint32_t)nL), (uint32_t)(wj + (bit >> 3)));
+                            if (nL < CM) sts_u8(hist_addr(hbase, (uint32_t)nL), (uint32_t)(wj + (bit >> 3)));  // NBW >= 8
                             ++nL;
                         }
                         while (fh) {
@@ -474,7 +495,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     const double q_hi = __dadd_rn(__dmul_rn(w_hi0, (double)y2), __dmul_rn(a.q.g_hi, (double)y3));
                     iq = q_hi - q_lo;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
+                    for (int i = 0; i < NBW; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
                 }
                 // ---- rescue: warp-cooperative full sort of the samples that could not be bucket-selected
                 unsigned todo = __ballot_sync(kFull, rescue);
@@ -547,7 +568,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
 template <typename T>
 __global__ void __launch_bounds__(256) k_windows(const void *__restrict__ xg, int64_t n_pad, int64_t xg_g0, int64_t g_begin,
                                                  int64_t g_end, int64_t n0, int64_t n1, float p_lo, float p_hi, float m,
-                                                 float z, float2 *__restrict__ win) {
+                                                 float z, float interior, float2 *__restrict__ win) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t g = g_begin + (wid >> 1);
@@ -578,7 +599,7 @@ __global__ void __launch_bounds__(256) k_windows(const void *__restrict__ xg, in
     }
     float scale = 0.0f, off = 1.0f;
     if (hi > lo) {
-        scale = 125.0f / (hi - lo);
+        scale = interior / (hi - lo);  // [lo, hi) -> buckets 1 .. interior; below -> 0, above -> interior + 1
         off = 1.0f - lo * scale;
         if (!isfinite(scale) || !isfinite(off)) {
             scale = 0.0f;
@@ -589,47 +610,53 @@ __global__ void __launch_bounds__(256) k_windows(const void *__restrict__ xg, in
 }
 
 struct PairGeometry {
-    int threads = 0, rounds = 0, bl_stride = 0, vals_bytes = 0;
+    int threads = 0, rounds = 0, bl_stride = 0, vals_bytes = 0, nbw = 0;
     size_t smem = 0;
 };
 
 // Shared-memory budget and thread count for S_local subsamples.  threads == 0: not eligible.
+// Among the two histogram widths, the one that needs fewer rounds wins (more resident threads);
+// on a tie the finer histogram (fewer candidates per range).
 template <typename T>
-static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_local) {
-    PairGeometry ge;
-    if (m < 1 || m > 255 || n0 > 65536 || n1 > 65536 || S_local < 1) return ge;
+static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_local, int force_nbw = 0) {
+    PairGeometry best;
+    if (m < 1 || m > 255 || n0 > 65536 || n1 > 65536 || S_local < 1) return best;
     const int64_t nmax = n0 > n1 ? n0 : n1;
-    ge.vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
+    const int vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
     int chunks = (int)((m + 15) / 16);
     if (chunks < 9) chunks = 9;       // the first 128 bytes double as the candidate-value area
     if ((chunks & 1) == 0) ++chunks;  // stride = 16 bytes * odd: 128-bit bucket-list accesses are conflict-free
-    ge.bl_stride = 16 * chunks;
-    const size_t fixed = (size_t)ge.vals_bytes + 16 + 2 * (kPairMaxThreads / 32) * sizeof(double);
-    const size_t per_thread = (size_t)kPairHistBytes + (size_t)ge.bl_stride;
-    if (fixed + 64 * per_thread > (size_t)kMaxSmemOptin) return ge;
-    int tmax = (int)(((size_t)kMaxSmemOptin - fixed) / per_thread) / 32 * 32;
-    if (tmax > kPairMaxThreads) tmax = kPairMaxThreads;
-    const int rounds = (int)((S_local + tmax - 1) / tmax);
-    int t = (int)((S_local + rounds - 1) / rounds);
-    t = (t + 31) / 32 * 32;
-    ge.threads = t;
-    ge.rounds = rounds;
-    ge.smem = fixed + (size_t)t * per_thread;
-    return ge;
+    const int bl_stride = 16 * chunks;
+    const size_t fixed = (size_t)vals_bytes + 16 + 2 * (kPairMaxThreads / 32) * sizeof(double);
+    for (int nbw = 32; nbw >= 16; nbw -= 16) {
+        if (force_nbw && nbw != force_nbw) continue;
+        const size_t per_thread = (size_t)(4 * nbw) + (size_t)bl_stride;
+        if (fixed + 64 * per_thread > (size_t)kMaxSmemOptin) continue;
+        int tmax = (int)(((size_t)kMaxSmemOptin - fixed) / per_thread) / 32 * 32;
+        if (tmax > kPairMaxThreads) tmax = kPairMaxThreads;
+        const int rounds = (int)((S_local + tmax - 1) / tmax);
+        int t = (int)((S_local + rounds - 1) / rounds);
+        t = (t + 31) / 32 * 32;
+        if (best.threads == 0 || rounds < best.rounds) {
+            best.threads = t;
+            best.rounds = rounds;
+            best.bl_stride = bl_stride;
+            best.vals_bytes = vals_bytes;
+            best.nbw = nbw;
+            best.smem = fixed + (size_t)t * per_thread;
+        }
+    }
+    return best;
 }
-
-}  // namespace phet
-
-namespace phet {
 
 // Returns 1 when the pair-per-thread path does not apply (caller falls back to the warp sorters).
 template <typename T>
 static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     if (!c->idxT_ok || c->step1_impl == 1) return 1;
     const int64_t S_local = args.s_end - args.s_begin;
-    const PairGeometry ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local);
+    const PairGeometry ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local, c->pair_nbw);
     if (ge.threads == 0) return 1;
-    auto kern = k_step1p<T>;
+    auto kern = ge.nbw == 32 ? k_step1p<T, 32> : k_step1p<T, 16>;
     PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
     int per_sm = 0;
     PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ge.threads, ge.smem));
@@ -649,7 +676,7 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
         const float mf = (float)args.m;
         k_windows<T><<<blocks, 256, 0, c->stream>>>(args.xg, args.n_pad, args.xg_g0, args.g_begin, args.g_end, c->n0, c->n1,
                                                    (float)args.q.j_lo / mf, (float)(args.q.k_hi + 1) / mf, mf, 4.0f,
-                                                   c->win.p);
+                                                   (float)(4 * ge.nbw - 3), c->win.p);
         c->launches++;
     }
     Step1PairArgs pa;
@@ -667,7 +694,7 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     c->step1_geom[0] = (int32_t)grid;
     c->step1_geom[1] = ge.threads;
     c->step1_geom[2] = (int32_t)ge.smem;
-    c->step1_geom[3] = 0;
+    c->step1_geom[3] = 4 * ge.nbw - 1;  // buckets
     c->step1_geom[4] = 1 | 4;  // staged; bit 2: pair-per-thread bucket-select path
     kern<<<(unsigned)grid, ge.threads, ge.smem, c->stream>>>(pa);
     c->launches++;

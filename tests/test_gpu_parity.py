@@ -214,12 +214,17 @@ def test_step1_pair_path_equals_sort_path(name, dt, monkeypatch):
     X = np.ascontiguousarray(X.astype(dt))
     y = np.r_[np.zeros(n0, dtype=np.int64), np.ones(X.shape[0] - n0, dtype=np.int64)]
     out = {}
-    for impl in ("auto", "warp"):
+    for impl, nbw in (("auto", "32"), ("auto", "16"), ("warp", "0")):
         monkeypatch.setenv("PHET_STEP1_IMPL", impl)
+        monkeypatch.setenv("PHET_STEP1_NBW", nbw)   # histogram width of the select kernel: 127 or 63 buckets
         np.random.seed(99)
         est = PHet(**kw, capture=True, distributed=False, permutation="device")
         est.fit_predict(X, y)
-        out[impl] = (est.R_.copy(), est.P_.copy(), est.step1_geometry_["path"])
-    assert out["auto"][2] == "pair-per-thread" and out["warp"][2] != "pair-per-thread"
-    assert np.array_equal(out["auto"][0], out["warp"][0]), "delta-IQR differs between the select and the sort path"
-    assert np.allclose(out["auto"][1], out["warp"][1], rtol=1e-11, atol=1e-300)
+        out[impl + nbw] = (est.R_.copy(), est.P_.copy(), est.step1_geometry_)
+    ref = out["warp0"]
+    assert ref[2]["path"] != "pair-per-thread"
+    for key, buckets in (("auto32", 127), ("auto16", 63)):
+        got = out[key]
+        assert got[2]["path"] == "pair-per-thread" and got[2]["E"] == buckets
+        assert np.array_equal(got[0], ref[0]), "delta-IQR differs between the select and the sort path"
+        assert np.allclose(got[1], ref[1], rtol=1e-11, atol=1e-300)
