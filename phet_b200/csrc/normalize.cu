@@ -78,41 +78,77 @@ __global__ void k_colstats_final(const Tin *__restrict__ X, int64_t N, int64_t G
     sd[g] = sqrt(var);
 }
 
+// Tile of kTQ grouped positions x kTG genes.  A warp reads one source row at a time: 4 x 128
+// contiguous bytes (the rows of a class-grouped, shuffled layout are scattered over X, so wide
+// row segments are what keeps DRAM pages busy); a thread owns genes lane, lane+32, lane+64,
+// lane+96 so the transposed SMEM writes hit 32 distinct banks (tile pitch kTQ+1 is odd).  Each
+// gene row of the tile leaves as kTQ contiguous elements (2 per lane, 8- or 16-byte stores).
+constexpr int kTQ = 64;
+constexpr int kTG = 128;
+constexpr int kNTThreads = 256;
+
 template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(kTile *kRowsPerBlock)
+__global__ void __launch_bounds__(kNTThreads)
     k_normalize_transpose(const Tin *__restrict__ X, int64_t ldx, int64_t N, int64_t G, int64_t n_pad,
                           const int32_t *__restrict__ rows_grouped, const double *__restrict__ mean,
                           const double *__restrict__ sd, int normalize, Tout *__restrict__ xg) {
-    __shared__ Tout tile[kTile][kTile + 1];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int64_t g0 = (int64_t)blockIdx.x * kTile;
-    const int64_t q0 = (int64_t)blockIdx.y * kTile;
-    {
-        const int64_t g = g0 + tx;
-        double mu = 0.0, sg = 1.0;
-        if (normalize && g < G) {
-            mu = mean[g];
-            sg = sd[g];
-        }
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    Tout(*tile)[kTQ + 1] = reinterpret_cast<Tout(*)[kTQ + 1]>(tile_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g0 = (int64_t)blockIdx.x * kTG;
+    const int64_t q0 = (int64_t)blockIdx.y * kTQ;
+    double mu[4], sg[4];
 #pragma unroll
-        for (int i = ty; i < kTile; i += kRowsPerBlock) {
-            const int64_t q = q0 + i;
-            double z = 0.0;
-            if (q < N && g < G) {
-                const int64_t row = rows_grouped[q];
-                const double x = (double)X[row * ldx + g];
-                z = normalize ? (x - mu) / sg : x;
-                if (!isfinite(z)) z = 0.0;  // nan_to_num(nan=0, posinf=0, neginf=0), phet.py:299
-            }
-            tile[i][tx] = (Tout)z;
+    for (int i = 0; i < 4; ++i) {
+        const int64_t g = g0 + lane + 32 * i;
+        mu[i] = 0.0;
+        sg[i] = 1.0;
+        if (normalize && g < G) {
+            mu[i] = mean[g];
+            sg[i] = sd[g];
+        }
+    }
+    constexpr int kRowsPerWarp = kTQ / (kNTThreads / 32);
+    int64_t src[kRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int64_t q = q0 + warp * kRowsPerWarp + r;
+        src[r] = (q < N) ? (int64_t)rows_grouped[q] : (int64_t)-1;
+    }
+    Tin x[kRowsPerWarp][4];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t g = g0 + lane + 32 * i;
+            x[r][i] = (src[r] >= 0 && g < G) ? X[src[r] * ldx + g] : Tin(0);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double z = normalize ? ((double)x[r][i] - mu[i]) / sg[i] : (double)x[r][i];
+            if (!isfinite(z) || src[r] < 0) z = 0.0;  // nan_to_num(nan=0, posinf=0, neginf=0), phet.py:299
+            tile[lane + 32 * i][warp * kRowsPerWarp + r] = (Tout)z;
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int i = ty; i < kTile; i += kRowsPerBlock) {
-        const int64_t g = g0 + i;
-        const int64_t q = q0 + tx;
-        if (g < G && q < n_pad) xg[g * n_pad + q] = tile[tx][i];
+    constexpr int kGenesPerWarp = kTG / (kNTThreads / 32);
+    const int64_t q = q0 + 2 * lane;  // n_pad is even for both storage types: q < n_pad implies q + 1 < n_pad
+    if (q < n_pad) {
+#pragma unroll 4
+        for (int k = 0; k < kGenesPerWarp; ++k) {
+            const int gi = warp * kGenesPerWarp + k;
+            const int64_t g = g0 + gi;
+            if (g < G) {
+                struct alignas(2 * sizeof(Tout)) Pair { Tout a, b; };
+                Pair pr;
+                pr.a = tile[gi][2 * lane];
+                pr.b = tile[gi][2 * lane + 1];
+                *reinterpret_cast<Pair *>(xg + g * n_pad + q) = pr;
+            }
+        }
     }
 }
 
@@ -141,16 +177,21 @@ static int run_normalize(phet_ctx *c, const Tin *X, int64_t ldx, int64_t g0, int
                                                                                   sd);
         c->launches++;
     }
-    dim3 blk(kTile, kRowsPerBlock);
-    dim3 grd((unsigned)((G + kTile - 1) / kTile), (unsigned)((c->n_pad + kTile - 1) / kTile));
+    dim3 grd((unsigned)((G + kTG - 1) / kTG), (unsigned)((c->n_pad + kTQ - 1) / kTQ));
     const size_t e_st = c->storage == PHET_F32 ? 4 : 8;
     unsigned char *out = c->xg.p + (size_t)(g0 - c->xg_g0) * (size_t)c->n_pad * e_st;
-    if (c->storage == PHET_F32)
-        k_normalize_transpose<Tin, float><<<grd, blk, 0, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean,
-                                                                     sd, normalize, (float *)out);
-    else
-        k_normalize_transpose<Tin, double><<<grd, blk, 0, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean,
-                                                                      sd, normalize, (double *)out);
+    const size_t tile_bytes = (size_t)kTG * (kTQ + 1) * e_st;
+    if (c->storage == PHET_F32) {
+        auto kern = k_normalize_transpose<Tin, float>;
+        PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+        kern<<<grd, kNTThreads, tile_bytes, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean, sd, normalize,
+                                                         (float *)out);
+    } else {
+        auto kern = k_normalize_transpose<Tin, double>;
+        PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+        kern<<<grd, kNTThreads, tile_bytes, c->stream>>>(X, ldx, N, G, c->n_pad, c->rows_grouped.p, mean, sd, normalize,
+                                                         (double *)out);
+    }
     c->launches++;
     PHET_CUDA(cudaGetLastError());
     return 0;
