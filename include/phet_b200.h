@@ -163,6 +163,13 @@ int phet_bin(phet_ctx *ctx, const double *edges, int32_t B, int64_t *counts_out)
  * scores_out: host double[G] or NULL (leave on device, PHET_BUF_SCORES). */
 int phet_combine(phet_ctx *ctx, const double *weights, int32_t B, double *scores_out);
 
+/* Context options.  PHET_OPT_KEEP_H (default 0): 1 = phet_step3 / phet_run_pipeline also fill PHET_BUF_H
+ * with the integer KS statistic of EVERY slice (parity / debugging; the sorting kernels run); 0 = only
+ * o[g] = min p is produced, which lets Step 3 bound h per slice from bucket histograms and evaluate
+ * exactly only the slices that can attain the gene's minimum p (phet.py:496 takes the min). */
+typedef enum { PHET_OPT_KEEP_H = 1 } phet_option;
+int phet_set_option(phet_ctx *ctx, int option, int64_t value);
+
 /* Raw device pointer / element count of a context buffer (for wrapping, no ownership change). */
 int phet_device_ptr(phet_ctx *ctx, int which, void **ptr_out, int64_t *bytes_out);
 /* Copy a context buffer to host memory (synchronises the stream). */
@@ -175,6 +182,8 @@ int phet_write_buffer(phet_ctx *ctx, int which, const void *host_in, int64_t byt
  * elements per lane E, staged = gene vector held in shared memory). */
 int64_t phet_launch_count(phet_ctx *ctx);
 int phet_step1_geometry(phet_ctx *ctx, int32_t out[5]);
+/* Kernel family of the last Step-3 launch: 1 full-warp sort, 2 half-warp sort, 3 bound-and-prune. */
+int phet_step3_path(phet_ctx *ctx);
 
 /* One-call convenience: everything above on one device with host buffers (used by C callers
  * and by the end-to-end benchmark leg).  perm_mode/seed as in phet_step3; with PHET_PERM_HOST

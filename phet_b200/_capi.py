@@ -17,6 +17,7 @@ PHET_F32, PHET_F64 = 0, 1
 NORM_NONE, NORM_ZSCORE = 0, 1
 TEST_T, TEST_Z = 0, 1
 PERM_HOST, PERM_DEVICE = 0, 1
+OPT_KEEP_H = 1
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
  BUF_STD, BUF_ROWS) = range(13)
 
@@ -24,7 +25,7 @@ EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_device_ptr",
-    "phet_read_buffer", "phet_write_buffer", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
+    "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -98,6 +99,8 @@ def load_library(build_if_missing: bool = True):
     lib.phet_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     lib.phet_read_buffer.argtypes = [vp, C.c_int, vp, i64]
     lib.phet_write_buffer.argtypes = [vp, C.c_int, vp, i64]
+    lib.phet_set_option.argtypes = [vp, C.c_int, i64]
+    lib.phet_step3_path.argtypes = [vp]
     lib.phet_launch_count.argtypes = [vp]
     lib.phet_launch_count.restype = i64
     lib.phet_step1_geometry.argtypes = [vp, C.POINTER(i32)]
@@ -151,6 +154,9 @@ class Context:
 
     def sync(self):
         _check(self.lib.phet_ctx_sync(self.h))
+
+    def set_option(self, option: int, value: int):
+        _check(self.lib.phet_set_option(self.h, int(option), int(value)))
 
     def set_classes(self, ctrl_rows, case_rows):
         a = np.ascontiguousarray(ctrl_rows, dtype=np.int32)
@@ -259,6 +265,9 @@ class Context:
     def write(self, which, arr: np.ndarray):
         arr = np.ascontiguousarray(arr)
         _check(self.lib.phet_write_buffer(self.h, which, _ptr(arr), arr.nbytes))
+
+    def step3_path(self):
+        return {0: "none", 1: "full-warp sort", 2: "half-warp sort", 3: "bound-and-prune"}[int(self.lib.phet_step3_path(self.h))]
 
     def launch_count(self):
         return int(self.lib.phet_launch_count(self.h))

@@ -207,6 +207,7 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (const char *impl = getenv("PHET_STEP1_IMPL")) c->step1_impl = (strcmp(impl, "warp") == 0) ? 1 : 0;
+    if (const char *impl = getenv("PHET_STEP3_IMPL")) c->step3_impl = (strcmp(impl, "sort") == 0) ? 1 : 0;
     if (const char *nbw = getenv("PHET_STEP1_NBW")) c->pair_nbw = (atoi(nbw) == 16) ? 16 : (atoi(nbw) == 32 ? 32 : 0);
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -242,6 +243,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->idxT.release();
     c->win.release();
     c->pair_scratch.release();
+    c->win3.release();
     c->acc.release();
     c->dbgP.release();
     c->dbgD.release();
@@ -445,6 +447,16 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
     const int64_t n_slices = (min_c + m - 1) / m;
     PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");
     c->n_slices = n_slices;
+    {   // h0: table_full is non-increasing on [h0, m] and table_full[h0] <= every earlier entry (the exact
+        // formula is only "essentially" monotone: rounding noise of 1 ulp at h = 1, 2 for some n)
+        int64_t h0 = 0;
+        for (int64_t h = 0; h < m; ++h)
+            if (table_full[h + 1] > table_full[h]) h0 = h + 1;
+        double floor0 = INFINITY;
+        for (int64_t h = 0; h < h0; ++h) floor0 = fmin(floor0, table_full[h]);
+        while (h0 <= m && table_full[h0] > floor0) ++h0;
+        c->tab_h0 = (int)h0;  // may be m + 1: every slice is then evaluated exactly
+    }
     if (int e = c->H.alloc((size_t)c->G * (size_t)n_slices)) return e;
     if (int e = c->tab_full.alloc((size_t)m + 1)) return e;
     if (int e = c->tab_last.alloc((size_t)n_last + 1)) return e;
@@ -671,7 +683,17 @@ int phet_write_buffer(phet_ctx *c, int which, const void *host_in, int64_t bytes
     return PHET_OK;
 }
 
+int phet_set_option(phet_ctx *c, int option, int64_t value) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    switch (option) {
+        case PHET_OPT_KEEP_H: c->keep_H = value != 0; return PHET_OK;
+        default: set_error("invalid: unknown option"); return PHET_ERR_INVALID;
+    }
+}
+
 int64_t phet_launch_count(phet_ctx *c) { return c ? c->launches : 0; }
+
+int phet_step3_path(phet_ctx *c) { return c ? c->step3_path : 0; }
 
 int phet_step1_geometry(phet_ctx *c, int32_t out[5]) {
     PHET_REQUIRE(c != nullptr && out, "NULL argument");

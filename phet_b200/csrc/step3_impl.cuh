@@ -206,6 +206,7 @@ static int launch_step3_inst(phet_ctx *c, const Step3Args &args, size_t smem_gen
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, kThreads3, smem, c->stream>>>(args);
     c->launches++;
+    c->step3_path = 1;
     PHET_CUDA(cudaGetLastError());
     return 0;
 }

@@ -152,6 +152,7 @@ static int launch_step3h_inst(phet_ctx *c, const Step3Args &args, size_t smem_ge
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, kThreads3, smem, c->stream>>>(args);
     c->launches++;
+    c->step3_path = 2;
     PHET_CUDA(cudaGetLastError());
     return 0;
 }
@@ -168,9 +169,17 @@ static int launch_step3h_E(phet_ctx *c, const Step3Args &args) {
     return rc;
 }
 
-// m <= 256: half-warp path; larger m: full-warp network (step3_impl.cuh).
+template <typename T>
+static int run_step3_prune(phet_ctx *c, const Step3Args &args);  // step3p_impl.cuh
+
+// Bound-and-prune path when it applies (step3p_impl.cuh); else m <= 256: half-warp path; larger m:
+// full-warp network (step3_impl.cuh).
 template <typename T>
 static int run_step3_any(phet_ctx *c, const Step3Args &args) {
+    {
+        const int rc = run_step3_prune<T>(c, args);
+        if (rc != 1) return rc;
+    }
     if (args.m > 256) return run_step3_T<T>(c, args);
     const int need = (int)((args.m + 15) / 16);
     if (need <= 1) return launch_step3h_E<T, 1>(c, args);

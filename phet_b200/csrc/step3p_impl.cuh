@@ -1,0 +1,412 @@
+// Step 3, bound-and-prune path (slice length m <= 255, one class vector fits in shared memory, H not
+// requested).  Same contract as k_step3 (step3_impl.cuh) for o[g]; replaces phet.py:473-498.
+//
+// o[g] = min over slices of the KS p-value, and p is (essentially) non-increasing in the integer
+// statistic h, so only the slices that can reach the gene's largest h need an exact h.  Per gene:
+//
+//   phase 1  (control vector staged)  one THREAD per slice walks its permutation slice, maps every
+//            value through a per-gene monotone affine map to one of 127 buckets and counts it in a
+//            thread-private byte histogram ha (bank == lane: conflict-free), as in k_step1p.
+//   phase 2  (case vector staged)  same for hb, then one pass over the 127 buckets gives rigorous
+//            bounds on h: with D_k = sum_{i<=k} (ha_i - hb_i) the ECDF difference at the bucket edges,
+//            L = max_k |D_k| <= h <= U = max_k max(D_{k-1} + ha_k, hb_k - D_{k-1})
+//            (inside a bucket the difference moves by at most +ha_k / -hb_k from D_{k-1}).
+//   prune    L* = max over full-length slices of L.  A slice with U <= L* cannot beat L*; since the
+//            table is non-increasing from h0 on (host-checked) its p is >= table[L*].  The rest
+//            (typically a few of ~160), and always a shorter last slice, are flagged.
+//   exact    flagged slices only: their case samples are sorted (half-warp merge-split sorter, two
+//            slices per warp) and parked in SMEM, the control vector is staged again, the control
+//            samples are sorted and the exact integer h is evaluated against the parked case
+//            sample exactly as in k_step3h.  o[g] = min(table[L*], exact p-values).
+//
+// Bucket maps come from k_window3 (one map per gene for both classes: the two ECDFs are compared
+// on common edges).  A poor map only flags more slices; the result is always the exact minimum.
+#pragma once
+
+#include "step1p_impl.cuh"
+#include "step3h_impl.cuh"
+
+namespace phet {
+
+constexpr int kS3pThreads = 512;
+constexpr int kS3pHistBytes = 128;  // per slice and class: 127 one-byte counters
+
+struct Step3PairArgs {
+    Step3Args a;
+    const float2 *win;  // [G]: (scale, offset) of the common bucket map of the gene
+    int32_t vals_bytes; // SMEM bytes reserved for one class vector (multiple of 128)
+    int32_t ns_pad;     // n_slices rounded up to 32
+    int32_t store_cap;  // case samples that can be parked per batch
+    int32_t h0_full;    // table_full is non-increasing on [h0, m] and table[h0] <= table[h] for h < h0
+};
+
+// Exact integer KS statistic of two ascending samples of length n held in shared memory (sb padded
+// with +BIG up to npad entries): all 32 lanes take a-values; see k_step3h for the derivation.
+template <typename T, int NPAD>
+__device__ __forceinline__ int ks_h_sorted(const T *__restrict__ sa, const T *__restrict__ sb, int n, int lane) {
+    int hmax = 0;
+    constexpr int RA = (NPAD + 31) / 32;
+#pragma unroll
+    for (int r = 0; r < RA; ++r) {
+        const int p = lane + 32 * r;
+        if (p < n) {
+            const T v = sa[p];
+            const bool first = (p == 0) || (sa[p - 1] != v);
+            const bool last = (p == n - 1) || (sa[p + 1] != v);
+            int lo1 = 0;
+#pragma unroll
+            for (int step = next_pow2(NPAD + 1) / 2; step >= 1; step >>= 1) {
+                const int mid = lo1 + step;
+                if (mid <= NPAD && sb[mid - 1] < v) lo1 = mid;
+            }
+            int lo2 = lo1;
+            if (lo1 < n && sb[lo1] == v) {
+                lo2 = 0;
+#pragma unroll
+                for (int step = next_pow2(NPAD + 1) / 2; step >= 1; step >>= 1) {
+                    const int mid = lo2 + step;
+                    if (mid <= NPAD && sb[mid - 1] <= v) lo2 = mid;
+                }
+                lo2 = min(lo2, n);
+            }
+            if (last) hmax = max(hmax, abs(p + 1 - lo2));
+            if (first) hmax = max(hmax, abs(p - lo1));
+        }
+    }
+    return __reduce_max_sync(kFull, hmax);
+}
+
+// Histogram of one slice of one class (thread-private).  pos(j) is supplied by the caller.
+template <typename T, typename PosFn>
+__device__ __forceinline__ void s3p_hist(PosFn pos_of, int n, uint32_t vals_sa, uint32_t hbase, float scale, float off) {
+    constexpr float kTop = 4.0f * 32 - 1.5f;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+        uint32_t ad[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const T v = lds_pos(vals_sa, pos_of(j + u), T(0));
+            pair_bucket((float)v, scale, off, kTop, hbase, ad[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]);
+            sts_u8(ad[u], c0 + 1u);
+            sts_u8(ad[u + 1], c1 + 1u + (ad[u] == ad[u + 1] ? 1u : 0u));
+        }
+    }
+    for (; j < n; ++j) {
+        uint32_t ad;
+        const T v = lds_pos(vals_sa, pos_of(j), T(0));
+        pair_bucket((float)v, scale, off, kTop, hbase, ad);
+        sts_u8(ad, lds_u8(ad) + 1u);
+    }
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs pa) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Step3Args &a = pa.a;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const int grp = lane >> 4;
+    const int hl = lane & 15;
+    const int m = (int)a.m;
+    const int n_slices = (int)a.n_slices;
+    const int n_last = (int)a.n_last;
+    constexpr int NPAD = 16 * E;
+
+    // shared memory: [class vector | mbarrier | control words | flagged slice list | per-slice bounds |
+    //                 histograms (ha, hb: 2 x 4 KB per 32 slices) | per-warp sorted-a scratch | parked sorted-b samples]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + pa.vals_bytes);
+    int *ctl = reinterpret_cast<int *>(bar + 2);                  // [0] n_flagged, [1] L*, [2..3] p_min bits
+    unsigned long long *pmin_bits = reinterpret_cast<unsigned long long *>(ctl + 2);
+    int *red = ctl + 4;                                           // [nw] per-warp maxima
+    uint16_t *flagged = reinterpret_cast<uint16_t *>(red + 32);
+    int *bounds = reinterpret_cast<int *>(flagged + pa.ns_pad);   // (L << 16) | U per slice
+    unsigned char *hist_raw = reinterpret_cast<unsigned char *>(bounds + pa.ns_pad);
+    hist_raw = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hist_raw) + 127) & ~(uintptr_t)127);
+    T *scratch = reinterpret_cast<T *>(hist_raw + (size_t)(pa.ns_pad / 32) * 2 * 32 * kS3pHistBytes);
+    T *sa0 = scratch + (size_t)warp * (2 * NPAD);
+    T *store = scratch + (size_t)nw * (2 * NPAD);
+    // histograms of slice t: words interleaved by lane inside the 32-slice group
+    const uint32_t hA = smem_u32(hist_raw) + (uint32_t)(tid >> 5) * (2u * 32u * kS3pHistBytes) + (uint32_t)lane * 4u;
+    const uint32_t hB = hA + 32u * kS3pHistBytes;
+    const bool own_slice = tid < n_slices;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    if (tid < pa.ns_pad) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            sts_u32(hA + 128u * (uint32_t)i, 0u);
+            sts_u32(hB + 128u * (uint32_t)i, 0u);
+        }
+    }
+    __syncthreads();
+
+    unsigned phase = 0;
+    const HalfSortCoef<T> coef(hl);
+    const size_t b0c[2] = {0, ((size_t)a.n0 * sizeof(T)) & ~(size_t)15};
+    const size_t b1c[2] = {(((size_t)a.n0 * sizeof(T)) + 15) & ~(size_t)15, (((size_t)(a.n0 + a.n1) * sizeof(T)) + 15) & ~(size_t)15};
+    const uint32_t vsa[2] = {smem_u32(smem_raw), smem_u32(smem_raw) + (uint32_t)((size_t)a.n0 * sizeof(T) - b0c[1])};
+
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const unsigned char *row = static_cast<const unsigned char *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad * sizeof(T);
+        const float2 wn = __ldg(pa.win + g);
+        const uint32_t *permc[2] = {nullptr, nullptr};
+        AffinePerm ap[2] = {{1u, 0u, 1u}, {1u, 0u, 1u}};
+        if (a.perm_mode == PHET_PERM_DEVICE) {
+            ap[0] = make_affine(a.seed, (uint64_t)g, 0u, (uint32_t)a.n0, a.coprime0);
+            ap[1] = make_affine(a.seed, (uint64_t)g, 1u, (uint32_t)a.n1, a.coprime1);
+        } else {
+            permc[0] = a.perm0 + g * a.min_c;
+            permc[1] = a.perm1 + g * a.min_c;
+        }
+        auto stage = [&](int cls) {
+            __syncthreads();  // every read of the vector in residence is done
+            if (tid == 0) stage_row(smem_raw, row + b0c[cls], b1c[cls] - b0c[cls], bar);
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        };
+        // gather + sort (ascending, blocked layout, +BIG pads) of slice k of class cls by this half-warp
+        auto sort_slice = [&](int cls, int k, T *dst, bool valid) {  // whole warp must call (full-mask shuffles)
+            const int n = (k == n_slices - 1) ? n_last : m;
+            const uint32_t ncls = (uint32_t)(cls ? a.n1 : a.n0);
+            T x[E];
+            if (a.perm_mode == PHET_PERM_DEVICE) {
+                uint32_t xr = affine_at(ap[cls], (uint64_t)k * (uint64_t)m + (uint64_t)hl);
+                const uint32_t step_r = (uint32_t)((16ull * ap[cls].a) % ncls);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    x[r] = (hl + 16 * r < n) ? lds_pos(vsa[cls], xr, T(0)) : Big<T>::v();
+                    xr = add_mod(xr, step_r, ncls);
+                }
+            } else {
+                const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m;
+#pragma unroll
+                for (int r = 0; r < E; ++r) x[r] = (hl + 16 * r < n) ? lds_pos(vsa[cls], __ldg(pp + hl + 16 * r), T(0)) : Big<T>::v();
+            }
+            halfwarp_sort_asc<T, E>(x, coef);
+            if (valid) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) dst[hl * E + r] = x[r];
+            }
+        };
+
+        if (tid == 0) {
+            ctl[0] = 0;
+            *pmin_bits = 0x7FF0000000000000ull;  // +inf
+        }
+        // ---- phases 1 and 2: thread-per-slice histograms of the control and the case slices
+        for (int cls = 0; cls < 2; ++cls) {
+            stage(cls);
+            if (own_slice) {
+                const int k = tid;
+                const int n = (k == n_slices - 1) ? n_last : m;
+                const uint32_t hb_ = cls ? hB : hA;
+                if (a.perm_mode == PHET_PERM_DEVICE) {
+                    const uint32_t ncls = (uint32_t)(cls ? a.n1 : a.n0);
+                    const uint32_t stepj = ap[cls].a % ncls;
+                    uint32_t xr = affine_at(ap[cls], (uint64_t)k * (uint64_t)m);
+                    s3p_hist<T>([&](int) { const uint32_t q = xr; xr = add_mod(xr, stepj, ncls); return q; }, n, vsa[cls], hb_, wn.x, wn.y);
+                } else {
+                    const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m;
+                    s3p_hist<T>([&](int j) { return __ldg(pp + j); }, n, vsa[cls], hb_, wn.x, wn.y);
+                }
+            }
+        }
+        // ---- bounds on h from the two histograms; clear them for the next gene
+        int L = 0, U = 0;
+        if (own_slice) {
+            int D = 0;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t wa = lds_u32(hA + 128u * (uint32_t)i), wb = lds_u32(hB + 128u * (uint32_t)i);
+                sts_u32(hA + 128u * (uint32_t)i, 0u);
+                sts_u32(hB + 128u * (uint32_t)i, 0u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ca = (int)((wa >> (8 * q)) & 255u), cb = (int)((wb >> (8 * q)) & 255u);
+                    U = max(U, max(D + ca, cb - D));
+                    D += ca - cb;
+                    L = max(L, abs(D));
+                }
+            }
+            bounds[tid] = (L << 16) | U;
+        }
+        const bool full_len = own_slice && !(tid == n_slices - 1 && n_last != m);
+        int lmax = __reduce_max_sync(kFull, full_len ? L : 0);
+        if (lane == 0) red[warp] = lmax;
+        __syncthreads();
+        int Lstar = 0;
+        for (int w = 0; w < nw; ++w) Lstar = max(Lstar, red[w]);
+        if (own_slice) {
+            const bool need = !full_len || U > Lstar || Lstar < pa.h0_full;
+            if (need) flagged[atomicAdd(&ctl[0], 1)] = (uint16_t)tid;
+        }
+        __syncthreads();
+        const int nflag = ctl[0];
+        // ---- exact h of the flagged slices, in batches of store_cap
+        for (int base = 0; base < nflag; base += pa.store_cap) {
+            const int nb = min(pa.store_cap, nflag - base);
+            if (base > 0) stage(1);
+            // case samples: two slices per warp trip (one per half-warp), parked in SMEM
+            for (int i0 = 2 * warp; i0 < nb; i0 += 2 * nw) {
+                const int i = min(i0 + grp, nb - 1);
+                sort_slice(1, (int)flagged[base + i], store + (size_t)i * NPAD, i0 + grp < nb);
+            }
+            stage(0);
+            for (int i0 = 2 * warp; i0 < nb; i0 += 2 * nw) {
+                const int i = min(i0 + grp, nb - 1);
+                sort_slice(0, (int)flagged[base + i], sa0 + (size_t)grp * NPAD, i0 + grp < nb);
+                __syncwarp();
+#pragma unroll 1
+                for (int u = 0; u < 2; ++u) {
+                    if (i0 + u < nb) {
+                        const int k = (int)flagged[base + i0 + u];
+                        const bool is_last = (k == n_slices - 1);
+                        const int n = is_last ? n_last : m;
+                        const int h = ks_h_sorted<T, NPAD>(sa0 + (size_t)u * NPAD, store + (size_t)(i0 + u) * NPAD, n, lane);
+                        if (lane == 0) {
+                            const double pv = (n == m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
+                            atomicMin(pmin_bits, (unsigned long long)__double_as_longlong(pv));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double o = __longlong_as_double((long long)*pmin_bits);
+            if (Lstar >= pa.h0_full) o = fmin(o, __ldg(a.tab_full + Lstar));  // some full slice reaches at least L*
+            a.o[g] = o;
+        }
+    }
+}
+
+// Common bucket map of a gene for Step 3: one warp sorts 256 + 256 cells of the two classes and
+// maps the central 99 % of the pooled sample onto buckets 1 .. interior.
+template <typename T>
+__global__ void __launch_bounds__(256) k_window3(const void *__restrict__ xg, int64_t n_pad, int64_t xg_g0, int64_t g_begin,
+                                                 int64_t g_end, int64_t n0, int64_t n1, float interior,
+                                                 float2 *__restrict__ win) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = g_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= g_end) return;
+    const int h0 = (int)(n0 < 256 ? n0 : 256), h1 = (int)(n1 < 256 ? n1 : 256);
+    const int ns = h0 + h1;
+    const T *gene = static_cast<const T *>(xg) + (g - xg_g0) * n_pad;
+    T v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int k = lane + 32 * r;
+        v[r] = (k < h0) ? __ldg(gene + k) : ((k < ns) ? __ldg(gene + n0 + (k - h0)) : Lim<T>::inf());
+    }
+    warp_sort_asc<T, 16>(v, lane);
+    const int cut = ns / 200;
+    float lo = (float)warp_pick<T, 16>(v, cut);
+    float hi = (float)warp_pick<T, 16>(v, ns - 1 - cut);
+    if (!(hi > lo)) {
+        lo = (float)warp_pick<T, 16>(v, 0);
+        hi = (float)warp_pick<T, 16>(v, ns - 1);
+    }
+    float scale = 0.0f, off = 1.0f;
+    if (hi > lo) {
+        scale = interior / (hi - lo);
+        off = 1.0f - lo * scale;
+        if (!isfinite(scale) || !isfinite(off)) {
+            scale = 0.0f;
+            off = 1.0f;
+        }
+    }
+    if (lane == 0) win[g] = make_float2(scale, off);
+}
+
+struct S3pGeometry {
+    bool ok = false;
+    int vals_bytes = 0, ns_pad = 0, store_cap = 0;
+    size_t smem = 0;
+};
+
+template <typename T, int E>
+static S3pGeometry s3p_geometry(const Step3Args &a) {
+    S3pGeometry ge;
+    const int64_t nmax = a.n0 > a.n1 ? a.n0 : a.n1;
+    if (a.m < 1 || a.m > 255 || a.n_slices > kS3pThreads || a.n_slices < 1) return ge;
+    ge.vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
+    ge.ns_pad = (int)((a.n_slices + 31) / 32 * 32);
+    const size_t npad_b = (size_t)16 * E * sizeof(T);
+    const size_t fixed = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * (2 + 4) + 128 +
+                         (size_t)ge.ns_pad * 2 * kS3pHistBytes + (size_t)(kS3pThreads / 32) * 2 * npad_b;
+    if (fixed + 2 * npad_b > (size_t)kMaxSmemOptin) return ge;
+    int cap = (int)(((size_t)kMaxSmemOptin - fixed) / npad_b) - 1;
+    if (cap > a.n_slices) cap = (int)a.n_slices;
+    cap &= ~1;  // the two half-warps of a warp park neighbouring samples
+    if (cap < 2) {
+        if (a.n_slices == 1) cap = 1;
+        else return ge;
+    }
+    ge.store_cap = cap;
+    ge.smem = fixed + (size_t)(cap + 1) * npad_b;
+    ge.ok = ge.smem <= (size_t)kMaxSmemOptin;
+    return ge;
+}
+
+// Returns 1 when the path does not apply (caller falls back to the sorting kernels).
+template <typename T, int E>
+static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
+    const S3pGeometry ge = s3p_geometry<T, E>(args);
+    if (!ge.ok) return 1;
+    auto kern = k_step3p<T, E>;
+    PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
+    int per_sm = 0;
+    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kS3pThreads, ge.smem));
+    if (per_sm < 1) return 1;
+    const int64_t ng = args.g_end - args.g_begin;
+    int64_t grid = (int64_t)per_sm * c->num_sms;
+    if (grid > ng) grid = ng;
+    if (grid < 1) return 0;
+    if (int e = c->win3.alloc((size_t)c->G)) return e;
+    k_window3<T><<<(unsigned)((ng + 7) / 8), 256, 0, c->stream>>>(args.xg, args.n_pad, args.xg_g0, args.g_begin, args.g_end,
+                                                              args.n0, args.n1, 125.0f, c->win3.p);
+    c->launches++;
+    Step3PairArgs pa;
+    pa.a = args;
+    pa.a.H = nullptr;
+    pa.win = c->win3.p;
+    pa.vals_bytes = ge.vals_bytes;
+    pa.ns_pad = ge.ns_pad;
+    pa.store_cap = ge.store_cap;
+    pa.h0_full = c->tab_h0;
+    kern<<<(unsigned)grid, kS3pThreads, ge.smem, c->stream>>>(pa);
+    c->launches++;
+    c->step3_path = 3;
+    PHET_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int run_step3_prune(phet_ctx *c, const Step3Args &args) {
+    if (c->keep_H || c->step3_impl == 1 || c->tab_h0 < 0) return 1;
+    const int need = (int)((args.m + 15) / 16);
+    if (need <= 1) return launch_step3p_E<T, 1>(c, args);
+    if (need <= 2) return launch_step3p_E<T, 2>(c, args);
+    if (need <= 3) return launch_step3p_E<T, 3>(c, args);
+    if (need <= 4) return launch_step3p_E<T, 4>(c, args);
+    if (need <= 5) return launch_step3p_E<T, 5>(c, args);
+    if (need <= 6) return launch_step3p_E<T, 6>(c, args);
+    if (need <= 7) return launch_step3p_E<T, 7>(c, args);
+    if (need <= 8) return launch_step3p_E<T, 8>(c, args);
+    if (need <= 9) return launch_step3p_E<T, 9>(c, args);
+    if (need <= 10) return launch_step3p_E<T, 10>(c, args);
+    if (need <= 12) return launch_step3p_E<T, 12>(c, args);
+    return launch_step3p_E<T, 16>(c, args);
+}
+
+}  // namespace phet

@@ -240,6 +240,7 @@ class PHet:
         else:
             g_range = g3_range = shard_range(G, rank, world)
             s_range = (0, S)
+        ctx.set_option(_capi.OPT_KEEP_H, 1 if self.capture else 0)   # per-slice KS statistics only for capture
         ctx.set_classes(examples_i, examples_j)
         ctx.set_index_sets(idx)
         prm = self._step1_params(X.dtype, m)
@@ -263,13 +264,14 @@ class PHet:
         self.index_sets_ = idx
         self.launches_ = ctx.launch_count()
         self.step1_geometry_ = ctx.step1_geometry()
+        self.step3_path_ = ctx.step3_path()
+        self.o_ = ctx.read(_capi.BUF_O, np.float64, (G,))           # min-over-slices KS p-value per gene
         if self.capture:
             self.layout_rows_ = ctx.read(_capi.BUF_ROWS, np.int32, (N,))
             self.device_seed_ = seed
             self.fsum_, self.rsum_ = ctx.read(_capi.BUF_ACC, np.float64, (2, G))
             self.f_ = ctx.read(_capi.BUF_F, np.float64, (G,))
             self.r_ = ctx.read(_capi.BUF_R, np.float64, (G,))
-            self.o_ = ctx.read(_capi.BUF_O, np.float64, (G,))
             self.H_ = ctx.read(_capi.BUF_H, np.int32, (G, n_slices))
             self.bins_ = ctx.read(_capi.BUF_BINS, np.int8, (G,))
             self.edges_ = edges

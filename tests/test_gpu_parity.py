@@ -228,3 +228,34 @@ def test_step1_pair_path_equals_sort_path(name, dt, monkeypatch):
         assert got[2]["path"] == "pair-per-thread" and got[2]["E"] == buckets
         assert np.array_equal(got[0], ref[0]), "delta-IQR differs between the select and the sort path"
         assert np.allclose(got[1], ref[1], rtol=1e-11, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_step3_prune_path_matches_reference(name):
+    """Without capture Step 3 runs the bound-and-prune kernel (histogram bounds on h, exact evaluation of
+    the slices that can attain the minimum p only): o must still be bit-exact, bins and counts identical."""
+    g = load_golden(name)
+    for tag in g["dtypes"]:
+        est, scores = _run(g, tag, capture=False)
+        assert est.step3_path_ == "bound-and-prune", est.step3_path_
+        assert np.array_equal(est.o_, g[f"o_{tag}"]), "o must be bit-exact"
+        assert np.array_equal(est.bin_counts_, g[f"bin_counts_{tag}"])
+        assert np.allclose(scores, g[f"scores_{tag}"], rtol=RTOL[tag], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(_adversarial_cases()))
+@pytest.mark.parametrize("perm", ["device", "reference"])
+def test_step3_prune_path_equals_sort_path(name, perm, monkeypatch):
+    from phet_b200 import PHet
+    X, n0, kw = _adversarial_cases()[name]
+    X = np.ascontiguousarray(X.astype(np.float64))
+    y = np.r_[np.zeros(n0, dtype=np.int64), np.ones(X.shape[0] - n0, dtype=np.int64)]
+    out = {}
+    for impl in ("auto", "sort"):
+        monkeypatch.setenv("PHET_STEP3_IMPL", impl)
+        np.random.seed(5)
+        est = PHet(**kw, capture=False, distributed=False, permutation=perm)
+        est.fit_predict(X, y)
+        out[impl] = (est.o_.copy(), est.step3_path_)
+    assert out["auto"][1] == "bound-and-prune" and out["sort"][1] != "bound-and-prune"
+    assert np.array_equal(out["auto"][0], out["sort"][0])
