@@ -56,7 +56,8 @@ typedef enum {
     PHET_BUF_XG = 9,       /* normalised gene-major matrix, storage dtype, [G][n_pad], class-grouped cells   */
     PHET_BUF_MEAN = 10,    /* double[G] column mean  */
     PHET_BUF_STD = 11,     /* double[G] column population sd */
-    PHET_BUF_ROWS = 12     /* int32[N]: original row held at each position of a gene-major row (the layout) */
+    PHET_BUF_ROWS = 12,    /* int32[N]: original row held at each position of a gene-major row (the layout) */
+    PHET_BUF_PROFILE = 13  /* uint64[16]: per-phase cycle counters of the Step-3 kernel, only with env PHET_PROFILE=1 */
 } phet_buffer;
 
 /* Order-statistic positions and lerp weights of the two percentiles, computed on the host

@@ -220,6 +220,9 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
         }
         c->own_stream = true;
     }
+    if (const char *pf = getenv("PHET_PROFILE")) {
+        if (atoi(pf) != 0 && c->prof.alloc(16) == 0) cudaMemset(c->prof.p, 0, 16 * sizeof(unsigned long long));
+    }
     if (int e = c->scalars.alloc(16)) {
         delete c;
         return e;
@@ -244,6 +247,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->win.release();
     c->pair_scratch.release();
     c->win3.release();
+    c->prof.release();
     c->acc.release();
     c->dbgP.release();
     c->dbgD.release();
@@ -643,6 +647,7 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_MEAN: *p = c->mean.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;
+        case PHET_BUF_PROFILE: *p = c->prof.p; *bytes = 16 * (int64_t)sizeof(unsigned long long); break;
         default:
             set_error("invalid: unknown buffer id");
             return PHET_ERR_INVALID;

@@ -95,6 +95,7 @@ struct phet_ctx {
     int pair_nbw = 0;                    // 0 auto, 16 / 32: forced histogram words (env PHET_STEP1_NBW, tests)
     phet::DevBuf<float2> win;            // [G][2] bucket map (scale, offset) per (gene, class)
     phet::DevBuf<double> pair_scratch;   // [grid][3][slots] control-class results awaiting the case sample
+    phet::DevBuf<unsigned long long> prof;  // [16] optional per-phase cycle counters (env PHET_PROFILE=1)
     phet::DevBuf<float2> win3;           // [G] common bucket map of a gene (bound-and-prune Step 3)
     bool keep_H = false;                 // phet_set_option(PHET_OPT_KEEP_H): per-slice KS statistics wanted
     int step3_impl = 0;                  // 0 auto, 1 sorting kernels only (env PHET_STEP3_IMPL=sort)

@@ -292,7 +292,17 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
             const size_t b0 = ((size_t)e0 * sizeof(T)) & ~(size_t)15;
             const size_t b1 = (((size_t)(e0 + ncls) * sizeof(T)) + 15) & ~(size_t)15;
             __syncthreads();  // every read of the previous class vector is done
-            if (tid == 0) stage_row(smem_raw, row + b0, b1 - b0, bar);
+            if (tid == 0) {
+                stage_row(smem_raw, row + b0, b1 - b0, bar);
+                // the vector staged next (this gene's case cells, or the control cells of the CTA's next gene)
+                // starts its trip from HBM to L2 now, under the work on this one
+                if (cls == 0) {
+                    const size_t c0 = ((size_t)pa.n0 * sizeof(T)) & ~(size_t)15;
+                    prefetch_row_l2(row + c0, ((((size_t)(pa.n0 + pa.n1) * sizeof(T)) + 15) & ~(size_t)15) - c0);
+                } else if (g + gridDim.x < a.g_end) {
+                    prefetch_row_l2(row + (size_t)gridDim.x * (size_t)a.n_pad * sizeof(T), (((size_t)pa.n0 * sizeof(T)) + 15) & ~(size_t)15);
+                }
+            }
             const uint32_t vals_sa = smem_u32(smem_raw) + (uint32_t)((size_t)e0 * sizeof(T) - b0);
             const float2 wn = __ldg(pa.win + (size_t)g * 2 + cls);
             mbar_wait(bar, phase);

@@ -170,7 +170,7 @@ static int launch_step3h_E(phet_ctx *c, const Step3Args &args) {
 }
 
 template <typename T>
-static int run_step3_prune(phet_ctx *c, const Step3Args &args);  // step3p_impl.cuh
+int run_step3_prune(phet_ctx *c, const Step3Args &args);  // step3p_impl.cuh, instantiated in step3p_f32.cu / step3p_f64.cu
 
 // Bound-and-prune path when it applies (step3p_impl.cuh); else m <= 256: half-warp path; larger m:
 // full-warp network (step3_impl.cuh).

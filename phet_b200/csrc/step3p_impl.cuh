@@ -38,6 +38,8 @@ struct Step3PairArgs {
     int32_t ns_pad;     // n_slices rounded up to 32
     int32_t store_cap;  // case samples that can be parked per batch
     int32_t h0_full;    // table_full is non-increasing on [h0, m] and table[h0] <= table[h] for h < h0
+    int32_t nwx;        // warps taking part in the exact phase (each owns a 4-sample scratch)
+    unsigned long long *prof;  // optional [8] cycle counters summed over CTAs (env PHET_PROFILE=1), else NULL
 };
 
 // Exact integer KS statistic of two ascending samples of length n held in shared memory (sb padded
@@ -89,10 +91,18 @@ __device__ __forceinline__ void s3p_hist(PosFn pos_of, int n, uint32_t vals_sa, 
             pair_bucket((float)v, scale, off, kTop, hbase, ad[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]);
+        for (int u = 0; u < 8; u += 4) {
+            // four histogram updates in flight: all counters are read before any is written; a later element
+            // of the group adds the number of earlier ones that share its counter (stores land in order)
+            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]), c2 = lds_u8(ad[u + 2]), c3 = lds_u8(ad[u + 3]);
+            const uint32_t e1 = (ad[u + 1] == ad[u]) ? 1u : 0u;
+            const uint32_t e2 = ((ad[u + 2] == ad[u]) ? 1u : 0u) + ((ad[u + 2] == ad[u + 1]) ? 1u : 0u);
+            const uint32_t e3 = ((ad[u + 3] == ad[u]) ? 1u : 0u) + ((ad[u + 3] == ad[u + 1]) ? 1u : 0u) +
+                                ((ad[u + 3] == ad[u + 2]) ? 1u : 0u);
             sts_u8(ad[u], c0 + 1u);
-            sts_u8(ad[u + 1], c1 + 1u + (ad[u] == ad[u + 1] ? 1u : 0u));
+            sts_u8(ad[u + 1], c1 + 1u + e1);
+            sts_u8(ad[u + 2], c2 + 1u + e2);
+            sts_u8(ad[u + 3], c3 + 1u + e3);
         }
     }
     for (; j < n; ++j) {
@@ -103,7 +113,8 @@ __device__ __forceinline__ void s3p_hist(PosFn pos_of, int n, uint32_t vals_sa, 
     }
 }
 
-template <typename T, int E>
+// P threads (lanes of one warp) share a slice in phases 1 and 2; each takes every P-th element.
+template <typename T, int E, int P>
 __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Step3Args &a = pa.a;
@@ -128,24 +139,27 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
     int *bounds = reinterpret_cast<int *>(flagged + pa.ns_pad);   // (L << 16) | U per slice
     unsigned char *hist_raw = reinterpret_cast<unsigned char *>(bounds + pa.ns_pad);
     hist_raw = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hist_raw) + 127) & ~(uintptr_t)127);
-    T *scratch = reinterpret_cast<T *>(hist_raw + (size_t)(pa.ns_pad / 32) * 2 * 32 * kS3pHistBytes);
-    T *sa0 = scratch + (size_t)warp * (2 * NPAD);
-    T *store = scratch + (size_t)nw * (2 * NPAD);
-    // histograms of slice t: words interleaved by lane inside the 32-slice group
-    const uint32_t hA = smem_u32(hist_raw) + (uint32_t)(tid >> 5) * (2u * 32u * kS3pHistBytes) + (uint32_t)lane * 4u;
-    const uint32_t hB = hA + 32u * kS3pHistBytes;
-    const bool own_slice = tid < n_slices;
+    // per-lane histogram (words interleaved by lane inside the warp: bank == lane), then the merged control
+    // histograms of all slices (pitch 132 bytes: consecutive slices start in consecutive banks)
+    constexpr int SL = 32 / P;  // slices per warp in phases 1 and 2
+    constexpr uint32_t kMergedPitch = kS3pHistBytes + 4;
+    const uint32_t hmine = smem_u32(hist_raw) + (uint32_t)warp * (32u * kS3pHistBytes) + (uint32_t)lane * 4u;
+    const int nwh = (n_slices + SL - 1) / SL;  // warps that build histograms
+    const uint32_t hmerged = smem_u32(hist_raw) + (uint32_t)nwh * (32u * kS3pHistBytes);
+    T *scratch = reinterpret_cast<T *>(hist_raw + (size_t)nwh * 32 * kS3pHistBytes + (size_t)pa.ns_pad * kMergedPitch);
+    T *sa0 = scratch + (size_t)warp * (4 * NPAD);  // sorted control samples of two slices, then their case samples
+    const int my_slice = warp * SL + lane / P;  // phases 1 and 2
+    const int my_part = lane % P;
+    const bool hist_lane = lane < SL * P && my_slice < n_slices;
+    const bool own_slice = tid < n_slices;      // bounds: one thread per slice, densely packed
 
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
-    if (tid < pa.ns_pad) {
+    if (warp < nwh) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            sts_u32(hA + 128u * (uint32_t)i, 0u);
-            sts_u32(hB + 128u * (uint32_t)i, 0u);
-        }
+        for (int i = 0; i < 32; ++i) sts_u32(hmine + 128u * (uint32_t)i, 0u);
     }
     __syncthreads();
 
@@ -169,11 +183,21 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
         }
         auto stage = [&](int cls) {
             __syncthreads();  // every read of the vector in residence is done
-            if (tid == 0) stage_row(smem_raw, row + b0c[cls], b1c[cls] - b0c[cls], bar);
+            if (tid == 0) {
+                stage_row(smem_raw, row + b0c[cls], b1c[cls] - b0c[cls], bar);
+                // the vector staged next (this gene's case cells, or the control cells of the CTA's next gene)
+                // starts its trip from HBM to L2 now
+                if (cls == 0) prefetch_row_l2(row + b0c[1], b1c[1] - b0c[1]);
+                else if (g + gridDim.x < a.g_end)
+                    prefetch_row_l2(row + (size_t)gridDim.x * (size_t)a.n_pad * sizeof(T), b1c[0] - b0c[0]);
+            }
             mbar_wait(bar, phase);
             phase ^= 1u;
         };
         // gather + sort (ascending, blocked layout, +BIG pads) of slice k of class cls by this half-warp
+        // (control values are gathered from global memory -- the row was just staged, so it sits in L2 -- because
+        // the case vector is the one in residence when the flagged slices are known)
+        const T *gene0 = reinterpret_cast<const T *>(row);
         auto sort_slice = [&](int cls, int k, T *dst, bool valid) {  // whole warp must call (full-mask shuffles)
             const int n = (k == n_slices - 1) ? n_last : m;
             const uint32_t ncls = (uint32_t)(cls ? a.n1 : a.n0);
@@ -183,13 +207,16 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
                 const uint32_t step_r = (uint32_t)((16ull * ap[cls].a) % ncls);
 #pragma unroll
                 for (int r = 0; r < E; ++r) {
-                    x[r] = (hl + 16 * r < n) ? lds_pos(vsa[cls], xr, T(0)) : Big<T>::v();
+                    x[r] = (hl + 16 * r < n) ? (cls ? lds_pos(vsa[1], xr, T(0)) : __ldg(gene0 + xr)) : Big<T>::v();
                     xr = add_mod(xr, step_r, ncls);
                 }
             } else {
                 const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m;
 #pragma unroll
-                for (int r = 0; r < E; ++r) x[r] = (hl + 16 * r < n) ? lds_pos(vsa[cls], __ldg(pp + hl + 16 * r), T(0)) : Big<T>::v();
+                for (int r = 0; r < E; ++r) {
+                    const uint32_t q = (hl + 16 * r < n) ? __ldg(pp + hl + 16 * r) : 0u;
+                    x[r] = (hl + 16 * r < n) ? (cls ? lds_pos(vsa[1], q, T(0)) : __ldg(gene0 + q)) : Big<T>::v();
+                }
             }
             halfwarp_sort_asc<T, E>(x, coef);
             if (valid) {
@@ -202,33 +229,70 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
             ctl[0] = 0;
             *pmin_bits = 0x7FF0000000000000ull;  // +inf
         }
-        // ---- phases 1 and 2: thread-per-slice histograms of the control and the case slices
+        long long t_mark = (pa.prof != nullptr && tid == 0) ? clock64() : 0;
+        auto mark = [&](int slot) {  // thread 0: cycles since the previous mark -> prof[slot]
+            if (pa.prof != nullptr && tid == 0) {
+                const long long t = clock64();
+                atomicAdd(pa.prof + slot, (unsigned long long)(t - t_mark));
+                t_mark = t;
+            }
+        };
+        // ---- phases 1 and 2: histograms of the control and the case slices, P lanes per slice
         for (int cls = 0; cls < 2; ++cls) {
             stage(cls);
-            if (own_slice) {
-                const int k = tid;
+            mark(cls ? 2 : 0);
+            if (hist_lane) {
+                const int k = my_slice;
                 const int n = (k == n_slices - 1) ? n_last : m;
-                const uint32_t hb_ = cls ? hB : hA;
+                const int npart = (n - my_part + P - 1) / P;  // elements my_part, my_part + P, ...
                 if (a.perm_mode == PHET_PERM_DEVICE) {
                     const uint32_t ncls = (uint32_t)(cls ? a.n1 : a.n0);
-                    const uint32_t stepj = ap[cls].a % ncls;
-                    uint32_t xr = affine_at(ap[cls], (uint64_t)k * (uint64_t)m);
-                    s3p_hist<T>([&](int) { const uint32_t q = xr; xr = add_mod(xr, stepj, ncls); return q; }, n, vsa[cls], hb_, wn.x, wn.y);
+                    const uint32_t stepj = (uint32_t)(((uint64_t)P * ap[cls].a) % ncls);
+                    uint32_t xr = affine_at(ap[cls], (uint64_t)k * (uint64_t)m + (uint64_t)my_part);
+                    s3p_hist<T>([&](int) { const uint32_t q = xr; xr = add_mod(xr, stepj, ncls); return q; }, npart, vsa[cls], hmine, wn.x, wn.y);
                 } else {
-                    const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m;
-                    s3p_hist<T>([&](int j) { return __ldg(pp + j); }, n, vsa[cls], hb_, wn.x, wn.y);
+                    const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m + my_part;
+                    s3p_hist<T>([&](int j) { return __ldg(pp + j * P); }, npart, vsa[cls], hmine, wn.x, wn.y);
                 }
             }
+            if (cls == 0) {
+                // control counts of a slice: sum of its P lanes' histograms, parked in the merged area so that
+                // the lanes' own histograms can take the case counts
+                __syncwarp();
+                if (hist_lane && my_part == 0) {
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        uint32_t w = lds_u32(hmine + 128u * (uint32_t)i);
+#pragma unroll
+                        for (int q = 1; q < P; ++q) w += lds_u32(hmine + 128u * (uint32_t)i + 4u * (uint32_t)q);  // bytes <= 255 in total
+                        sts_u32(hmerged + (uint32_t)my_slice * kMergedPitch + 4u * (uint32_t)i, w);
+                    }
+                }
+                __syncwarp();
+                if (warp < nwh) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sts_u32(hmine + 128u * (uint32_t)i, 0u);
+                }
+                mark(1);
+            }
         }
-        // ---- bounds on h from the two histograms; clear them for the next gene
+        mark(3);  // (phase 2 of thread 0's own warp)
+        __syncthreads();  // the bounds are taken by one thread per slice, across the warps that built the histograms
+        mark(4);
+        // ---- bounds on h from the two histograms; clear the case counts for the next gene
         int L = 0, U = 0;
         if (own_slice) {
+            const uint32_t hb0 = smem_u32(hist_raw) + (uint32_t)(tid / SL) * (32u * kS3pHistBytes) + (uint32_t)((tid % SL) * P) * 4u;
             int D = 0;
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
-                const uint32_t wa = lds_u32(hA + 128u * (uint32_t)i), wb = lds_u32(hB + 128u * (uint32_t)i);
-                sts_u32(hA + 128u * (uint32_t)i, 0u);
-                sts_u32(hB + 128u * (uint32_t)i, 0u);
+                const uint32_t wa = lds_u32(hmerged + (uint32_t)tid * kMergedPitch + 4u * (uint32_t)i);
+                uint32_t wb = 0u;
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    wb += lds_u32(hb0 + 128u * (uint32_t)i + 4u * (uint32_t)q);
+                    sts_u32(hb0 + 128u * (uint32_t)i + 4u * (uint32_t)q, 0u);
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int ca = (int)((wa >> (8 * q)) & 255u), cb = (int)((wb >> (8 * q)) & 255u);
@@ -237,7 +301,6 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
                     L = max(L, abs(D));
                 }
             }
-            bounds[tid] = (L << 16) | U;
         }
         const bool full_len = own_slice && !(tid == n_slices - 1 && n_last != m);
         int lmax = __reduce_max_sync(kFull, full_len ? L : 0);
@@ -251,37 +314,32 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
         }
         __syncthreads();
         const int nflag = ctl[0];
-        // ---- exact h of the flagged slices, in batches of store_cap
-        for (int base = 0; base < nflag; base += pa.store_cap) {
-            const int nb = min(pa.store_cap, nflag - base);
-            if (base > 0) stage(1);
-            // case samples: two slices per warp trip (one per half-warp), parked in SMEM
-            for (int i0 = 2 * warp; i0 < nb; i0 += 2 * nw) {
-                const int i = min(i0 + grp, nb - 1);
-                sort_slice(1, (int)flagged[base + i], store + (size_t)i * NPAD, i0 + grp < nb);
-            }
-            stage(0);
-            for (int i0 = 2 * warp; i0 < nb; i0 += 2 * nw) {
-                const int i = min(i0 + grp, nb - 1);
-                sort_slice(0, (int)flagged[base + i], sa0 + (size_t)grp * NPAD, i0 + grp < nb);
-                __syncwarp();
+        mark(5);
+        // ---- exact h of the flagged slices: two per warp trip (one per half-warp), both samples sorted into the
+        //      warp's scratch, then all 32 lanes evaluate each pair of sorted samples
+        for (int i0 = 2 * warp; i0 < nflag && warp < pa.nwx; i0 += 2 * pa.nwx) {
+            const int i = min(i0 + grp, nflag - 1);
+            const int kk = (int)flagged[i];
+            sort_slice(1, kk, sa0 + (size_t)(2 + grp) * NPAD, true);
+            sort_slice(0, kk, sa0 + (size_t)grp * NPAD, true);
+            __syncwarp();
 #pragma unroll 1
-                for (int u = 0; u < 2; ++u) {
-                    if (i0 + u < nb) {
-                        const int k = (int)flagged[base + i0 + u];
-                        const bool is_last = (k == n_slices - 1);
-                        const int n = is_last ? n_last : m;
-                        const int h = ks_h_sorted<T, NPAD>(sa0 + (size_t)u * NPAD, store + (size_t)(i0 + u) * NPAD, n, lane);
-                        if (lane == 0) {
-                            const double pv = (n == m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
-                            atomicMin(pmin_bits, (unsigned long long)__double_as_longlong(pv));
-                        }
+            for (int u = 0; u < 2; ++u) {
+                if (i0 + u < nflag) {
+                    const int k = (int)flagged[i0 + u];
+                    const int n = (k == n_slices - 1) ? n_last : m;
+                    const int h = ks_h_sorted<T, NPAD>(sa0 + (size_t)u * NPAD, sa0 + (size_t)(2 + u) * NPAD, n, lane);
+                    if (lane == 0) {
+                        const double pv = (n == m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
+                        atomicMin(pmin_bits, (unsigned long long)__double_as_longlong(pv));
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         }
+        mark(6);
         __syncthreads();
+        mark(7);
         if (tid == 0) {
             double o = __longlong_as_double((long long)*pmin_bits);
             if (Lstar >= pa.h0_full) o = fmin(o, __ldg(a.tab_full + Lstar));  // some full slice reaches at least L*
@@ -330,40 +388,45 @@ __global__ void __launch_bounds__(256) k_window3(const void *__restrict__ xg, in
 
 struct S3pGeometry {
     bool ok = false;
-    int vals_bytes = 0, ns_pad = 0, store_cap = 0;
+    int vals_bytes = 0, ns_pad = 0, P = 1, nwx = 0;
     size_t smem = 0;
 };
 
+// Largest (lanes per slice, exact-phase warps) combination whose shared memory fits.
 template <typename T, int E>
 static S3pGeometry s3p_geometry(const Step3Args &a) {
     S3pGeometry ge;
     const int64_t nmax = a.n0 > a.n1 ? a.n0 : a.n1;
-    if (a.m < 1 || a.m > 255 || a.n_slices > kS3pThreads || a.n_slices < 1) return ge;
+    if (a.m < 1 || a.m > 255 || a.n_slices < 1) return ge;
     ge.vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
     ge.ns_pad = (int)((a.n_slices + 31) / 32 * 32);
     const size_t npad_b = (size_t)16 * E * sizeof(T);
-    const size_t fixed = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * (2 + 4) + 128 +
-                         (size_t)ge.ns_pad * 2 * kS3pHistBytes + (size_t)(kS3pThreads / 32) * 2 * npad_b;
-    if (fixed + 2 * npad_b > (size_t)kMaxSmemOptin) return ge;
-    int cap = (int)(((size_t)kMaxSmemOptin - fixed) / npad_b) - 1;
-    if (cap > a.n_slices) cap = (int)a.n_slices;
-    cap &= ~1;  // the two half-warps of a warp park neighbouring samples
-    if (cap < 2) {
-        if (a.n_slices == 1) cap = 1;
-        else return ge;
+    for (int P = 3; P >= 1; P -= 2) {
+        const int SL = 32 / P;
+        if (a.n_slices > (kS3pThreads / 32) * SL) continue;
+        const size_t nwh = (size_t)((a.n_slices + SL - 1) / SL);
+        for (int nwx = kS3pThreads / 32; nwx >= 2; nwx >>= 1) {
+            const size_t smem = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * (2 + 4) + 128 +
+                                nwh * 32 * kS3pHistBytes + (size_t)ge.ns_pad * (kS3pHistBytes + 4) + (size_t)nwx * 4 * npad_b;
+            if (smem <= (size_t)kMaxSmemOptin) {
+                ge.P = P;
+                ge.nwx = nwx;
+                ge.smem = smem;
+                ge.ok = true;
+                return ge;
+            }
+        }
     }
-    ge.store_cap = cap;
-    ge.smem = fixed + (size_t)(cap + 1) * npad_b;
-    ge.ok = ge.smem <= (size_t)kMaxSmemOptin;
     return ge;
 }
 
 // Returns 1 when the path does not apply (caller falls back to the sorting kernels).
 template <typename T, int E>
 static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
+    // as many lanes per slice as the slice count allows (16 warps x 32/P slices)
     const S3pGeometry ge = s3p_geometry<T, E>(args);
     if (!ge.ok) return 1;
-    auto kern = k_step3p<T, E>;
+    auto kern = ge.P == 3 ? k_step3p<T, E, 3> : k_step3p<T, E, 1>;
     PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
     int per_sm = 0;
     PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kS3pThreads, ge.smem));
@@ -382,7 +445,9 @@ static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
     pa.win = c->win3.p;
     pa.vals_bytes = ge.vals_bytes;
     pa.ns_pad = ge.ns_pad;
-    pa.store_cap = ge.store_cap;
+    pa.store_cap = 0;
+    pa.nwx = ge.nwx;
+    pa.prof = c->prof.p;
     pa.h0_full = c->tab_h0;
     kern<<<(unsigned)grid, kS3pThreads, ge.smem, c->stream>>>(pa);
     c->launches++;
@@ -392,7 +457,7 @@ static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
 }
 
 template <typename T>
-static int run_step3_prune(phet_ctx *c, const Step3Args &args) {
+int run_step3_prune(phet_ctx *c, const Step3Args &args) {
     if (c->keep_H || c->step3_impl == 1 || c->tab_h0 < 0) return 1;
     const int need = (int)((args.m + 15) / 16);
     if (need <= 1) return launch_step3p_E<T, 1>(c, args);

@@ -166,6 +166,19 @@ __device__ __forceinline__ void stage_row(void *smem_dst, const void *gmem_src, 
     }
 }
 
+// Ask the TMA unit to pull `bytes` (multiple of 16, 16-byte aligned) into L2 without a destination:
+// the HBM read of the NEXT vector a CTA will stage then overlaps the work on the current one.
+__device__ __forceinline__ void prefetch_row_l2(const void *gmem_src, size_t bytes) {
+    constexpr unsigned kChunk = 32768;
+    size_t off = 0;
+    while (off < bytes) {
+        const unsigned n = static_cast<unsigned>(bytes - off < kChunk ? bytes - off : kChunk);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char *>(gmem_src) + off), "r"(n)
+                     : "memory");
+        off += n;
+    }
+}
+
 // =================================================================================================
 // Half-warp merge-split sorter (the fast path for m <= 256).
 //
