@@ -62,16 +62,62 @@ __global__ void k_remap_perm(uint32_t *__restrict__ perm, int64_t n, const int32
 
 // [S][2][m] grouped positions -> [2][nblk][mp][32] class-local positions, 16 bits each (mp = m rounded
 // up to 16, rows >= m are 0): the 32 subsamples of a block are adjacent, so a warp of k_step1p reads 64
-// contiguous bytes per element, and whole 16-element chunks can be loaded without bounds checks
+// contiguous bytes per element, and whole 16-element chunks can be loaded without bounds checks.
+//
+// The ORDER of the elements inside a subsample is free (every statistic of Step 1 is a function of the
+// set), so it is chosen to spread the warp's shared-memory gathers over the banks: at row r the
+// subsample in lane l prefers an element whose position is congruent to l + r (mod 32).  Lanes that get
+// their preferred residue hit 32 different banks; only the leftovers (~20 %) collide at random, which
+// brings the gather from ~3.5 to ~2 wavefronts.  One thread per (class, subsample); m <= 255.
 __global__ void k_build_idxT(const int32_t *__restrict__ idx, int64_t S, int64_t m, int64_t mp, int64_t n0, int64_t nblk,
                              uint16_t *__restrict__ idxT) {
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk][mp][32]
-    if (o >= 2 * nblk * mp * 32) return;
-    const int64_t sl = o & 31;
-    const int64_t j = (o >> 5) % mp;
-    const int64_t cb = (o >> 5) / mp;  // c * nblk + blk
-    const int64_t c = cb / nblk, s = (cb % nblk) * 32 + sl;
-    idxT[o] = (s < S && j < m) ? (uint16_t)(idx[(s * 2 + c) * m + j] - (c ? n0 : 0)) : (uint16_t)0;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk * 32]
+    if (t >= 2 * nblk * 32) return;
+    const int64_t c = t / (nblk * 32), s = t % (nblk * 32);
+    uint16_t *out = idxT + ((c * nblk + (s >> 5)) * mp) * 32 + (s & 31);  // row r at out[32 * r]
+    if (s >= S) {
+        for (int64_t r = 0; r < mp; ++r) out[32 * r] = 0;
+        return;
+    }
+    const int32_t *src = idx + (s * 2 + c) * m;
+    const int32_t off = c ? (int32_t)n0 : 0;
+    uint16_t sorted[256];   // positions grouped by residue mod 32
+    unsigned char start[33], left[32];
+    int cnt[32];
+    for (int b = 0; b < 32; ++b) cnt[b] = 0;
+    for (int64_t j = 0; j < m; ++j) cnt[(src[j] - off) & 31]++;
+    int acc = 0;
+    for (int b = 0; b < 32; ++b) {
+        start[b] = (unsigned char)acc;
+        left[b] = (unsigned char)cnt[b];
+        acc += cnt[b];
+        cnt[b] = 0;
+    }
+    start[32] = (unsigned char)acc;
+    for (int64_t j = 0; j < m; ++j) {
+        const int p = src[j] - off, b = p & 31;
+        sorted[start[b] + cnt[b]++] = (uint16_t)p;
+    }
+    const int lane = (int)(s & 31);
+    // pass 1: preferred residues; rows that cannot be served are marked with 0xFFFF
+    for (int64_t r = 0; r < m; ++r) {
+        const int d = (lane + (int)r) & 31;
+        if (left[d] > 0) {
+            --left[d];
+            out[32 * r] = sorted[start[d] + left[d]];
+        } else {
+            out[32 * r] = 0xFFFF;
+        }
+    }
+    // pass 2: leftovers fill the unserved rows
+    int b = 0;
+    for (int64_t r = 0; r < m; ++r) {
+        if (out[32 * r] != 0xFFFF) continue;
+        while (left[b] == 0) ++b;
+        --left[b];
+        out[32 * r] = sorted[start[b] + left[b]];
+    }
+    for (int64_t r = m; r < mp; ++r) out[32 * r] = 0;
 }
 
 static uint64_t gcd_u64(uint64_t a, uint64_t b) {
@@ -418,7 +464,7 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
         const int64_t mp = (m + 15) / 16 * 16;
         const int64_t nT = 2 * nblk * mp * 32;
         if (int e = c->idxT.alloc((size_t)nT)) return e;
-        k_build_idxT<<<(unsigned)((nT + 255) / 256), 256, 0, c->stream>>>(c->idx.p, S, m, mp, c->n0, nblk, c->idxT.p);
+        k_build_idxT<<<(unsigned)((2 * nblk * 32 + 63) / 64), 64, 0, c->stream>>>(c->idx.p, S, m, mp, c->n0, nblk, c->idxT.p);
         c->launches++;
         PHET_CUDA(cudaGetLastError());
         c->idxT_ok = true;

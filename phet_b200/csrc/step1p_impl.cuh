@@ -54,6 +54,7 @@ struct Step1PairArgs {
     int32_t bl_stride;     // bytes per thread of the bucket list (16 * odd)
     int32_t vals_bytes;    // SMEM bytes reserved for one class vector (multiple of 128)
     int64_t n0, n1;
+    unsigned long long *prof;  // optional [16] cycle counters (slots 8..15), env PHET_PROFILE=1, else NULL
 };
 
 // ---- explicit shared-window accesses (the scratch areas are addressed by byte arithmetic) ----
@@ -160,16 +161,23 @@ __device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint
         }
     }
 #pragma unroll
-    for (int u = 0; u < 16; u += 2) {
-        // two histogram updates in flight: both counters are read before either is written, and
-        // the second write accounts for the first when the two elements share a bucket
+    for (int u = 0; u < 16; u += 4) {
+        // four histogram updates in flight: all four counters are read before any is written; a later element
+        // of the group adds the number of earlier ones that share its counter (the stores land in order)
         if (!TAIL) {
-            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]);
+            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]), c2 = lds_u8(ad[u + 2]), c3 = lds_u8(ad[u + 3]);
+            const uint32_t e1 = (ad[u + 1] == ad[u]) ? 1u : 0u;
+            const uint32_t e2 = ((ad[u + 2] == ad[u]) ? 1u : 0u) + ((ad[u + 2] == ad[u + 1]) ? 1u : 0u);
+            const uint32_t e3 = ((ad[u + 3] == ad[u]) ? 1u : 0u) + ((ad[u + 3] == ad[u + 1]) ? 1u : 0u) +
+                                ((ad[u + 3] == ad[u + 2]) ? 1u : 0u);
             sts_u8(ad[u], c0 + 1u);
-            sts_u8(ad[u + 1], c1 + 1u + (ad[u] == ad[u + 1] ? 1u : 0u));
+            sts_u8(ad[u + 1], c1 + 1u + e1);
+            sts_u8(ad[u + 2], c2 + 1u + e2);
+            sts_u8(ad[u + 3], c3 + 1u + e3);
         } else {
-            if (j0 + u < m) sts_u8(ad[u], lds_u8(ad[u]) + 1u);
-            if (j0 + u + 1 < m) sts_u8(ad[u + 1], lds_u8(ad[u + 1]) + 1u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j0 + u + q < m) sts_u8(ad[u + q], lds_u8(ad[u + q]) + 1u);
         }
     }
     uint32_t pk[4];
@@ -307,7 +315,16 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
             const float2 wn = __ldg(pa.win + (size_t)g * 2 + cls);
             mbar_wait(bar, phase);
             phase ^= 1u;
+            if (pa.prof != nullptr && tid == 0) atomicAdd(pa.prof + 15, 1ull);  // class passes (for averaging)
 
+            long long t_mark = (pa.prof != nullptr && tid == 0) ? clock64() : 0;
+            auto mark = [&](int slot_) {  // thread 0: cycles since the previous mark -> prof[slot_]
+                if (pa.prof != nullptr && tid == 0) {
+                    const long long t = clock64();
+                    atomicAdd(pa.prof + slot_, (unsigned long long)(t - t_mark));
+                    t_mark = t;
+                }
+            };
             for (int r = 0; r < pa.rounds; ++r) {
                 const int slot = r * (int)blockDim.x + tid;
                 const int64_t s = a.s_begin + slot;
@@ -357,6 +374,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         sx = sxp[0] + sxp[1];
                         qx = qxp[0] + qxp[1];
                     }
+                    mark(8);
                     // ---- locate the four sorted positions in the histogram
                     uint32_t wi = 0, x = lds_u32(hbase), s4 = (x * 0x01010101u) >> 24;
                     int cum = 0;
@@ -387,6 +405,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     T tieL = T(0), tieH = T(0);
                     if (!smallL) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[0], (uint32_t)B[1], tieL);
                     if (!smallH) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[2], (uint32_t)B[3], tieH) || rescue;
+                    mark(9);
                     // ---- one pass over the bucket list: words holding an element of either bucket range become
                     //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
                     //      bits 0-5), compacted in place over the part of the list already consumed
@@ -413,6 +432,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             }
                         }
                     }
+                    mark(10);
                     // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
                     int nL = 0, nH = 0;
                     for (int i = 0; i < nrec; ++i) {
@@ -433,6 +453,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         }
                     }
                     rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
+                    mark(11);
                     // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
                     //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
                     {
@@ -456,6 +477,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             }
                         }
                     }
+                    mark(12);
                     // ---- sort the candidates of each range and read off the two ranks
                     T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
 #pragma unroll 1
@@ -507,6 +529,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
 #pragma unroll
                     for (int i = 0; i < NBW; ++i) sts_u32(hbase + 128u * (uint32_t)i, 0u);
                 }
+                mark(13);
                 // ---- rescue: warp-cooperative full sort of the samples that could not be bucket-selected
                 unsigned todo = __ballot_sync(kFull, rescue);
                 while (todo) {
@@ -548,6 +571,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         if (a.dbgP != nullptr) a.dbgP[g * a.dbg_ld + (s - a.s_begin)] = (p == p && !isinf(p)) ? p : 0.0;
                     }
                 }
+                mark(14);
             }
         }
         facc = warp_sum(facc);
@@ -701,6 +725,7 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     pa.vals_bytes = ge.vals_bytes;
     pa.n0 = c->n0;
     pa.n1 = c->n1;
+    pa.prof = c->prof.p;
     c->step1_geom[0] = (int32_t)grid;
     c->step1_geom[1] = ge.threads;
     c->step1_geom[2] = (int32_t)ge.smem;
