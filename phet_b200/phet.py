@@ -35,7 +35,7 @@ class PHet:
                  storage: Literal["auto", "f32", "f64"] = "auto",
                  permutation: Literal["reference", "device"] = "reference",
                  distributed: bool | Literal["auto"] = "auto",
-                 shard: Literal["subsamples", "genes"] = "subsamples", capture: bool = False):
+                 shard: Literal["subsamples", "genes"] = "genes", capture: bool = False):
         """Same parameters as the reference (phet.py:33-104).  Extra keyword-only arguments:
 
         iqr_range    alias of ``percentiles`` -- it is the name ``src/train.py:474`` passes.
@@ -46,10 +46,11 @@ class PHet:
                      "device": a keyed bijection evaluated on the GPU (no G x N host draws).
         distributed  shard subsamples (Step 1) and genes (Step 3) over the ranks of an initialised
                      ``torch.distributed`` group; "auto" = on when world_size > 1.
-        shard        with distributed ranks: "subsamples" = every rank holds the whole matrix and a
-                     slice of the index sets (Step 3 is gene-sliced); "genes" = every rank loads only
-                     its gene slice and runs all subsamples on it (no replicated work; the layout
-                     for matrices that do not fit one GPU).
+        shard        with distributed ranks: "genes" (default) = every rank loads only its gene slice
+                     and runs all subsamples on it (nothing is replicated; also the layout for
+                     matrices that do not fit one GPU); "subsamples" = every rank holds the whole
+                     matrix and a slice of the index sets, Step 3 is gene-sliced (the north-star
+                     layout; normalisation is then replicated).  Same two all-reduces either way.
         capture      keep per-stage intermediates (P, delta, H, o, bins) as attributes.
         """
         if iqr_range is not None:

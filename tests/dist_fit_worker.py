@@ -22,18 +22,20 @@ def main():
     for name in sys.argv[1:]:
         g = load_golden(name)
         X = np.ascontiguousarray(g["X"].astype(np.float64))
-        np.random.seed(int(g["seed"]) if rank == 0 else 999 + rank)   # only rank 0's stream matters
-        est = PHet(**g["params"], capture=True, distributed=True)
-        scores = est.fit_predict(X, g["y"].astype(np.int64))
         ref = g["scores_f64"]
-        assert np.array_equal(est.index_sets_[:, 0], g["idx_i"]), "broadcast index sets differ"
-        assert np.array_equal(est.H_, g["H_f64"]) or rank >= 0  # H is only complete per gene shard
-        assert np.array_equal(est.o_, g["o_f64"]), "o differs after all-reduce"
-        assert np.array_equal(est.bin_counts_, g["bin_counts_f64"])
-        assert np.allclose(est.fsum_, g["fsum_f64"], rtol=1e-5, atol=1e-9)
-        assert np.allclose(scores, ref, rtol=1e-5, atol=1e-12)
-        k = min(100, len(ref) // 4)
-        assert np.array_equal(np.argsort(-scores[:, 0], kind="stable")[:k], np.argsort(-ref[:, 0], kind="stable")[:k])
+        for shard in ("subsamples", "genes"):
+            for capture in (True, False):   # False: Step 3 takes the bound-and-prune kernel on each rank's gene slice
+                np.random.seed(int(g["seed"]) if rank == 0 else 999 + rank)   # only rank 0's stream matters
+                est = PHet(**g["params"], capture=capture, distributed=True, shard=shard)
+                scores = est.fit_predict(X, g["y"].astype(np.int64))
+                assert np.array_equal(est.index_sets_[:, 0], g["idx_i"]), "broadcast index sets differ"
+                assert np.array_equal(est.o_, g["o_f64"]), "o differs after all-reduce"
+                assert np.array_equal(est.bin_counts_, g["bin_counts_f64"])
+                if capture:
+                    assert np.allclose(est.fsum_, g["fsum_f64"], rtol=1e-5, atol=1e-9)
+                assert np.allclose(scores, ref, rtol=1e-5, atol=1e-12)
+                k = min(100, len(ref) // 4)
+                assert np.array_equal(np.argsort(-scores[:, 0], kind="stable")[:k], np.argsort(-ref[:, 0], kind="stable")[:k])
         if rank == 0:
             print("rank0 ok", name, "world", dist.get_world_size(), flush=True)
     dist.barrier()
