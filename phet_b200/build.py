@@ -51,8 +51,35 @@ def needs_build():
         return fh.read().strip() != _source_hash()
 
 
+def _deps(path, seen=None):
+    """Transitive closure of the quoted #includes of a source (paths relative to the including file)."""
+    import re
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', fh.read(), flags=re.M):
+            _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
+def _object_hash(src):
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(_deps(os.path.join(CSRC, src))):
+        with open(f, "rb") as fh:
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def _compile(src, verbose):
     obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+    stamp = obj + ".stamp"
+    want = _object_hash(src)
+    if not verbose and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return obj, ""   # this object's source and headers are unchanged
     cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -60,6 +87,8 @@ def _compile(src, verbose):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(want)
     return obj, r.stderr
 
 

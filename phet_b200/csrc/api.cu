@@ -397,6 +397,7 @@ static int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int norm
     c->N = N;
     c->G = G;
     c->storage = storage;
+    c->fast_moments = (storage == PHET_F32 && normalize == PHET_NORM_ZSCORE && getenv("PHET_EXACT_MOMENTS") == nullptr);
     const int64_t per16 = 16 / (int64_t)e_st;
     c->n_pad = (N + per16 - 1) / per16 * per16;
     c->xg_g0 = g_begin;

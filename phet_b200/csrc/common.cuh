@@ -92,6 +92,7 @@ struct phet_ctx {
     phet::DevBuf<uint16_t> idxT;         // [2][m][S] class-local positions (pair-per-thread Step 1)
     bool idxT_ok = false;
     int step1_impl = 0;                  // 0 auto, 1 warp sorters only (env PHET_STEP1_IMPL=warp)
+    bool fast_moments = false;           // float storage of z-scored data: fp32 chunk sums in k_step1p (set by prepare_matrix)
     int pair_nbw = 0;                    // 0 auto, 16 / 32: forced histogram words (env PHET_STEP1_NBW, tests)
     phet::DevBuf<float2> win;            // [G][2] bucket map (scale, offset) per (gene, class)
     phet::DevBuf<double> pair_scratch;   // [grid][3][slots] control-class results awaiting the case sample

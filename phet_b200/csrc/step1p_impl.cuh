@@ -32,6 +32,7 @@
 // thread-private global scratch line and combined when the same thread finishes the case sample.
 #pragma once
 
+#include "smem_prims.cuh"
 #include "step1_impl.cuh"
 
 namespace phet {
@@ -57,84 +58,11 @@ struct Step1PairArgs {
     unsigned long long *prof;  // optional [16] cycle counters (slots 8..15), env PHET_PROFILE=1, else NULL
 };
 
-// ---- explicit shared-window accesses (the scratch areas are addressed by byte arithmetic) ----
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v));
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v));
-}
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w));
-}
-__device__ __forceinline__ void sts_val(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
-}
-__device__ __forceinline__ void sts_val(uint32_t addr, double v) {
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
-}
-__device__ __forceinline__ float lds_val(uint32_t addr, float) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ double lds_val(uint32_t addr, double) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
-    return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
-}
-
-// Bucket of v and the shared-memory address of its counter.  t = v*scale + off, clamped to
-// top = 4*NBW - 1.5, is monotone non-decreasing in v (fma with scale >= 0, min, truncation and the
-// saturation of the conversion all are); below the window and NaN -> 0.  The counter of bucket b is
-// byte b%4 of word b/4, and the words of a thread sit 128 bytes apart (bank == lane: conflict-free).
-// (One conversion only: F2I runs on the quarter-rate XU pipe, which the fp64 conversions also use.)
-__device__ __forceinline__ uint32_t pair_bucket(float v, float scale, float off, float top, uint32_t hbase,
-                                                uint32_t &addr) {
-    const float t = fminf(fmaf(v, scale, off), top);
-    uint32_t b;
-    asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(b) : "f"(t));
-    addr = hist_addr(hbase, b);
-    return b;
-}
-
 // Bytes of w are bucket ids < 128.  Bit 7 of byte i of the result is set iff lo <= byte i <= hi
 // (lo4 = lo * 0x01010101, hi4h = hi * 0x01010101 | 0x80808080; no borrow crosses a byte).
 __device__ __forceinline__ uint32_t range_flags(uint32_t w, uint32_t lo4, uint32_t hi4h) {
     return ((w | 0x80808080u) - lo4) & (hi4h - w) & 0x80808080u;
 }
-
-// vals[pos] with the address formed by one IMAD (FMA pipe) instead of LEA (ALU pipe)
-__device__ __forceinline__ float lds_pos(uint32_t base, uint32_t pos, float) {
-    float v;
-    asm volatile("{\n.reg .u32 a;\nmad.lo.u32 a, %1, 4, %2;\nld.shared.f32 %0, [a];\n}" : "=f"(v) : "r"(pos), "r"(base));
-    return v;
-}
-__device__ __forceinline__ double lds_pos(uint32_t base, uint32_t pos, double) {
-    double v;
-    asm volatile("{\n.reg .u32 a;\nmad.lo.u32 a, %1, 8, %2;\nld.shared.f64 %0, [a];\n}" : "=d"(v) : "r"(pos), "r"(base));
-    return v;
-}
-
 
 // Indices of one 16-element chunk.  The index table is zero-padded to a multiple of 16 rows, so the
 // loads (and the gathers they feed) need no bounds predicate.
@@ -144,41 +72,55 @@ __device__ __forceinline__ void pair_load_pos(const uint16_t *__restrict__ ip, i
     for (int u = 0; u < 16; ++u) pos[u] = (uint32_t)__ldg(ipc + u * 32);
 }
 
-// One 16-element chunk of pass A on gathered values.  TAIL: elements j >= m are fillers.
-template <typename T, bool TAIL>
+// One 16-element chunk of pass A on gathered values.  TAIL: elements j >= m are fillers: they add 0 to
+// the moments, carry the filler id in the bucket list and count in a dummy byte (the last one of the
+// histogram, beyond every real bucket) -- selects, not branches.
+// FASTMOM (float storage of z-scored data): moments of the deviations d = v - c from the sample's first
+// element c; the chunk's sum of d and of d*d are formed in fp32 (two interleaved partial sums each) and
+// added to the fp64 accumulators once per chunk: 2 conversions per chunk instead of 16 on the
+// quarter-rate conversion pipe.  A sample of identical values gives exactly zero sums (so the zero-variance
+// cases of the reference stay exact); otherwise the relative error of the moments is ~1e-7, against the
+// 1e-3 tolerance of float storage.  fp64 storage and un-normalised data keep exact fp64 accumulation.
+template <typename T, bool TAIL, bool FASTMOM>
 __device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint32_t hbase, uint32_t blbase, float scale,
-                                           float off, float top, double (&sx)[2], double (&qx)[2]) {
+                                           float off, float top, uint32_t dummy, float cshift, double (&sx)[2],
+                                           double (&qx)[2]) {
     uint32_t b[16], ad[16];
+    float fs[2] = {0.0f, 0.0f}, fq[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-        b[u] = kPairPadId;
-        ad[u] = hbase;
-        if (!TAIL || j0 + u < m) {
-            const double vd = (double)v[u];
+        const bool ok = !TAIL || j0 + u < m;
+        if (FASTMOM) {
+            const float d = ok ? (float)v[u] - cshift : 0.0f;
+            fs[u & 1] += d;
+            fq[u & 1] = fmaf(d, d, fq[u & 1]);
+        } else {
+            const T vm = ok ? v[u] : T(0);
+            const double vd = (double)vm;
             sx[u & 1] += vd;
             qx[u & 1] = fma(vd, vd, qx[u & 1]);
-            b[u] = pair_bucket((float)v[u], scale, off, top, hbase, ad[u]);
         }
+        const uint32_t bb = pair_bucket((float)v[u], scale, off, top, hbase, ad[u]);
+        b[u] = ok ? bb : kPairPadId;
+        if (TAIL) ad[u] = ok ? ad[u] : dummy;
+    }
+    if (FASTMOM) {
+        sx[0] += (double)(fs[0] + fs[1]);
+        qx[0] += (double)(fq[0] + fq[1]);
     }
 #pragma unroll
     for (int u = 0; u < 16; u += 4) {
         // four histogram updates in flight: all four counters are read before any is written; a later element
         // of the group adds the number of earlier ones that share its counter (the stores land in order)
-        if (!TAIL) {
-            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]), c2 = lds_u8(ad[u + 2]), c3 = lds_u8(ad[u + 3]);
-            const uint32_t e1 = (ad[u + 1] == ad[u]) ? 1u : 0u;
-            const uint32_t e2 = ((ad[u + 2] == ad[u]) ? 1u : 0u) + ((ad[u + 2] == ad[u + 1]) ? 1u : 0u);
-            const uint32_t e3 = ((ad[u + 3] == ad[u]) ? 1u : 0u) + ((ad[u + 3] == ad[u + 1]) ? 1u : 0u) +
-                                ((ad[u + 3] == ad[u + 2]) ? 1u : 0u);
-            sts_u8(ad[u], c0 + 1u);
-            sts_u8(ad[u + 1], c1 + 1u + e1);
-            sts_u8(ad[u + 2], c2 + 1u + e2);
-            sts_u8(ad[u + 3], c3 + 1u + e3);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (j0 + u + q < m) sts_u8(ad[u + q], lds_u8(ad[u + q]) + 1u);
-        }
+        const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]), c2 = lds_u8(ad[u + 2]), c3 = lds_u8(ad[u + 3]);
+        const uint32_t e1 = (ad[u + 1] == ad[u]) ? 1u : 0u;
+        const uint32_t e2 = ((ad[u + 2] == ad[u]) ? 1u : 0u) + ((ad[u + 2] == ad[u + 1]) ? 1u : 0u);
+        const uint32_t e3 = ((ad[u + 3] == ad[u]) ? 1u : 0u) + ((ad[u + 3] == ad[u + 1]) ? 1u : 0u) +
+                            ((ad[u + 3] == ad[u + 2]) ? 1u : 0u);
+        sts_u8(ad[u], c0 + 1u);
+        sts_u8(ad[u + 1], c1 + 1u + e1);
+        sts_u8(ad[u + 2], c2 + 1u + e2);
+        sts_u8(ad[u + 3], c3 + 1u + e3);
     }
     uint32_t pk[4];
 #pragma unroll
@@ -252,7 +194,7 @@ __device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int
     return vmin == vmax;
 }
 
-template <typename T, int NBW>
+template <typename T, int NBW, bool FASTMOM>
 __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int CM = PairCand<T>::kMax;
@@ -264,6 +206,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
     const int m = (int)a.m;
     constexpr uint32_t kHistWarpBytes = 32u * 4u * NBW;
     constexpr float kTop = 4.0f * NBW - 1.5f;
+    constexpr bool kFast = FASTMOM && sizeof(T) == 4;
 
     // shared memory: [class vector | mbarrier | per-warp partials | histograms (128*NBW bytes per warp) | bucket lists]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + pa.vals_bytes);
@@ -271,6 +214,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
     unsigned char *hist_raw = reinterpret_cast<unsigned char *>(part + 2 * (kPairMaxThreads / 32));
     const uint32_t hbase = smem_u32(hist_raw) + (uint32_t)warp * kHistWarpBytes + (uint32_t)lane * 4u;
     const uint32_t blbase = smem_u32(hist_raw) + (uint32_t)nw * kHistWarpBytes + (uint32_t)tid * (uint32_t)pa.bl_stride;
+    const uint32_t hdummy = hist_addr(hbase, 4u * NBW - 1u);  // counter of the chunk fillers (beyond every real bucket)
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -339,6 +283,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     {
                         uint32_t pos[16], nxt[16];
                         pair_load_pos(ip, 0, pos);
+                        const float cshift = kFast ? (float)lds_pos(vals_sa, pos[0], T(0)) : 0.0f;
                         int j0 = 0;
                         for (; j0 + 32 <= m_full; j0 += 32) {  // two chunks per trip: the index buffers swap roles
                             pair_load_pos(ip, j0 + 16, nxt);
@@ -346,14 +291,14 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                                 T v[16];
 #pragma unroll
                                 for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
-                                pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                                pair_chunk<T, false, kFast>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                             }
                             if (j0 + 32 < m) pair_load_pos(ip, j0 + 32, pos);
                             {
                                 T v[16];
 #pragma unroll
                                 for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, nxt[u], T(0));
-                                pair_chunk<T, false>(v, j0 + 16, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                                pair_chunk<T, false, kFast>(v, j0 + 16, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                             }
                         }
                         if (j0 < m_full) {  // one more full chunk
@@ -361,7 +306,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             T v[16];
 #pragma unroll
                             for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
-                            pair_chunk<T, false>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                            pair_chunk<T, false, kFast>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
 #pragma unroll
                             for (int u = 0; u < 16; ++u) pos[u] = nxt[u];
                         }
@@ -369,10 +314,15 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             T v[16];
 #pragma unroll
                             for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
-                            pair_chunk<T, true>(v, m_full, m, hbase, blbase, wn.x, wn.y, kTop, sxp, qxp);
+                            pair_chunk<T, true, kFast>(v, m_full, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                         }
-                        sx = sxp[0] + sxp[1];
-                        qx = qxp[0] + qxp[1];
+                        // sx: sum of the sample; qx: sum of squared deviations from its mean
+                        const double sd = sxp[0] + sxp[1], qd = qxp[0] + qxp[1];
+                        double ss = qd - sd * sd * inv_n;
+                        if (!kFast && fabs(ss) <= 1e-15 * qd) ss = 0.0;  // identical values: exactly 0 like the two-pass variance
+                        if (kFast && ss < 0.0) ss = 0.0;  // fp32 rounding of a (near-)zero variance
+                        sx = sd + (double)m * (double)cshift;
+                        qx = ss;
                     }
                     mark(8);
                     // ---- locate the four sorted positions in the histogram
@@ -438,18 +388,15 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     for (int i = 0; i < nrec; ++i) {
                         const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
                         const int wj = (int)(rec & 63u) * 4;
-                        uint32_t fl = rec & 0x80808080u, fh = (rec << 1) & 0x80808080u;
-                        while (fl) {
-                            const int bit = __ffs((int)fl) - 1;
-                            fl &= fl - 1u;
-                            if (nL < CM) sts_u8(hist_addr(hbase, (uint32_t)nL), (uint32_t)(wj + (bit >> 3)));  // NBW >= 8
-                            ++nL;
-                        }
-                        while (fh) {
-                            const int bit = __ffs((int)fh) - 1;
-                            fh &= fh - 1u;
-                            if (nH < CM) sts_u8(hist_addr(hbase, 16u + (uint32_t)nH), (uint32_t)(wj + (bit >> 3)));
-                            ++nH;
+                        uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
+                        while (f) {
+                            const int bit = __ffs((int)f) - 1;
+                            f &= f - 1u;
+                            const bool hi = (bit & 1) == 0;
+                            const int cnt = hi ? nH : nL;
+                            if (cnt < CM) sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), (uint32_t)(wj + (bit >> 3)));  // NBW >= 8
+                            nH += hi ? 1 : 0;
+                            nL += hi ? 0 : 1;
                         }
                     }
                     rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
@@ -553,12 +500,8 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         scr[pa.slots + slot] = qx;
                         scr[2 * pa.slots + slot] = iq;
                     } else {
-                        const double sx0 = scr[slot], qx0 = scr[pa.slots + slot], iq0 = scr[2 * pa.slots + slot];
-                        double ss0 = qx0 - sx0 * sx0 * inv_n;
-                        if (fabs(ss0) <= 1e-15 * qx0) ss0 = 0.0;
-                        double ss1 = qx - sx * sx * inv_n;
-                        if (fabs(ss1) <= 1e-15 * qx) ss1 = 0.0;
-                        const double svar = (ss0 + ss1) * inv_df;
+                        const double sx0 = scr[slot], ss0 = scr[pa.slots + slot], iq0 = scr[2 * pa.slots + slot];
+                        const double svar = (ss0 + qx) * inv_df;
                         const double dmean = (sx0 - sx) * inv_n;
                         const double stat = dmean * rsqrt(svar * inv_pair);
                         double delta = fabs(iq0 - iq);
@@ -690,7 +633,9 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     const int64_t S_local = args.s_end - args.s_begin;
     const PairGeometry ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local, c->pair_nbw);
     if (ge.threads == 0) return 1;
-    auto kern = ge.nbw == 32 ? k_step1p<T, 32> : k_step1p<T, 16>;
+    const bool fast = c->fast_moments && sizeof(T) == 4;
+    auto kern = ge.nbw == 32 ? (fast ? k_step1p<T, 32, true> : k_step1p<T, 32, false>)
+                             : (fast ? k_step1p<T, 16, true> : k_step1p<T, 16, false>);
     PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
     int per_sm = 0;
     PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ge.threads, ge.smem));

@@ -23,7 +23,7 @@
 // on common edges).  A poor map only flags more slices; the result is always the exact minimum.
 #pragma once
 
-#include "step1p_impl.cuh"
+#include "smem_prims.cuh"
 #include "step3h_impl.cuh"
 
 namespace phet {

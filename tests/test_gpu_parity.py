@@ -227,7 +227,8 @@ def test_step1_pair_path_equals_sort_path(name, dt, monkeypatch):
         got = out[key]
         assert got[2]["path"] == "pair-per-thread" and got[2]["E"] == buckets
         assert np.array_equal(got[0], ref[0]), "delta-IQR differs between the select and the sort path"
-        assert np.allclose(got[1], ref[1], rtol=1e-11, atol=1e-300)
+        # float storage of z-scored data sums each 16-element chunk in fp32 (k_step1p FASTMOM): moments to ~1e-7
+        assert np.allclose(got[1], ref[1], rtol=1e-11 if dt == np.float64 else 2e-4, atol=1e-300)
 
 
 @pytest.mark.parametrize("name", NAMES)
