@@ -80,15 +80,18 @@ __global__ void k_colstats_final(const Tin *__restrict__ X, int64_t N, int64_t G
 
 // Tile of kTQ grouped positions x kTG genes.  A warp reads one source row at a time: 4 x 128
 // contiguous bytes (the rows of a class-grouped, shuffled layout are scattered over X, so wide
-// row segments are what keeps DRAM pages busy); a thread owns genes lane, lane+32, lane+64,
-// lane+96 so the transposed SMEM writes hit 32 distinct banks (tile pitch kTQ+1 is odd).  Each
-// gene row of the tile leaves as kTQ contiguous elements (2 per lane, 8- or 16-byte stores).
+// row segments are what keeps DRAM pages busy); a thread owns genes lane, lane+32, ..., so the
+// transposed SMEM writes hit 32 distinct banks (tile pitch kTQ+1 is odd).  Each gene row of the
+// tile leaves as kTQ contiguous elements (2 per lane, 8- or 16-byte stores).
+// z = (x - mu) * (1 / sd) in fp64: the reciprocal is taken once per gene (a per-element fp64 division
+// costs ~15 instructions); the map stays monotone in x, so ties and order are those of x.
 constexpr int kTQ = 64;
 constexpr int kTG = 128;
 constexpr int kNTThreads = 256;
+constexpr int kGPT = kTG / 32;  // genes per thread
 
 template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(kNTThreads)
+__global__ void __launch_bounds__(kNTThreads, 3)
     k_normalize_transpose(const Tin *__restrict__ X, int64_t ldx, int64_t N, int64_t G, int64_t n_pad,
                           const int32_t *__restrict__ rows_grouped, const double *__restrict__ mean,
                           const double *__restrict__ sd, int normalize, Tout *__restrict__ xg) {
@@ -97,15 +100,15 @@ __global__ void __launch_bounds__(kNTThreads)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g0 = (int64_t)blockIdx.x * kTG;
     const int64_t q0 = (int64_t)blockIdx.y * kTQ;
-    double mu[4], sg[4];
+    double mu[kGPT], rs[kGPT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kGPT; ++i) {
         const int64_t g = g0 + lane + 32 * i;
         mu[i] = 0.0;
-        sg[i] = 1.0;
+        rs[i] = 1.0;
         if (normalize && g < G) {
             mu[i] = mean[g];
-            sg[i] = sd[g];
+            rs[i] = 1.0 / sd[g];  // sd == 0 -> inf -> 0 * inf = NaN -> 0 below, like x / 0
         }
     }
     constexpr int kRowsPerWarp = kTQ / (kNTThreads / 32);
@@ -115,11 +118,11 @@ __global__ void __launch_bounds__(kNTThreads)
         const int64_t q = q0 + warp * kRowsPerWarp + r;
         src[r] = (q < N) ? (int64_t)rows_grouped[q] : (int64_t)-1;
     }
-    Tin x[kRowsPerWarp][4];
+    Tin x[kRowsPerWarp][kGPT];
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kGPT; ++i) {
             const int64_t g = g0 + lane + 32 * i;
             x[r][i] = (src[r] >= 0 && g < G) ? X[src[r] * ldx + g] : Tin(0);
         }
@@ -127,8 +130,8 @@ __global__ void __launch_bounds__(kNTThreads)
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double z = normalize ? ((double)x[r][i] - mu[i]) / sg[i] : (double)x[r][i];
+        for (int i = 0; i < kGPT; ++i) {
+            double z = normalize ? ((double)x[r][i] - mu[i]) * rs[i] : (double)x[r][i];
             if (!isfinite(z) || src[r] < 0) z = 0.0;  // nan_to_num(nan=0, posinf=0, neginf=0), phet.py:299
             tile[lane + 32 * i][warp * kRowsPerWarp + r] = (Tout)z;
         }

@@ -143,15 +143,15 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
     // histograms of all slices (pitch 132 bytes: consecutive slices start in consecutive banks)
     constexpr int SL = 32 / P;  // slices per warp in phases 1 and 2
     constexpr uint32_t kMergedPitch = kS3pHistBytes + 4;
-    const uint32_t hmine = smem_u32(hist_raw) + (uint32_t)warp * (32u * kS3pHistBytes) + (uint32_t)lane * 4u;
+    const uint32_t hwarp = smem_u32(hist_raw) + (uint32_t)warp * (32u * kS3pHistBytes);
+    const uint32_t hmine = hwarp + (uint32_t)lane * 4u;
     const int nwh = (n_slices + SL - 1) / SL;  // warps that build histograms
     const uint32_t hmerged = smem_u32(hist_raw) + (uint32_t)nwh * (32u * kS3pHistBytes);
     T *scratch = reinterpret_cast<T *>(hist_raw + (size_t)nwh * 32 * kS3pHistBytes + (size_t)pa.ns_pad * kMergedPitch);
-    T *sa0 = scratch + (size_t)warp * (4 * NPAD);  // sorted control samples of two slices, then their case samples
+    T *sa0 = scratch + (size_t)warp * (2 * NPAD);  // sorted control sample of a slice, then its case sample
     const int my_slice = warp * SL + lane / P;  // phases 1 and 2
     const int my_part = lane % P;
     const bool hist_lane = lane < SL * P && my_slice < n_slices;
-    const bool own_slice = tid < n_slices;      // bounds: one thread per slice, densely packed
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -256,84 +256,113 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
                 }
             }
             if (cls == 0) {
-                // control counts of a slice: sum of its P lanes' histograms, parked in the merged area so that
-                // the lanes' own histograms can take the case counts
+                // control counts of a slice: sum of its P lanes' histograms (each lane sums every P-th word),
+                // parked in the merged area so that the lanes' own histograms can take the case counts
                 __syncwarp();
-                if (hist_lane && my_part == 0) {
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        uint32_t w = lds_u32(hmine + 128u * (uint32_t)i);
+                if (hist_lane) {
+                    const uint32_t h0l = hmine - 4u * (uint32_t)my_part;  // lane of part 0 of my slice
+                    for (int i = my_part; i < 32; i += P) {
+                        uint32_t w = 0u;
 #pragma unroll
-                        for (int q = 1; q < P; ++q) w += lds_u32(hmine + 128u * (uint32_t)i + 4u * (uint32_t)q);  // bytes <= 255 in total
+                        for (int q = 0; q < P; ++q)  // (lane p starts with region p: the P lanes of a slice hit P banks)
+                            w += lds_u32(h0l + 128u * (uint32_t)i + 4u * (uint32_t)((q + my_part) % P));  // bytes <= 255 in total
                         sts_u32(hmerged + (uint32_t)my_slice * kMergedPitch + 4u * (uint32_t)i, w);
                     }
                 }
                 __syncwarp();
-                if (warp < nwh) {
+                if (warp < nwh) {  // the warp's 4 KB of histograms are contiguous: each lane clears 128 of them
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sts_u32(hmine + 128u * (uint32_t)i, 0u);
+                    for (int i = 0; i < 8; ++i) sts_v4(hwarp + 512u * (uint32_t)i + 16u * (uint32_t)lane, 0u, 0u, 0u, 0u);
                 }
+                __syncwarp();
                 mark(1);
             }
         }
         mark(3);  // (phase 2 of thread 0's own warp)
-        __syncthreads();  // the bounds are taken by one thread per slice, across the warps that built the histograms
-        mark(4);
-        // ---- bounds on h from the two histograms; clear the case counts for the next gene
+        // ---- bounds on h from the two histograms, by the P lanes of the slice: lane p takes the words
+        //      [w0, w1) of the 32, after an exclusive prefix of the per-lane totals of (ha - hb)
+        __syncwarp();
         int L = 0, U = 0;
-        if (own_slice) {
-            const uint32_t hb0 = smem_u32(hist_raw) + (uint32_t)(tid / SL) * (32u * kS3pHistBytes) + (uint32_t)((tid % SL) * P) * 4u;
-            int D = 0;
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t wa = lds_u32(hmerged + (uint32_t)tid * kMergedPitch + 4u * (uint32_t)i);
-                uint32_t wb = 0u;
+        {
+            const int w0 = (32 * my_part) / P, w1 = (32 * (my_part + 1)) / P;
+            const uint32_t h0l = hmine - 4u * (uint32_t)my_part;
+            const uint32_t hm = hmerged + (uint32_t)(hist_lane ? my_slice : 0) * kMergedPitch;
+            int dsum = 0;
+            if (hist_lane) {
+                for (int i = w0; i < w1; ++i) {
+                    const uint32_t wa = lds_u32(hm + 4u * (uint32_t)i);
+                    uint32_t wb = 0u;
 #pragma unroll
-                for (int q = 0; q < P; ++q) {
-                    wb += lds_u32(hb0 + 128u * (uint32_t)i + 4u * (uint32_t)q);
-                    sts_u32(hb0 + 128u * (uint32_t)i + 4u * (uint32_t)q, 0u);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ca = (int)((wa >> (8 * q)) & 255u), cb = (int)((wb >> (8 * q)) & 255u);
-                    U = max(U, max(D + ca, cb - D));
-                    D += ca - cb;
-                    L = max(L, abs(D));
+                    for (int q = 0; q < P; ++q) wb += lds_u32(h0l + 128u * (uint32_t)i + 4u * (uint32_t)((q + my_part) % P));
+                    dsum += (int)((wa * 0x01010101u) >> 24) - (int)((wb * 0x01010101u) >> 24);
                 }
             }
+            int D = 0;  // ECDF difference at the lower edge of my first bucket
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                const int dq = __shfl_up_sync(kFull, dsum, q);
+                if (my_part >= q) D += dq;
+            }
+            if (hist_lane) {
+                for (int i = w0; i < w1; ++i) {
+                    const uint32_t wa = lds_u32(hm + 4u * (uint32_t)i);
+                    uint32_t wb = 0u;
+#pragma unroll
+                    for (int q = 0; q < P; ++q) wb += lds_u32(h0l + 128u * (uint32_t)i + 4u * (uint32_t)((q + my_part) % P));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int ca = (int)((wa >> (8 * q)) & 255u), cb = (int)((wb >> (8 * q)) & 255u);
+                        U = max(U, max(D + ca, cb - D));
+                        D += ca - cb;
+                        L = max(L, abs(D));
+                    }
+                }
+            }
+            // max over the P lanes of the slice (lanes part 0 .. P-1 are adjacent)
+            int Lm = L, Um = U;
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                const int ld = __shfl_down_sync(kFull, L, q), ud = __shfl_down_sync(kFull, U, q);
+                if (my_part == 0) {
+                    Lm = max(Lm, ld);
+                    Um = max(Um, ud);
+                }
+            }
+            L = Lm;
+            U = Um;
+            __syncwarp();
+            if (warp < nwh) {  // clear the case counts for the next gene
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sts_v4(hwarp + 512u * (uint32_t)i + 16u * (uint32_t)lane, 0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
         }
-        const bool full_len = own_slice && !(tid == n_slices - 1 && n_last != m);
+        mark(4);
+        const bool leader = hist_lane && my_part == 0;  // holds the slice's L and U
+        const bool full_len = leader && !(my_slice == n_slices - 1 && n_last != m);
         int lmax = __reduce_max_sync(kFull, full_len ? L : 0);
         if (lane == 0) red[warp] = lmax;
         __syncthreads();
         int Lstar = 0;
         for (int w = 0; w < nw; ++w) Lstar = max(Lstar, red[w]);
-        if (own_slice) {
+        if (leader) {
             const bool need = !full_len || U > Lstar || Lstar < pa.h0_full;
-            if (need) flagged[atomicAdd(&ctl[0], 1)] = (uint16_t)tid;
+            if (need) flagged[atomicAdd(&ctl[0], 1)] = (uint16_t)my_slice;
         }
         __syncthreads();
         const int nflag = ctl[0];
         mark(5);
-        // ---- exact h of the flagged slices: two per warp trip (one per half-warp), both samples sorted into the
-        //      warp's scratch, then all 32 lanes evaluate each pair of sorted samples
-        for (int i0 = 2 * warp; i0 < nflag && warp < pa.nwx; i0 += 2 * pa.nwx) {
-            const int i = min(i0 + grp, nflag - 1);
-            const int kk = (int)flagged[i];
-            sort_slice(1, kk, sa0 + (size_t)(2 + grp) * NPAD, true);
-            sort_slice(0, kk, sa0 + (size_t)grp * NPAD, true);
+        // ---- exact h of the flagged slices: one per warp trip; the half-warp sorter sorts the control sample
+        //      (lanes 0-15, values gathered from L2) and the case sample (lanes 16-31, from SMEM) at once
+        for (int i = warp; i < nflag && warp < pa.nwx; i += pa.nwx) {
+            const int k = (int)flagged[i];
+            const int n = (k == n_slices - 1) ? n_last : m;
+            sort_slice(grp, k, sa0 + (size_t)grp * NPAD, true);
             __syncwarp();
-#pragma unroll 1
-            for (int u = 0; u < 2; ++u) {
-                if (i0 + u < nflag) {
-                    const int k = (int)flagged[i0 + u];
-                    const int n = (k == n_slices - 1) ? n_last : m;
-                    const int h = ks_h_sorted<T, NPAD>(sa0 + (size_t)u * NPAD, sa0 + (size_t)(2 + u) * NPAD, n, lane);
-                    if (lane == 0) {
-                        const double pv = (n == m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
-                        atomicMin(pmin_bits, (unsigned long long)__double_as_longlong(pv));
-                    }
-                }
+            const int h = ks_h_sorted<T, NPAD>(sa0, sa0 + NPAD, n, lane);
+            if (lane == 0) {
+                const double pv = (n == m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
+                atomicMin(pmin_bits, (unsigned long long)__double_as_longlong(pv));
             }
             __syncwarp();
         }
@@ -407,7 +436,7 @@ static S3pGeometry s3p_geometry(const Step3Args &a) {
         const size_t nwh = (size_t)((a.n_slices + SL - 1) / SL);
         for (int nwx = kS3pThreads / 32; nwx >= 2; nwx >>= 1) {
             const size_t smem = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * (2 + 4) + 128 +
-                                nwh * 32 * kS3pHistBytes + (size_t)ge.ns_pad * (kS3pHistBytes + 4) + (size_t)nwx * 4 * npad_b;
+                                nwh * 32 * kS3pHistBytes + (size_t)ge.ns_pad * (kS3pHistBytes + 4) + (size_t)nwx * 2 * npad_b;
             if (smem <= (size_t)kMaxSmemOptin) {
                 ge.P = P;
                 ge.nwx = nwx;
