@@ -16,6 +16,9 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v));
 }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -50,7 +53,9 @@ __device__ __forceinline__ double lds_val(uint32_t addr, double) {
 }
 
 __device__ __forceinline__ uint32_t hist_addr(uint32_t hbase, uint32_t b) {
-    return hbase + ((b & ~3u) << 5) + (b & 3u);  // word b/4 of this lane (words interleaved by lane), byte b%4
+    // word b/4 of this lane (words interleaved by lane, 128 bytes apart), byte b%4:
+    // 128*(b/4) + b%4 == 32*b - 31*(b%4); two IMADs (FMA pipe) and one LOP3
+    return (b & 3u) * 0xFFFFFFE1u + (b * 32u + hbase);
 }
 
 // Bucket of v and the shared-memory address of its counter.  t = v*scale + off, clamped to
