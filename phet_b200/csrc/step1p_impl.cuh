@@ -156,7 +156,7 @@ __device__ __forceinline__ T pick_reg(const T (&x)[N], int r) {
 
 template <typename T>
 struct PairCand {
-    static constexpr int kMax = 16;  // candidates per bucket range that are enumerated and sorted (more: tie check or rescue)
+    static constexpr int kMax = 64 / (int)sizeof(T);  // candidates per bucket range (64 bytes of the bucket-list area each)
 };
 
 // A bucket range with more than kMax elements: exact only if it is one tie group.
@@ -377,66 +377,81 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         }
                     }
                     mark(10);
-                    // ---- records -> candidate positions: all four index entries of a flagged word are fetched (two
-                    //      records per trip, so eight L2 loads overlap) and the flagged ones are appended to the range's
-                    //      list of 16-bit positions (histogram words 0..7: low range, 8..15: high range; NBW >= 16)
+                    // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
                     int nL = 0, nH = 0;
-                    for (int i = 0; i < nrec; i += 2) {
-                        const uint32_t r0 = lds_u32(blbase + 4u * (uint32_t)i);
-                        const uint32_t r1 = (i + 1 < nrec) ? lds_u32(blbase + 4u * (uint32_t)(i + 1)) : (r0 & 63u);  // flagless twin
-                        const uint16_t *q0 = ip + (r0 & 63u) * 128u, *q1 = ip + (r1 & 63u) * 128u;
-                        uint32_t pp[8];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            pp[u] = (uint32_t)__ldg(q0 + 32 * u);
-                            pp[4 + u] = (uint32_t)__ldg(q1 + 32 * u);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const uint32_t rec = u < 4 ? r0 : r1;
-                            if (rec & (0x80u << (8 * (u & 3)))) {
-                                if (nL < CM) sts_u16(hbase + 128u * (uint32_t)(nL >> 1) + 2u * (uint32_t)(nL & 1), pp[u]);
-                                ++nL;
-                            }
-                            if (rec & (0x40u << (8 * (u & 3)))) {
-                                if (nH < CM) sts_u16(hbase + 128u * (uint32_t)(8 + (nH >> 1)) + 2u * (uint32_t)(nH & 1), pp[u]);
-                                ++nH;
-                            }
+                    for (int i = 0; i < nrec; ++i) {
+                        const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
+                        const int wj = (int)(rec & 63u) * 4;
+                        uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
+                        while (f) {
+                            const int bit = __ffs((int)f) - 1;
+                            f &= f - 1u;
+                            const bool hi = (bit & 1) == 0;
+                            const int cnt = hi ? nH : nL;
+                            if (cnt < CM) sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), (uint32_t)(wj + (bit >> 3)));  // NBW >= 8
+                            nH += hi ? 1 : 0;
+                            nL += hi ? 0 : 1;
                         }
                     }
                     rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
                     mark(11);
+                    // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
+                    //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
+                    {
+                        const int nLc = nL < CM ? nL : CM, nHc = nH < CM ? nH : CM;
+                        const int nmax = nLc > nHc ? nLc : nHc;
+                        for (int i0 = 0; i0 < nmax; i0 += 4) {
+                            uint32_t pl[4], ph[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
+                                const uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
+                                const uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
+                                pl[u] = (uint32_t)__ldg(ip + jl * 32u);
+                                ph[u] = (uint32_t)__ldg(ip + jh * 32u);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const T vl = lds_pos(vals_sa, pl[u], T(0)), vh = lds_pos(vals_sa, ph[u], T(0));
+                                if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
+                                if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
+                            }
+                        }
+                    }
                     mark(12);
-                    // ---- gather, sort (8- or 16-input network) and rank the candidates of each range
+                    // ---- sort the candidates of each range and read off the two ranks
                     T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
                         const int nc = h ? nH : nL;
                         const bool small = h ? smallH : smallL;
                         const int ra = h ? P2 - E[2] : P0 - E[0], rb = h ? P3 - E[2] : P1 - E[0];
+                        const uint32_t cb = blbase + (h ? 64u : 0u);
                         T ya, yb;
                         if (!small) {
                             ya = h ? tieH : tieL;
                             yb = ya;
-                        } else if (nc <= 8) {
+                        } else if (nc <= 8 || CM <= 8) {
                             T c[8];
+                            if (sizeof(T) == 4) {
+                                const uint4 q0 = lds_v4(cb), q1 = lds_v4(cb + 16u);
+                                c[0] = (T)__uint_as_float(q0.x); c[1] = (T)__uint_as_float(q0.y);
+                                c[2] = (T)__uint_as_float(q0.z); c[3] = (T)__uint_as_float(q0.w);
+                                c[4] = (T)__uint_as_float(q1.x); c[5] = (T)__uint_as_float(q1.y);
+                                c[6] = (T)__uint_as_float(q1.z); c[7] = (T)__uint_as_float(q1.w);
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t w = lds_u32(hbase + 128u * (uint32_t)(8 * h + k));
-                                c[2 * k] = (2 * k < nc) ? lds_pos(vals_sa, w & 0xFFFFu, T(0)) : Big<T>::v();
-                                c[2 * k + 1] = (2 * k + 1 < nc) ? lds_pos(vals_sa, w >> 16, T(0)) : Big<T>::v();
+                                for (int i = 0; i < 8; ++i) c[i] = lds_val(cb + 8u * (uint32_t)i, T(0));
                             }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? c[i] : Big<T>::v();
                             sort_pow2_asc<T, 8>(c);
                             ya = pick_reg<T, 8>(c, ra);
                             yb = pick_reg<T, 8>(c, rb);
                         } else {
                             T c[16];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const uint32_t w = lds_u32(hbase + 128u * (uint32_t)(8 * h + k));
-                                c[2 * k] = (2 * k < nc) ? lds_pos(vals_sa, w & 0xFFFFu, T(0)) : Big<T>::v();
-                                c[2 * k + 1] = (2 * k + 1 < nc) ? lds_pos(vals_sa, w >> 16, T(0)) : Big<T>::v();
-                            }
+                            for (int i = 0; i < 16; ++i) c[i] = (i < nc) ? lds_val(cb + (uint32_t)(i * (int)sizeof(T)), T(0)) : Big<T>::v();
                             sort_pow2_asc<T, 16>(c);
                             ya = pick_reg<T, 16>(c, ra);
                             yb = pick_reg<T, 16>(c, rb);
