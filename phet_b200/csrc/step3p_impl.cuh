@@ -4,9 +4,10 @@
 // o[g] = min over slices of the KS p-value, and p is (essentially) non-increasing in the integer
 // statistic h, so only the slices that can reach the gene's largest h need an exact h.  Per gene:
 //
-//   phase 1  (control vector staged)  one THREAD per slice walks its permutation slice, maps every
-//            value through a per-gene monotone affine map to one of 127 buckets and counts it in a
-//            thread-private byte histogram ha (bank == lane: conflict-free), as in k_step1p.
+//   phase 1  (control vector staged)  P = 3 lanes per slice (every P-th element each) walk its permutation
+//            slice, map every value through a per-gene monotone affine map to one of 127 buckets and
+//            count it in a lane-private byte histogram (bank == lane: conflict-free), as in k_step1p;
+//            the P partial histograms are summed into ha and parked.
 //   phase 2  (case vector staged)  same for hb, then one pass over the 127 buckets gives rigorous
 //            bounds on h: with D_k = sum_{i<=k} (ha_i - hb_i) the ECDF difference at the bucket edges,
 //            L = max_k |D_k| <= h <= U = max_k max(D_{k-1} + ha_k, hb_k - D_{k-1})
@@ -14,10 +15,10 @@
 //   prune    L* = max over full-length slices of L.  A slice with U <= L* cannot beat L*; since the
 //            table is non-increasing from h0 on (host-checked) its p is >= table[L*].  The rest
 //            (typically a few of ~160), and always a shorter last slice, are flagged.
-//   exact    flagged slices only: their case samples are sorted (half-warp merge-split sorter, two
-//            slices per warp) and parked in SMEM, the control vector is staged again, the control
-//            samples are sorted and the exact integer h is evaluated against the parked case
-//            sample exactly as in k_step3h.  o[g] = min(table[L*], exact p-values).
+//   exact    flagged slices only, one per warp trip: the half-warp merge-split sorter sorts the control
+//            sample (lanes 0-15; values gathered from L2, where the row just staged still sits) and the
+//            case sample (lanes 16-31, from SMEM) at once, and the exact integer h is evaluated as in
+//            k_step3h.  o[g] = min(table[L*], exact p-values).
 //
 // Bucket maps come from k_window3 (one map per gene for both classes: the two ECDFs are compared
 // on common edges).  A poor map only flags more slices; the result is always the exact minimum.
@@ -36,7 +37,6 @@ struct Step3PairArgs {
     const float2 *win;  // [G]: (scale, offset) of the common bucket map of the gene
     int32_t vals_bytes; // SMEM bytes reserved for one class vector (multiple of 128)
     int32_t ns_pad;     // n_slices rounded up to 32
-    int32_t store_cap;  // case samples that can be parked per batch
     int32_t h0_full;    // table_full is non-increasing on [h0, m] and table[h0] <= table[h] for h < h0
     int32_t nwx;        // warps taking part in the exact phase (each owns a 4-sample scratch)
     unsigned long long *prof;  // optional [8] cycle counters summed over CTAs (env PHET_PROFILE=1), else NULL
@@ -129,15 +129,14 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
     const int n_last = (int)a.n_last;
     constexpr int NPAD = 16 * E;
 
-    // shared memory: [class vector | mbarrier | control words | flagged slice list | per-slice bounds |
-    //                 histograms (ha, hb: 2 x 4 KB per 32 slices) | per-warp sorted-a scratch | parked sorted-b samples]
+    // shared memory: [class vector | mbarrier | control words | flagged slice list | per-lane histograms (4 KB per
+    //                 warp) | merged control histograms (132 bytes per slice) | per-warp scratch for two sorted samples]
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + pa.vals_bytes);
     int *ctl = reinterpret_cast<int *>(bar + 2);                  // [0] n_flagged, [1] L*, [2..3] p_min bits
     unsigned long long *pmin_bits = reinterpret_cast<unsigned long long *>(ctl + 2);
     int *red = ctl + 4;                                           // [nw] per-warp maxima
     uint16_t *flagged = reinterpret_cast<uint16_t *>(red + 32);
-    int *bounds = reinterpret_cast<int *>(flagged + pa.ns_pad);   // (L << 16) | U per slice
-    unsigned char *hist_raw = reinterpret_cast<unsigned char *>(bounds + pa.ns_pad);
+    unsigned char *hist_raw = reinterpret_cast<unsigned char *>(flagged + pa.ns_pad);
     hist_raw = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hist_raw) + 127) & ~(uintptr_t)127);
     // per-lane histogram (words interleaved by lane inside the warp: bank == lane), then the merged control
     // histograms of all slices (pitch 132 bytes: consecutive slices start in consecutive banks)
@@ -435,7 +434,7 @@ static S3pGeometry s3p_geometry(const Step3Args &a) {
         if (a.n_slices > (kS3pThreads / 32) * SL) continue;
         const size_t nwh = (size_t)((a.n_slices + SL - 1) / SL);
         for (int nwx = kS3pThreads / 32; nwx >= 2; nwx >>= 1) {
-            const size_t smem = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * (2 + 4) + 128 +
+            const size_t smem = (size_t)ge.vals_bytes + 16 + 16 + 32 * sizeof(int) + (size_t)ge.ns_pad * 2 + 128 +
                                 nwh * 32 * kS3pHistBytes + (size_t)ge.ns_pad * (kS3pHistBytes + 4) + (size_t)nwx * 2 * npad_b;
             if (smem <= (size_t)kMaxSmemOptin) {
                 ge.P = P;
@@ -474,7 +473,6 @@ static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
     pa.win = c->win3.p;
     pa.vals_bytes = ge.vals_bytes;
     pa.ns_pad = ge.ns_pad;
-    pa.store_cap = 0;
     pa.nwx = ge.nwx;
     pa.prof = c->prof.p;
     pa.h0_full = c->tab_h0;
