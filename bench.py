@@ -43,6 +43,7 @@ WORKLOADS = {
 FEATURE_WEIGHT = [0.4, 0.3, 0.2, 0.1]
 PERCENTILES = (25, 75)
 SEED = 12345
+NCU_STEP1_DRAM_BYTES = 6003228000 + 7337000   # k_step1p<float,16,1>, config 4, one launch (profiles/r1_ncu_full_v6.txt)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -394,12 +395,17 @@ def main():
              "full-warp": "k_step1<float,E=%d>" % geom["E"]}[geom["path"]]
     roofline = {"bound": "hbm", "kernel": "%s (staged=%s)" % (kname, geom["staged"]),
                 "achieved": hbm_bytes / step1_s / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": hbm_bytes / step1_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": hbm_bytes / step1_s / 1e9 / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
+                # capture (profiles/r1_ncu_full_v6.txt; config 4 on one GPU only)
+                "traffic": NCU_STEP1_DRAM_BYTES if (args.workload == "cfg4" and world == 1 and geom["path"] == "pair-per-thread") else None,
+                "peak_source": peak_src,
                 "launch_ms": phase[1], "algorithmic_hbm_bytes_per_launch": int(hbm_bytes),
                 "smem_gather_gbs": smem_bytes / step1_s / 1e9,
                 "smem_gather_peak_gbs": 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                "note": "k_step1 is issue/ALU bound (register sorting network), not HBM bound: HBM is touched once "
-                        "per gene; see profiles/ for the ncu issue-slot utilisation",
+                "note": "the Step-1 kernel is not HBM bound: each class vector is staged once per gene (traffic == "
+                        "algorithmic bytes) and then serves ~1000 samples from SMEM; ncu: issue slots 61 %, ALU pipe 47 %, "
+                        "SMEM wavefronts 44 % (profiles/r1_ncu_full_v6.txt)",
                 "grid": geom["grid"], "block": geom["block"], "smem_per_cta": geom["smem"]}
     cpu = None
     if not args.no_cpu:
