@@ -261,3 +261,25 @@ def test_step3_prune_path_equals_sort_path(name, perm, monkeypatch):
         out[impl] = (est.o_.copy(), est.step3_path_)
     assert out["auto"][1] == "bound-and-prune" and out["sort"][1] != "bound-and-prune"
     assert np.array_equal(out["auto"][0], out["sort"][0])
+
+
+def test_big_class_fallback_matches_oracle():
+    """Classes above 65,536 cells (BASELINE config 5's regime) cannot use the 16-bit index table of the
+    select kernel and do not fit shared memory: the warp-cooperative sorters gather from L2 instead.
+    140,000 cells -> m = 264 (full-warp sorter), 266 KS slices; checked against the oracle."""
+    from oracle import phet_oracle as po
+    from phet_b200 import PHet
+    rng = np.random.default_rng(11)
+    N, G, S = 140000, 6, 5
+    y = np.r_[np.zeros(N // 2, dtype=np.int64), np.ones(N - N // 2, dtype=np.int64)]
+    X = rng.gamma(2.0, 1.0, (N, G))
+    X[y == 1, 0] += 0.05
+    np.random.seed(3)
+    est = PHet(num_subsamples=S, capture=True, distributed=False)
+    scores = est.fit_predict(X, y)
+    assert est.step1_geometry_["path"] == "full-warp" and not est.step1_geometry_["staged"]
+    np.random.seed(3)
+    ref = po.fit_predict_oracle(X, y, num_subsamples=S)
+    assert np.array_equal(est.H_, ref.H)
+    assert np.array_equal(est.bin_counts_, ref.bin_counts)
+    assert np.allclose(scores, ref.scores, rtol=1e-5, atol=1e-12)
