@@ -176,11 +176,8 @@ class Fit:
             from phet_b200.distributed import allreduce_device_buffer
             allreduce_device_buffer(c, self.capi.BUF_ACC, self.dist)
             allreduce_device_buffer(c, self.capi.BUF_O, self.dist)
-        c.fisher(self.S)
-        o_min, o_max = c.o_minmax()
-        edges = self.hostmath.uniform_bin_edges(o_min, o_max, len(self.weights))
-        self.counts = c.bin(edges)
-        return c.combine(self.weights, fetch=fetch)
+        scores, self.counts, _ = c.finalize(self.S, self.weights, fetch=fetch)
+        return scores
 
     def step_resident(self, X_dev_ptr, events=None):
         """Timed unit for `value`: raw matrix + index sets already in HBM."""

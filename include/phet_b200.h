@@ -164,6 +164,13 @@ int phet_bin(phet_ctx *ctx, const double *edges, int32_t B, int64_t *counts_out)
  * scores_out: host double[G] or NULL (leave on device, PHET_BUF_SCORES). */
 int phet_combine(phet_ctx *ctx, const double *weights, int32_t B, double *scores_out);
 
+/* phet_fisher + phet_o_minmax + np.linspace edges + phet_bin + phet_combine in one call with no host round
+ * trip in between (the edges are formed on the device with numpy's operation order, so bins are the same as
+ * with host-supplied edges).  Replaces phet.py:435-462 and 500-516.  weights: host double[B], normalised.
+ * scores_out: host double[G]; counts_out: host int64[B]; edges_out: host double[B+1]; each may be NULL. */
+int phet_finalize(phet_ctx *ctx, int64_t S_total, const double *weights, int32_t B, double *scores_out,
+                  int64_t *counts_out, double *edges_out);
+
 /* Context options.  PHET_OPT_KEEP_H (default 0): 1 = phet_step3 / phet_run_pipeline also fill PHET_BUF_H
  * with the integer KS statistic of EVERY slice (parity / debugging; the sorting kernels run); 0 = only
  * o[g] = min p is produced, which lets Step 3 bound h per slice from bucket histograms and evaluate

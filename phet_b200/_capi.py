@@ -24,7 +24,7 @@ OPT_KEEP_H = 1
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
-    "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_device_ptr",
+    "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
@@ -96,6 +96,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_o_minmax.argtypes = [vp, C.POINTER(dbl)]
     lib.phet_bin.argtypes = [vp, vp, i32, vp]
     lib.phet_combine.argtypes = [vp, vp, i32, vp]
+    lib.phet_finalize.argtypes = [vp, i64, vp, i32, vp, vp, vp]
     lib.phet_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     lib.phet_read_buffer.argtypes = [vp, C.c_int, vp, i64]
     lib.phet_write_buffer.argtypes = [vp, C.c_int, vp, i64]
@@ -250,6 +251,17 @@ class Context:
         out = np.empty(self.G, dtype=np.float64) if fetch else None
         _check(self.lib.phet_combine(self.h, _ptr(w), w.size, _ptr(out) if fetch else None))
         return out
+
+    def finalize(self, S_total, weights: np.ndarray, fetch=True):
+        """Fisher + uniform binning of o + combine on the device in one call: (scores, bin counts, edges)."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        B = w.size
+        scores = np.empty(self.G, dtype=np.float64) if fetch else None
+        counts = np.zeros(B, dtype=np.int64)
+        edges = np.empty(B + 1, dtype=np.float64)
+        _check(self.lib.phet_finalize(self.h, int(S_total), _ptr(w), B, _ptr(scores) if fetch else None, _ptr(counts),
+                                      _ptr(edges)))
+        return scores, counts, edges
 
     def device_ptr(self, which):
         p = C.c_void_p()

@@ -679,6 +679,20 @@ int phet_combine(phet_ctx *c, const double *weights, int32_t B, double *scores_o
     return PHET_OK;
 }
 
+int phet_finalize(phet_ctx *c, int64_t S_total, const double *weights, int32_t B, double *scores_out,
+                  int64_t *counts_out, double *edges_out) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set, "ctx not ready");
+    PHET_REQUIRE(S_total >= 1, "S_total must be >= 1");
+    PHET_REQUIRE(weights != nullptr && B >= 1 && B <= 127, "need 1 <= B <= 127 feature weights");
+    PHET_CUDA(cudaSetDevice(c->device));
+    if (int e = c->edges.alloc((size_t)B + 1)) return e;
+    if (int e = c->counts.alloc((size_t)B)) return e;
+    if (int e = c->weights.alloc((size_t)B)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->weights.p, weights, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    c->n_bins = B;
+    return launch_finalize(c, S_total, B, scores_out, counts_out, edges_out);  // synchronises: weights is a host buffer
+}
+
 static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
     switch (which) {
         case PHET_BUF_ACC: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 2 * c->G; break;
@@ -795,24 +809,7 @@ int phet_fit_host(phet_ctx *c, const void *X, int dtype, int64_t N, int64_t G, c
     pp.n_last = prm->n_last;
     pp.block_genes = 0;
     if (int e = phet_run_pipeline(c, X, 0, N, G, dtype, &pp)) return e;
-    if (int e = phet_fisher(c, S)) return e;
-    double mm[2];
-    if (int e = phet_o_minmax(c, mm)) return e;
-    std::vector<double> edges;
-    int B = prm->n_bins;
-    if (mm[0] == mm[1]) {  // sklearn: constant feature -> one bin, everything ordinal 0
-        edges = {-INFINITY, INFINITY};
-        std::vector<int64_t> cnt1(1);
-        if (int e = phet_bin(c, edges.data(), 1, cnt1.data())) return e;
-        if (bin_counts_out) {
-            for (int i = 0; i < B; ++i) bin_counts_out[i] = 0;
-            bin_counts_out[0] = cnt1[0];
-        }
-    } else {
-        linspace_edges(mm[0], mm[1], B, edges);
-        if (int e = phet_bin(c, edges.data(), B, bin_counts_out)) return e;
-    }
-    return phet_combine(c, prm->weights, B, scores_out);
+    return phet_finalize(c, S, prm->weights, prm->n_bins, scores_out, bin_counts_out, nullptr);
 }
 
 // Host evaluations of the device p-value routines (same source, pvalue.cuh) for CPU unit tests.

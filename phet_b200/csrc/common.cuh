@@ -130,5 +130,6 @@ int launch_fisher(phet_ctx *c, int64_t S_total);
 int launch_o_minmax(phet_ctx *c, double out[2]);
 int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
+int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
 
 }  // namespace phet

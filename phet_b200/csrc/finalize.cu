@@ -93,6 +93,27 @@ __global__ void k_combine(const double *__restrict__ r, const double *__restrict
     scores[g] = v;
 }
 
+// np.linspace(min o, max o, B + 1) on the device, operation for operation (numpy function_base.linspace:
+// step = (hi - lo) / B; y[i] = i * step + lo with the product and the sum rounded separately; y[B] = hi), so
+// the edges -- and with them every bin -- are the ones sklearn's KBinsDiscretizer(strategy="uniform") computes
+// (_discretization.py:339).  min == max: one bin holding everything (edges -inf, +inf, ...).
+__global__ void k_edges(const double *__restrict__ mm, int B, double *__restrict__ edges) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double lo = mm[0], hi = mm[1];
+    if (lo == hi) {
+        edges[0] = -CUDART_INF;
+        for (int i = 1; i <= B; ++i) edges[i] = CUDART_INF;
+        return;
+    }
+    const double delta = __dsub_rn(hi, lo);
+    const double step = __ddiv_rn(delta, (double)B);
+    for (int i = 0; i <= B; ++i) {
+        const double prod = (step != 0.0) ? __dmul_rn((double)i, step) : __dmul_rn(__ddiv_rn((double)i, (double)B), delta);
+        edges[i] = __dadd_rn(prod, lo);
+    }
+    edges[B] = hi;
+}
+
 static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 int launch_fisher(phet_ctx *c, int64_t S_total) {
@@ -146,5 +167,23 @@ int launch_combine(phet_ctx *c, int32_t B, double *scores_out) {
     }
     return 0;
 }
+
+// Fisher standardisation, edges, binning and combine back to back on the stream; one synchronisation at the end.
+int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out) {
+    if (int e = launch_fisher(c, S_total)) return e;
+    k_reduce3<<<1, kRedThreads, 0, c->stream>>>(c->o.p, c->G, c->scalars.p);
+    k_edges<<<1, 32, 0, c->stream>>>(c->scalars.p, B, c->edges.p);
+    c->launches += 2;
+    if (int e = launch_bin(c, B, nullptr)) return e;
+    if (int e = launch_combine(c, B, nullptr)) return e;
+    if (scores_out) PHET_CUDA(cudaMemcpyAsync(scores_out, c->scores.p, sizeof(double) * c->G, cudaMemcpyDeviceToHost, c->stream));
+    if (counts_out)
+        PHET_CUDA(cudaMemcpyAsync(counts_out, c->counts.p, sizeof(unsigned long long) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (edges_out) PHET_CUDA(cudaMemcpyAsync(edges_out, c->edges.p, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+
 
 }  // namespace phet

@@ -254,13 +254,9 @@ class PHet:
             from .distributed import allreduce_device_buffer
             allreduce_device_buffer(ctx, _capi.BUF_ACC, dist)       # sum_s -2 ln p, sum_s delta
             allreduce_device_buffer(ctx, _capi.BUF_O, dist)         # genes outside a rank's slice are 0
-        ctx.fisher(S)                                                # phet.py:435-462
-        o_min, o_max = ctx.o_minmax()
-        B = len(self.feature_weight)
-        edges = hostmath.uniform_bin_edges(o_min, o_max, B)          # sklearn KBinsDiscretizer 'uniform'
-        counts = ctx.bin(edges)                                      # phet.py:500-504
-        self.bin_counts_ = np.concatenate([counts, np.zeros(B - len(counts), dtype=np.int64)])
-        scores = ctx.combine(self.feature_weight)                    # phet.py:510-516
+        # Fisher standardisation, KBinsDiscretizer('uniform') on o, weights and combine (phet.py:435-462, 500-516)
+        scores, counts, edges = ctx.finalize(S, self.feature_weight)
+        self.bin_counts_ = counts
         self.m_ = m
         self.index_sets_ = idx
         self.launches_ = ctx.launch_count()
