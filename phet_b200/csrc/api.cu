@@ -610,7 +610,9 @@ int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int6
             }
             int64_t gb = p->block_genes;
             if (gb <= 0) {  // ~128 MB per staging buffer, a multiple of the persistent grid (one CTA per SM)
-                gb = (int64_t)((128u << 20) / ((size_t)N * e_in));
+                size_t block_bytes = (size_t)128 << 20;
+                if (const char *mb = getenv("PHET_BLOCK_MB")) block_bytes = (size_t)(atoi(mb) > 0 ? atoi(mb) : 128) << 20;
+                gb = (int64_t)(block_bytes / ((size_t)N * e_in));
                 gb = gb / c->num_sms * c->num_sms;
                 if (gb < c->num_sms) gb = c->num_sms;
             }
