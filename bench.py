@@ -174,8 +174,7 @@ class Fit:
         c = self.ctx
         if self.dist is not None:
             from phet_b200.distributed import allreduce_device_buffer
-            allreduce_device_buffer(c, self.capi.BUF_ACC, self.dist)
-            allreduce_device_buffer(c, self.capi.BUF_O, self.dist)
+            allreduce_device_buffer(c, self.capi.BUF_ACC_O, self.dist)   # sum -2 ln p | sum delta | o in one all-reduce
         scores, self.counts, _ = c.finalize(self.S, self.weights, fetch=fetch)
         return scores
 

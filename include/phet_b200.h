@@ -57,6 +57,7 @@ typedef enum {
     PHET_BUF_MEAN = 10,    /* double[G] column mean  */
     PHET_BUF_STD = 11,     /* double[G] column population sd */
     PHET_BUF_ROWS = 12,    /* int32[N]: original row held at each position of a gene-major row (the layout) */
+    PHET_BUF_ACC_O = 14,   /* double[3][G]: PHET_BUF_ACC followed by PHET_BUF_O, contiguous (one all-reduce for both)    */
     PHET_BUF_PROFILE = 13  /* uint64[16]: per-phase cycle counters of the Step-3 kernel, only with env PHET_PROFILE=1 */
 } phet_buffer;
 

@@ -19,7 +19,7 @@ TEST_T, TEST_Z = 0, 1
 PERM_HOST, PERM_DEVICE = 0, 1
 OPT_KEEP_H = 1
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
- BUF_STD, BUF_ROWS, BUF_PROFILE) = range(14)
+ BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O) = range(15)
 
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",

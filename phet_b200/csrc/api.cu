@@ -405,8 +405,11 @@ static int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int norm
     if (int e = c->xg.alloc((size_t)(c->xg_rows > 0 ? c->xg_rows : 1) * (size_t)c->n_pad * e_st)) return e;
     if (int e = c->mean.alloc((size_t)G)) return e;
     if (int e = c->sd.alloc((size_t)G)) return e;
-    if (int e = c->acc.alloc((size_t)2 * G)) return e;
-    if (int e = c->o.alloc((size_t)G)) return e;
+    if (c->acc.n < (size_t)3 * G || c->o.p != c->acc.p + 2 * G) {
+        c->o.release();
+        if (int e = c->acc.alloc((size_t)3 * G)) return e;
+        c->o.alias(c->acc.p + 2 * G, (size_t)G);  // o rides behind the two accumulators
+    }
     if (int e = c->f.alloc((size_t)G)) return e;
     if (int e = c->r.alloc((size_t)G)) return e;
     if (int e = c->fw.alloc((size_t)G)) return e;
@@ -513,9 +516,18 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
     if (int e = c->tab_last.alloc((size_t)n_last + 1)) return e;
     PHET_CUDA(cudaMemsetAsync(c->H.p, 0, sizeof(int32_t) * c->G * n_slices, c->stream));
     PHET_CUDA(cudaMemsetAsync(c->o.p, 0, sizeof(double) * c->G, c->stream));
-    PHET_CUDA(cudaMemcpyAsync(c->tab_full.p, table_full, sizeof(double) * (m + 1), cudaMemcpyHostToDevice, c->stream));
-    PHET_CUDA(
-        cudaMemcpyAsync(c->tab_last.p, table_last, sizeof(double) * (n_last + 1), cudaMemcpyHostToDevice, c->stream));
+    // the tables only change with (m, n_last): keep a host copy and upload on change, synchronously, so that
+    // no caller-owned host buffer is in flight when the launch calls return
+    if (c->tab_full_host.size() != (size_t)m + 1 || memcmp(c->tab_full_host.data(), table_full, sizeof(double) * (m + 1)) != 0) {
+        c->tab_full_host.assign(table_full, table_full + m + 1);
+        PHET_CUDA(cudaMemcpyAsync(c->tab_full.p, c->tab_full_host.data(), sizeof(double) * (m + 1), cudaMemcpyHostToDevice, c->stream));
+        PHET_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (c->tab_last_host.size() != (size_t)n_last + 1 || memcmp(c->tab_last_host.data(), table_last, sizeof(double) * (n_last + 1)) != 0) {
+        c->tab_last_host.assign(table_last, table_last + n_last + 1);
+        PHET_CUDA(cudaMemcpyAsync(c->tab_last.p, c->tab_last_host.data(), sizeof(double) * (n_last + 1), cudaMemcpyHostToDevice, c->stream));
+        PHET_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (perm_mode == PHET_PERM_HOST) {
         PHET_REQUIRE(perm_ctrl && perm_case, "host permutations are NULL");
         const size_t n = (size_t)c->G * (size_t)min_c;
@@ -561,8 +573,8 @@ int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_
     if (int e = step3_prepare(c, m, perm_mode, perm_ctrl, perm_case, table_full, table_last, n_last)) return e;
     int rc = launch_step3(c, g_begin, g_end, m, perm_mode, seed, n_last);
     if (rc) return rc;
-    // tables and permutations are host buffers owned by the caller: finish the copies before returning
-    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    // host permutations are caller-owned: finish their copies before returning (tables were copied in prepare)
+    if (perm_mode == PHET_PERM_HOST) PHET_CUDA(cudaStreamSynchronize(c->stream));
     return PHET_OK;
 }
 
@@ -637,7 +649,9 @@ int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int6
             }
         }
     }
-    PHET_CUDA(cudaStreamSynchronize(c->stream));  // X, tables and permutations are caller-owned host memory
+    // host X and host permutations are caller-owned and still being read; a device matrix with device-mode
+    // permutations leaves nothing of the caller's in flight, so the call returns with the work queued
+    if (!is_device || p->perm_mode == PHET_PERM_HOST) PHET_CUDA(cudaStreamSynchronize(c->stream));
     c->matrix_set = true;
     return PHET_OK;
 }
@@ -710,6 +724,7 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_MEAN: *p = c->mean.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;
+        case PHET_BUF_ACC_O: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 3 * c->G; break;
         case PHET_BUF_PROFILE: *p = c->prof.p; *bytes = 16 * (int64_t)sizeof(unsigned long long); break;
         default:
             set_error("invalid: unknown buffer id");

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/phet_b200.h"
 
@@ -48,10 +49,18 @@ struct DevBuf {
         return 0;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
     }
+    void alias(T *ptr, size_t count) {  // view into another buffer (not freed here)
+        release();
+        p = ptr;
+        n = count;
+        owned = false;
+    }
+    bool owned = true;
     size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -102,7 +111,8 @@ struct phet_ctx {
     int step3_impl = 0;                  // 0 auto, 1 sorting kernels only (env PHET_STEP3_IMPL=sort)
     int step3_path = 0;                  // last Step-3 launch: 1 full-warp sort, 2 half-warp sort, 3 bound-and-prune
     int tab_h0 = -1;                     // table_full is non-increasing from here on (host-checked); -1: unknown
-    phet::DevBuf<double> acc;            // [2][G]
+    phet::DevBuf<double> acc;            // [3][G]: sum -2 ln p, sum delta, and o (aliased below): one all-reduce covers all three
+    std::vector<double> tab_full_host, tab_last_host;  // last uploaded KS tables (re-uploaded only when they change)
     phet::DevBuf<double> dbgP, dbgD;     // [G][S_local]
     phet::DevBuf<double> o;              // [G]
     phet::DevBuf<int32_t> H;             // [G][n_slices]

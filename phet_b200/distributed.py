@@ -47,10 +47,14 @@ class _DeviceView:
 
 
 def device_tensor(ctx, which, typestr="<f8", itemsize=8):
-    """A torch tensor aliasing a context buffer (no copy, no ownership change)."""
+    """A torch tensor aliasing a context buffer (no copy, no ownership change); cached per (pointer, size)."""
     import torch
     ptr, nbytes = ctx.device_ptr(which)
-    return torch.as_tensor(_DeviceView(ptr, nbytes, typestr, itemsize), device="cuda:%d" % ctx.device)
+    cache = ctx.__dict__.setdefault("_tensor_cache", {})
+    key = (which, ptr, nbytes, typestr)
+    if key not in cache:
+        cache[key] = torch.as_tensor(_DeviceView(ptr, nbytes, typestr, itemsize), device="cuda:%d" % ctx.device)
+    return cache[key]
 
 
 def allreduce_device_buffer(ctx, which, dist):

@@ -252,8 +252,8 @@ class PHet:
                          storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed)
         if dist is not None:
             from .distributed import allreduce_device_buffer
-            allreduce_device_buffer(ctx, _capi.BUF_ACC, dist)       # sum_s -2 ln p, sum_s delta
-            allreduce_device_buffer(ctx, _capi.BUF_O, dist)         # genes outside a rank's slice are 0
+            # sum_s -2 ln p | sum_s delta | o, contiguous: one all-reduce (genes outside a rank's slice are 0)
+            allreduce_device_buffer(ctx, _capi.BUF_ACC_O, dist)
         # Fisher standardisation, KBinsDiscretizer('uniform') on o, weights and combine (phet.py:435-462, 500-516)
         scores, counts, edges = ctx.finalize(S, self.feature_weight)
         self.bin_counts_ = counts
