@@ -38,6 +38,12 @@ WORKLOADS = {
                  S=1000),
     "cfg3": dict(name="synthetic 10k cells x 30k genes, 1000 subsamples (BASELINE configs[2])", N=10000, G=30000,
                  S=1000),
+    # BASELINE configs[4] (HBM-capacity sizing): the whole matrix (48 GB raw + 48 GB gene-major) fits one B200;
+    # "cfg5r8" is the share of ONE rank when the genes are sharded over the 8 GPUs of a box (7,500 genes)
+    "cfg5": dict(name="synthetic 200k cells x 60k genes, 5000 subsamples (BASELINE configs[4])", N=200000, G=60000,
+                 S=5000),
+    "cfg5r8": dict(name="one rank's gene slice (7,500 of 60k genes) of BASELINE configs[4]: 200k cells, 5000 subsamples",
+                   N=200000, G=7500, S=5000),
     "tiny": dict(name="synthetic 2k cells x 512 genes, 64 subsamples (debug)", N=2000, G=512, S=64),
 }
 FEATURE_WEIGHT = [0.4, 0.3, 0.2, 0.1]
@@ -266,7 +272,7 @@ def main():
     m = hostmath.subsample_size(N // 2, N - N // 2, "sqrt")
     config = {"workload": wl["name"], "cells": N, "genes": G, "subsamples": S, "m": m, "iqr_range": list(PERCENTILES),
               "feature_weight": FEATURE_WEIGHT, "storage": "f32", "step3_permutations": "device",
-              "l2": "working set 12 GB >> 126 MB L2, no flush needed",
+              "l2": "working set %.0f GB >> 126 MB L2, no flush needed" % (2 * 4.0 * N * G / 1e9),
               "parallelism": "%s-shard x%d" % (args.shard, world)}
 
     if args.impl == "reference":
