@@ -120,6 +120,34 @@ __global__ void k_build_idxT(const int32_t *__restrict__ idx, int64_t S, int64_t
     for (int64_t r = m; r < mp; ++r) out[32 * r] = 0;
 }
 
+// BIG variant of the table: [2][nblk][mp][32] class-local positions, 32 bits each, every subsample's positions in
+// ASCENDING order (the order is free, see above): the warps of a CTA then walk the class vector front to back
+// together and share the lines they pull into L1.  One thread per (class, subsample); m <= 496.
+__global__ void k_build_idxT32(const int32_t *__restrict__ idx, int64_t S, int64_t m, int64_t mp, int64_t n0, int64_t nblk,
+                               uint32_t *__restrict__ idxT) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over [2][nblk * 32]
+    if (t >= 2 * nblk * 32) return;
+    const int64_t c = t / (nblk * 32), s = t % (nblk * 32);
+    uint32_t *out = idxT + ((c * nblk + (s >> 5)) * mp) * 32 + (s & 31);  // row r at out[32 * r]
+    if (s >= S) {
+        for (int64_t r = 0; r < mp; ++r) out[32 * r] = 0;
+        return;
+    }
+    const int32_t *src = idx + (s * 2 + c) * m;
+    const int32_t off = c ? (int32_t)n0 : 0;
+    // insertion sort straight into the (strided) output column
+    for (int64_t j = 0; j < m; ++j) {
+        const uint32_t p = (uint32_t)(src[j] - off);
+        int64_t r = j;
+        while (r > 0 && out[32 * (r - 1)] > p) {
+            out[32 * r] = out[32 * (r - 1)];
+            --r;
+        }
+        out[32 * r] = p;
+    }
+    for (int64_t r = m; r < mp; ++r) out[32 * r] = 0;
+}
+
 static uint64_t gcd_u64(uint64_t a, uint64_t b) {
     while (b) {
         const uint64_t t = a % b;
@@ -254,6 +282,11 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
     c->num_sms = prop.multiProcessorCount;
     if (const char *impl = getenv("PHET_STEP1_IMPL")) c->step1_impl = (strcmp(impl, "warp") == 0) ? 1 : 0;
     if (const char *impl = getenv("PHET_STEP3_IMPL")) c->step3_impl = (strcmp(impl, "sort") == 0) ? 1 : 0;
+    if (const char *fb = getenv("PHET_STEP1_FORCE_BIG")) c->pair_force_big = atoi(fb) != 0;
+    if (const char *bt = getenv("PHET_STEP1_BIG_THREADS")) {
+        const int t = atoi(bt);
+        if (t >= 64 && t <= 512) c->pair_big_threads = t / 32 * 32;
+    }
     if (const char *nbw = getenv("PHET_STEP1_NBW")) c->pair_nbw = (atoi(nbw) == 16) ? 16 : (atoi(nbw) == 32 ? 32 : 0);
     if (stream) {
         c->stream = (cudaStream_t)stream;
@@ -290,6 +323,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->xraw.release();
     c->idx.release();
     c->idxT.release();
+    c->idxT32.release();
     c->win.release();
     c->pair_scratch.release();
     c->win3.release();
@@ -472,6 +506,18 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
         c->launches++;
         PHET_CUDA(cudaGetLastError());
         c->idxT_ok = true;
+    }
+    c->idxT32_ok = false;
+    const int64_t ncmax = c->n0 > c->n1 ? c->n0 : c->n1;
+    if ((!c->idxT_ok || c->pair_force_big || ncmax * 4 > 90 * 1024) && m <= 496) {  // 32-bit ascending copy for the global-gather variant (big classes or m > 255)
+        const int64_t nblk = (S + 31) / 32;
+        const int64_t mp = (m + 15) / 16 * 16;
+        const int64_t nT = 2 * nblk * mp * 32;
+        if (int e = c->idxT32.alloc((size_t)nT)) return e;
+        k_build_idxT32<<<(unsigned)((2 * nblk * 32 + 63) / 64), 64, 0, c->stream>>>(c->idx.p, S, m, mp, c->n0, nblk, c->idxT32.p);
+        c->launches++;
+        PHET_CUDA(cudaGetLastError());
+        c->idxT32_ok = true;
     }
     c->S = S;
     c->m = m;

@@ -100,6 +100,12 @@ struct phet_ctx {
     phet::DevBuf<int32_t> idx;           // [S][2][m] grouped positions
     phet::DevBuf<uint16_t> idxT;         // [2][m][S] class-local positions (pair-per-thread Step 1)
     bool idxT_ok = false;
+    phet::DevBuf<uint32_t> idxT32;       // same table with 32-bit positions in ascending order (k_step1p, BIG variant)
+    bool idxT32_ok = false;
+    bool pair_force_big = false;         // env PHET_STEP1_FORCE_BIG=1: BIG variant even where staging applies (tests)
+    int pair_big_threads = 256;          // threads per CTA of the BIG variant (env PHET_STEP1_BIG_THREADS): what is
+                                         // left of the 256 KB L1/SMEM array is the L1 that serves the gathers --
+                                         // config 5: 512 threads (205 KB SMEM) 175 ms, 384: 73 ms, 256-352: 64-65 ms
     int step1_impl = 0;                  // 0 auto, 1 warp sorters only (env PHET_STEP1_IMPL=warp)
     bool fast_moments = false;           // float storage of z-scored data: fp32 chunk sums in k_step1p (set by prepare_matrix)
     int pair_nbw = 0;                    // 0 auto, 16 / 32: forced histogram words (env PHET_STEP1_NBW, tests)

@@ -1,6 +1,12 @@
-// Step 1, pair-per-thread path (m <= 255, both classes <= 65536 cells, one class vector fits in
-// shared memory).  Same contract as k_step1 (step1_impl.cuh); replaces phet.py:397-432 + 435,
-// 449-451.
+// Step 1, pair-per-thread path.  Same contract as k_step1 (step1_impl.cuh); replaces phet.py:397-432
+// + 435, 449-451.  Two instantiations of one kernel:
+//   BIG = false  m <= 255, both classes <= 65536 cells, one class vector fits in shared memory: the
+//                vector is staged with TMA and gathered from SMEM through 16-bit positions (configs 1-4);
+//   BIG = true   m <= 496 or classes too large to stage (config 5: 100k-cell classes, m = 316): the
+//                values are gathered from global memory through 32-bit positions.  A class vector
+//                (400 KB) lives in L2 while its gene is worked on, and every subsample's positions are
+//                stored in ASCENDING order, so the 16 warps of a CTA sweep the vector front to back
+//                together and most gathers hit lines another lane has just pulled into L1.
 //
 // Why a third formulation: the warp-cooperative sorters are bound by the ALU pipe (FMNMX at one
 // warp-instruction per two cycles per scheduler, ~470 of them per unit) although only four order
@@ -46,7 +52,8 @@ constexpr int kWinSample = 512;       // cells per class sampled by k_windows
 
 struct Step1PairArgs {
     Step1Args a;
-    const uint16_t *idxT;  // [2][nblk][m][32]: class-local grouped position of element j of subsample 32*blk + lane
+    const void *idxT;      // [2][nblk][m][32]: class-local grouped position of element j of subsample 32*blk + lane
+                           // (uint16_t, bank-spread order; BIG: uint32_t, ascending order)
     int64_t nblk;          // ceil(S_total / 32)
     const float2 *win;     // [G][2]: (scale, offset) of the bucket map of (gene, class)
     double *scratch;       // [grid][3][slots]
@@ -66,8 +73,9 @@ __device__ __forceinline__ uint32_t range_flags(uint32_t w, uint32_t lo4, uint32
 
 // Indices of one 16-element chunk.  The index table is zero-padded to a multiple of 16 rows, so the
 // loads (and the gathers they feed) need no bounds predicate.
-__device__ __forceinline__ void pair_load_pos(const uint16_t *__restrict__ ip, int j0, uint32_t (&pos)[16]) {
-    const uint16_t *ipc = ip + j0 * 32;  // element j of this thread's subsample sits at ip[32 * j]
+template <typename IT>
+__device__ __forceinline__ void pair_load_pos(const IT *__restrict__ ip, int j0, uint32_t (&pos)[16]) {
+    const IT *ipc = ip + j0 * 32;  // element j of this thread's subsample sits at ip[32 * j]
 #pragma unroll
     for (int u = 0; u < 16; ++u) pos[u] = (uint32_t)__ldg(ipc + u * 32);
 }
@@ -154,14 +162,29 @@ __device__ __forceinline__ T pick_reg(const T (&x)[N], int r) {
     return y;
 }
 
+// Where the values of the current class vector are read from: the staged copy in shared memory, or
+// (BIG) the gene-major matrix itself (L2 / L1).
+template <typename T, bool BIG>
+struct PairSrc {
+    uint32_t sa;   // shared address of element 0 (staged)
+    const T *gp;   // global address of element 0 (BIG)
+    __device__ __forceinline__ T at(uint32_t pos) const {
+        if (BIG) return __ldg(gp + pos);
+        return lds_pos(sa, pos, T(0));
+    }
+};
+
+template <bool BIG> struct PairIdx { typedef uint16_t type; };
+template <> struct PairIdx<true> { typedef uint32_t type; };
+
 template <typename T>
 struct PairCand {
     static constexpr int kMax = 64 / (int)sizeof(T);  // candidates per bucket range (64 bytes of the bucket-list area each)
 };
 
 // A bucket range with more than kMax elements: exact only if it is one tie group.
-template <typename T>
-__device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int m, uint32_t vals_sa, uint32_t blbase,
+template <typename T, typename IT, bool BIG>
+__device__ __noinline__ bool pair_big_range(const IT *__restrict__ ip, int m, const PairSrc<T, BIG> src, uint32_t blbase,
                                             uint32_t blo, uint32_t bhi, T &y) {
     const uint32_t lo4 = blo * 0x01010101u;
     const uint32_t hi4h = (bhi * 0x01010101u) | 0x80808080u;
@@ -177,7 +200,7 @@ __device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int
                 f &= f - 1u;
                 const int j = c * 16 + k * 4 + (bit >> 3);
                 if (j < m) {
-                    const T v = lds_pos(vals_sa, (uint32_t)__ldg(ip + j * 32), T(0));
+                    const T v = src.at((uint32_t)__ldg(ip + j * 32));
                     vmin = tmin(vmin, v);
                     vmax = tmax(vmax, v);
                 }
@@ -188,10 +211,12 @@ __device__ __noinline__ bool pair_big_range(const uint16_t *__restrict__ ip, int
     return vmin == vmax;
 }
 
-template <typename T, int NBW, bool FASTMOM>
+template <typename T, int NBW, bool FASTMOM, bool BIG>
 __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairArgs pa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename PairIdx<BIG>::type IT;
     constexpr int CM = PairCand<T>::kMax;
+    constexpr int RR = BIG ? 16 : 8;  // values per lane of the rescue sort (32 * RR >= m)
     const Step1Args &a = pa.a;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -237,9 +262,9 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
             const int64_t ncls = cls ? pa.n1 : pa.n0;
             const size_t b0 = ((size_t)e0 * sizeof(T)) & ~(size_t)15;
             const size_t b1 = (((size_t)(e0 + ncls) * sizeof(T)) + 15) & ~(size_t)15;
-            __syncthreads();  // every read of the previous class vector is done
+            __syncthreads();  // every read of the previous class vector (and of part[]) is done
             if (tid == 0) {
-                stage_row(smem_raw, row + b0, b1 - b0, bar);
+                if (!BIG) stage_row(smem_raw, row + b0, b1 - b0, bar);
                 // the vector staged next (this gene's case cells, or the control cells of the CTA's next gene)
                 // starts its trip from HBM to L2 now, under the work on this one
                 if (cls == 0) {
@@ -249,10 +274,14 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     prefetch_row_l2(row + (size_t)gridDim.x * (size_t)a.n_pad * sizeof(T), (((size_t)pa.n0 * sizeof(T)) + 15) & ~(size_t)15);
                 }
             }
-            const uint32_t vals_sa = smem_u32(smem_raw) + (uint32_t)((size_t)e0 * sizeof(T) - b0);
+            PairSrc<T, BIG> src;
+            src.sa = smem_u32(smem_raw) + (uint32_t)((size_t)e0 * sizeof(T) - b0);
+            src.gp = reinterpret_cast<const T *>(row) + e0;
             const float2 wn = __ldg(pa.win + (size_t)g * 2 + cls);
-            mbar_wait(bar, phase);
-            phase ^= 1u;
+            if (!BIG) {
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
             if (pa.prof != nullptr && tid == 0) atomicAdd(pa.prof + 15, 1ull);  // class passes (for averaging)
 
             long long t_mark = (pa.prof != nullptr && tid == 0) ? clock64() : 0;
@@ -268,7 +297,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                 const int64_t s = a.s_begin + slot;
                 const bool active = s < a.s_end;
                 const int64_t sa = active ? s : a.s_begin;
-                const uint16_t *ip = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sa >> 5)) * idx_rows) * 32u + (size_t)(sa & 31);
+                const IT *ip = static_cast<const IT *>(pa.idxT) + (((size_t)cls * (size_t)pa.nblk + (size_t)(sa >> 5)) * idx_rows) * 32u + (size_t)(sa & 31);
                 double sx = 0.0, qx = 0.0, iq = 0.0;
                 bool rescue = false;
                 if (active) {
@@ -277,21 +306,21 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     {
                         uint32_t pos[16], nxt[16];
                         pair_load_pos(ip, 0, pos);
-                        const float cshift = kFast ? (float)lds_pos(vals_sa, pos[0], T(0)) : 0.0f;
+                        const float cshift = kFast ? (float)src.at(pos[0]) : 0.0f;
                         int j0 = 0;
                         for (; j0 + 32 <= m_full; j0 += 32) {  // two chunks per trip: the index buffers swap roles
                             pair_load_pos(ip, j0 + 16, nxt);
                             {
                                 T v[16];
 #pragma unroll
-                                for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                                for (int u = 0; u < 16; ++u) v[u] = src.at(pos[u]);
                                 pair_chunk<T, false, kFast>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                             }
                             if (j0 + 32 < m) pair_load_pos(ip, j0 + 32, pos);
                             {
                                 T v[16];
 #pragma unroll
-                                for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, nxt[u], T(0));
+                                for (int u = 0; u < 16; ++u) v[u] = src.at(nxt[u]);
                                 pair_chunk<T, false, kFast>(v, j0 + 16, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                             }
                         }
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             if (j0 + 16 < m) pair_load_pos(ip, j0 + 16, nxt);
                             T v[16];
 #pragma unroll
-                            for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                            for (int u = 0; u < 16; ++u) v[u] = src.at(pos[u]);
                             pair_chunk<T, false, kFast>(v, j0, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
 #pragma unroll
                             for (int u = 0; u < 16; ++u) pos[u] = nxt[u];
@@ -307,7 +336,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         if (m_full < m) {
                             T v[16];
 #pragma unroll
-                            for (int u = 0; u < 16; ++u) v[u] = lds_pos(vals_sa, pos[u], T(0));
+                            for (int u = 0; u < 16; ++u) v[u] = src.at(pos[u]);
                             pair_chunk<T, true, kFast>(v, m_full, m, hbase, blbase, wn.x, wn.y, kTop, hdummy, cshift, sxp, qxp);
                         }
                         // sx: sum of the sample; qx: sum of squared deviations from its mean
@@ -320,7 +349,9 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     }
                     mark(8);
                     // ---- locate the four sorted positions in the histogram
-                    uint32_t wi = 0, x = lds_u32(hbase), s4 = (x * 0x01010101u) >> 24;
+                    // sum of the four counters of a word: m <= 255 keeps it below 256 (one IMAD); BIG needs the exact sum
+                    auto sum4 = [](uint32_t w) -> uint32_t { return BIG ? __dp4a(w, 0x01010101u, 0u) : (w * 0x01010101u) >> 24; };
+                    uint32_t wi = 0, x = lds_u32(hbase), s4 = sum4(x);
                     int cum = 0;
                     int B[4], E[4], C[4];
                     const int P[4] = {P0, P1, P2, P3};
@@ -330,7 +361,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             cum += (int)s4;
                             ++wi;
                             x = lds_u32(hbase + 128u * wi);
-                            s4 = (x * 0x01010101u) >> 24;
+                            s4 = sum4(x);
                         }
                         int run = cum;
                         uint32_t q = 0, c = x & 255u;
@@ -343,12 +374,22 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         E[t] = run;
                         C[t] = (int)c;
                     }
+                    // BIG (m > 255 possible): a one-byte counter wraps when 256 or more elements share a bucket (a big tie
+                    // group); the counters then no longer add up to the number of list entries and the sample goes
+                    // to the full sort below.  Nothing read from a wrapped histogram is trusted (all uses are bounded).
+                    bool wrapped = false;
+                    if (BIG) {
+                        int tot = cum + (int)s4;
+                        for (uint32_t w2 = wi + 1u; w2 < (uint32_t)NBW; ++w2) tot += (int)sum4(lds_u32(hbase + 128u * w2));
+                        wrapped = tot != nchunk * 16;
+                    }
                     const int cntL = E[1] + C[1] - E[0], cntH = E[3] + C[3] - E[2];
                     const bool smallL = cntL <= CM, smallH = cntH <= CM;
                     // ---- a range too big to enumerate is exact only if it is one tie group (needs the intact bucket list)
                     T tieL = T(0), tieH = T(0);
-                    if (!smallL) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[0], (uint32_t)B[1], tieL);
-                    if (!smallH) rescue = !pair_big_range<T>(ip, m, vals_sa, blbase, (uint32_t)B[2], (uint32_t)B[3], tieH) || rescue;
+                    if (!smallL) rescue = !pair_big_range<T, IT, BIG>(ip, m, src, blbase, (uint32_t)B[0], (uint32_t)B[1], tieL);
+                    if (!smallH) rescue = !pair_big_range<T, IT, BIG>(ip, m, src, blbase, (uint32_t)B[2], (uint32_t)B[3], tieH) || rescue;
+                    rescue = rescue || wrapped;
                     mark(9);
                     // ---- one pass over the bucket list: words holding an element of either bucket range become
                     //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
@@ -370,7 +411,8 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                                 const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
                                 const uint32_t f = fl | (fh >> 1);
                                 if (f) {
-                                    sts_u32(blbase + 4u * (uint32_t)nrec, f | (uint32_t)(4 * c + k));
+                                    const uint32_t wno = (uint32_t)(4 * c + k);  // < 64 (BIG: < 128, bit 6 goes to byte 1)
+                                    sts_u32(blbase + 4u * (uint32_t)nrec, f | (BIG ? ((wno & 63u) | ((wno >> 6) << 8)) : wno));
                                     ++nrec;
                                 }
                             }
@@ -381,14 +423,18 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     int nL = 0, nH = 0;
                     for (int i = 0; i < nrec; ++i) {
                         const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
-                        const int wj = (int)(rec & 63u) * 4;
+                        const int wj = (int)(BIG ? ((rec & 63u) | ((rec >> 2) & 0xFC0u)) : (rec & 63u)) * 4;
                         uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
                         while (f) {
                             const int bit = __ffs((int)f) - 1;
                             f &= f - 1u;
                             const bool hi = (bit & 1) == 0;
                             const int cnt = hi ? nH : nL;
-                            if (cnt < CM) sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), (uint32_t)(wj + (bit >> 3)));  // NBW >= 8
+                            if (cnt < CM) {
+                                const uint32_t jn = (uint32_t)(wj + (bit >> 3));
+                                sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), jn);  // NBW >= 8
+                                if (BIG) sts_u8(hist_addr(hbase, (uint32_t)(32 + cnt + (hi ? 16 : 0))), jn >> 8);  // NBW >= 16
+                            }
                             nH += hi ? 1 : 0;
                             nL += hi ? 0 : 1;
                         }
@@ -405,14 +451,18 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
-                                const uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
-                                const uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
+                                uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
+                                uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
+                                if (BIG) {
+                                    jl |= okl ? lds_u8(hist_addr(hbase, 32u + (uint32_t)(i0 + u))) << 8 : 0u;
+                                    jh |= okh ? lds_u8(hist_addr(hbase, 48u + (uint32_t)(i0 + u))) << 8 : 0u;
+                                }
                                 pl[u] = (uint32_t)__ldg(ip + jl * 32u);
                                 ph[u] = (uint32_t)__ldg(ip + jh * 32u);
                             }
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const T vl = lds_pos(vals_sa, pl[u], T(0)), vh = lds_pos(vals_sa, ph[u], T(0));
+                                const T vl = src.at(pl[u]), vh = src.at(ph[u]);
                                 if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
                                 if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
                             }
@@ -477,15 +527,15 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     const int L = __ffs((int)todo) - 1;
                     todo &= todo - 1u;
                     const int64_t sL = __shfl_sync(kFull, s, L);
-                    const uint16_t *ipL = pa.idxT + (((size_t)cls * (size_t)pa.nblk + (size_t)(sL >> 5)) * idx_rows) * 32u + (size_t)(sL & 31);
-                    T v[8];
+                    const IT *ipL = static_cast<const IT *>(pa.idxT) + (((size_t)cls * (size_t)pa.nblk + (size_t)(sL >> 5)) * idx_rows) * 32u + (size_t)(sL & 31);
+                    T v[RR];
 #pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
+                    for (int rr = 0; rr < RR; ++rr) {
                         const int j = lane + 32 * rr;
-                        v[rr] = (j < m) ? lds_pos(vals_sa, (uint32_t)__ldg(ipL + j * 32), T(0)) : Lim<T>::inf();
+                        v[rr] = (j < m) ? src.at((uint32_t)__ldg(ipL + j * 32)) : Lim<T>::inf();
                     }
-                    warp_sort_asc<T, 8>(v, lane);
-                    const double iqL = iqr_of_sorted<T, 8>(v, a.q);
+                    warp_sort_asc<T, RR>(v, lane);
+                    const double iqL = iqr_of_sorted<T, RR>(v, a.q);
                     if (lane == L) iq = iqL;
                 }
                 if (active) {
@@ -583,17 +633,22 @@ __global__ void __launch_bounds__(256) k_windows(const void *__restrict__ xg, in
 struct PairGeometry {
     int threads = 0, rounds = 0, bl_stride = 0, vals_bytes = 0, nbw = 0;
     size_t smem = 0;
+    bool big = false;
 };
+constexpr int kPairBigMaxM = 496;  // 31 chunks: word numbers < 128, element numbers < 512, rescue sort of 32 * 16
 
 // Shared-memory budget and thread count for S_local subsamples.  threads == 0: not eligible.
 // Among the two histogram widths, the one that needs fewer rounds wins (more resident threads);
 // on a tie the finer histogram (fewer candidates per range).
 template <typename T>
-static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_local, int force_nbw = 0) {
+static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_local, int force_nbw = 0, bool big = false,
+                                  int max_threads = kPairMaxThreads) {
     PairGeometry best;
-    if (m < 1 || m > 255 || n0 > 65536 || n1 > 65536 || S_local < 1) return best;
+    best.big = big;
+    if (m < 1 || S_local < 1) return best;
+    if (big ? (m > kPairBigMaxM) : (m > 255 || n0 > 65536 || n1 > 65536)) return best;
     const int64_t nmax = n0 > n1 ? n0 : n1;
-    const int vals_bytes = (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
+    const int vals_bytes = big ? 0 : (int)((nmax * (int64_t)sizeof(T) + 32 + 127) / 128 * 128);
     int chunks = (int)((m + 15) / 16);
     if (chunks < 9) chunks = 9;       // the first 128 bytes double as the candidate-value area
     if ((chunks & 1) == 0) ++chunks;  // stride = 16 bytes * odd: 128-bit bucket-list accesses are conflict-free
@@ -604,7 +659,7 @@ static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_l
         const size_t per_thread = (size_t)(4 * nbw) + (size_t)bl_stride;
         if (fixed + 64 * per_thread > (size_t)kMaxSmemOptin) continue;
         int tmax = (int)(((size_t)kMaxSmemOptin - fixed) / per_thread) / 32 * 32;
-        if (tmax > kPairMaxThreads) tmax = kPairMaxThreads;
+        if (tmax > max_threads) tmax = max_threads;
         const int rounds = (int)((S_local + tmax - 1) / tmax);
         int t = (int)((S_local + rounds - 1) / rounds);
         t = (t + 31) / 32 * 32;
@@ -623,18 +678,24 @@ static PairGeometry pair_geometry(int64_t n0, int64_t n1, int64_t m, int64_t S_l
 // Returns 1 when the pair-per-thread path does not apply (caller falls back to the warp sorters).
 template <typename T>
 static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
-    if (!c->idxT_ok || c->step1_impl == 1) return 1;
+    if (c->step1_impl == 1) return 1;
     const int64_t S_local = args.s_end - args.s_begin;
-    const PairGeometry ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local, c->pair_nbw);
+    PairGeometry ge;
+    if (c->idxT_ok && !c->pair_force_big) ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local, c->pair_nbw);
+    if (ge.threads == 0 && c->idxT32_ok)  // no staged geometry: gather from global memory (config-5 regime)
+        ge = pair_geometry<T>(c->n0, c->n1, args.m, S_local, c->pair_nbw, true, c->pair_big_threads);
     if (ge.threads == 0) return 1;
     const bool fast = c->fast_moments && sizeof(T) == 4;
-    auto kern = ge.nbw == 32 ? (fast ? k_step1p<T, 32, true> : k_step1p<T, 32, false>)
-                             : (fast ? k_step1p<T, 16, true> : k_step1p<T, 16, false>);
+    auto kern = ge.big ? (ge.nbw == 32 ? (fast ? k_step1p<T, 32, true, true> : k_step1p<T, 32, false, true>)
+                                       : (fast ? k_step1p<T, 16, true, true> : k_step1p<T, 16, false, true>))
+                       : (ge.nbw == 32 ? (fast ? k_step1p<T, 32, true, false> : k_step1p<T, 32, false, false>)
+                                       : (fast ? k_step1p<T, 16, true, false> : k_step1p<T, 16, false, false>));
     PHET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ge.smem));
     int per_sm = 0;
     PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ge.threads, ge.smem));
     if (per_sm < 1) return 1;
     const int64_t ng = args.g_end - args.g_begin;
+    if (ge.big) per_sm = 1;  // a second CTA would bring a second class vector into the same L1 (measured: 4x slower)
     int64_t grid = (int64_t)per_sm * c->num_sms;
     if (grid > ng) grid = ng;
     if (grid < 1) return 0;
@@ -654,7 +715,7 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     }
     Step1PairArgs pa;
     pa.a = args;
-    pa.idxT = c->idxT.p;
+    pa.idxT = ge.big ? static_cast<const void *>(c->idxT32.p) : static_cast<const void *>(c->idxT.p);
     pa.nblk = (c->S + 31) / 32;
     pa.win = c->win.p;
     pa.scratch = c->pair_scratch.p;
@@ -669,7 +730,7 @@ static int run_step1_pair(phet_ctx *c, const Step1Args &args) {
     c->step1_geom[1] = ge.threads;
     c->step1_geom[2] = (int32_t)ge.smem;
     c->step1_geom[3] = 4 * ge.nbw - 1;  // buckets
-    c->step1_geom[4] = 1 | 4;  // staged; bit 2: pair-per-thread bucket-select path
+    c->step1_geom[4] = (ge.big ? 0 : 1) | 4;  // bit 0: staged; bit 2: pair-per-thread bucket-select path
     kern<<<(unsigned)grid, ge.threads, ge.smem, c->stream>>>(pa);
     c->launches++;
     PHET_CUDA(cudaGetLastError());

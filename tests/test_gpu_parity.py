@@ -265,12 +265,74 @@ def test_step3_prune_path_equals_sort_path(name, perm, monkeypatch):
     assert np.array_equal(out["auto"][0], out["sort"][0])
 
 
-def test_big_class_fallback_matches_oracle():
-    """Classes above 65,536 cells (BASELINE config 5's regime) cannot use the 16-bit index table of the
-    select kernel and do not fit shared memory: the warp-cooperative sorters gather from L2 instead.
-    140,000 cells -> m = 264 (full-warp sorter), 266 KS slices; checked against the oracle."""
+def _global_gather_cases():
+    """Inputs for the global-gather instantiation of the select kernel (BASELINE config 5's regime:
+    m > 255 and/or classes that cannot be staged in shared memory)."""
+    rng = np.random.default_rng(21)
+    cases = dict(_adversarial_cases())
+    X = rng.gamma(2.0, 1.0, (1500, 16))
+    cases["m_316"] = (X, 700, dict(num_subsamples=40, subsampling_size=316))
+    cases["m_496_p1090"] = (X, 750, dict(num_subsamples=33, subsampling_size=496, percentiles=(10, 90)))
+    # tie groups of 256 and more elements in one bucket: the one-byte counters wrap -> full-sort rescue
+    X = rng.poisson(0.3, (1600, 12)).astype(np.float64)
+    X[:, 0] = 1.0
+    cases["m_400_big_ties"] = (X, 800, dict(num_subsamples=35, subsampling_size=400))
+    X = rng.integers(0, 3, (1200, 10)).astype(np.float64)
+    cases["m_300_three_levels"] = (X, 600, dict(num_subsamples=33, subsampling_size=300, percentiles=(30, 70)))
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_global_gather_cases()))
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_step1_global_gather_path_equals_sort_path(name, dt, monkeypatch):
+    """k_step1p<BIG> (values gathered from global memory through 32-bit ascending positions, exact word
+    sums, wrap detection of the byte counters, 16-bit element numbers) against the sorting kernels."""
+    from phet_b200 import PHet
+    X, n0, kw = _global_gather_cases()[name]
+    X = np.ascontiguousarray(X.astype(dt))
+    y = np.r_[np.zeros(n0, dtype=np.int64), np.ones(X.shape[0] - n0, dtype=np.int64)]
+    out = {}
+    monkeypatch.setenv("PHET_STEP1_FORCE_BIG", "1")
+    for impl, nbw in (("auto", "32"), ("auto", "16"), ("warp", "0")):
+        monkeypatch.setenv("PHET_STEP1_IMPL", impl)
+        monkeypatch.setenv("PHET_STEP1_NBW", nbw)
+        np.random.seed(99)
+        est = PHet(**kw, capture=True, distributed=False, permutation="device")
+        est.fit_predict(X, y)
+        out[impl + nbw] = (est.R_.copy(), est.P_.copy(), est.step1_geometry_)
+    ref = out["warp0"]
+    assert ref[2]["path"] != "pair-per-thread"
+    for key, buckets in (("auto32", 127), ("auto16", 63)):
+        got = out[key]
+        assert got[2]["path"] == "pair-per-thread" and got[2]["E"] == buckets and not got[2]["staged"]
+        assert np.array_equal(got[0], ref[0]), "delta-IQR differs between the select and the sort path"
+        assert np.allclose(got[1], ref[1], rtol=1e-11 if dt == np.float64 else 2e-4, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_global_gather_path_matches_reference(name, monkeypatch):
+    """Every golden case again with the global-gather instantiation of Step 1 forced."""
+    monkeypatch.setenv("PHET_STEP1_FORCE_BIG", "1")
+    g = load_golden(name)
+    for tag in g["dtypes"]:
+        est, scores = _run(g, tag)
+        assert est.step1_geometry_["path"] == "pair-per-thread" and not est.step1_geometry_["staged"]
+        ks = g[f"P_head_{tag}"].shape[1]
+        rtol = RTOL[tag]
+        assert np.allclose(est.R_[:, :ks], g[f"R_head_{tag}"], rtol=rtol, atol=1e-5 if tag == "f32" else 1e-12)
+        assert np.allclose(est.P_[:, :ks], g[f"P_head_{tag}"], rtol=rtol, atol=1e-300)
+        assert np.array_equal(est.bin_counts_, g[f"bin_counts_{tag}"])
+        assert np.allclose(scores, g[f"scores_{tag}"], rtol=rtol, atol=1e-12)
+
+
+@pytest.mark.parametrize("impl", ["auto", "warp"])
+def test_big_class_matches_oracle(impl, monkeypatch):
+    """Classes above 65,536 cells (BASELINE config 5's regime) cannot use the 16-bit index table and do
+    not fit shared memory.  140,000 cells -> m = 264, 266 KS slices.  auto: the global-gather select kernel;
+    warp: the warp-cooperative sorters gathering from L2 (the fallback).  Both against the oracle."""
     from oracle import phet_oracle as po
     from phet_b200 import PHet
+    monkeypatch.setenv("PHET_STEP1_IMPL", impl)
     rng = np.random.default_rng(11)
     N, G, S = 140000, 6, 5
     y = np.r_[np.zeros(N // 2, dtype=np.int64), np.ones(N - N // 2, dtype=np.int64)]
@@ -279,9 +341,11 @@ def test_big_class_fallback_matches_oracle():
     np.random.seed(3)
     est = PHet(num_subsamples=S, capture=True, distributed=False)
     scores = est.fit_predict(X, y)
-    assert est.step1_geometry_["path"] == "full-warp" and not est.step1_geometry_["staged"]
+    assert not est.step1_geometry_["staged"]
+    assert est.step1_geometry_["path"] == ("pair-per-thread" if impl == "auto" else "full-warp")
     np.random.seed(3)
     ref = po.fit_predict_oracle(X, y, num_subsamples=S)
     assert np.array_equal(est.H_, ref.H)
     assert np.array_equal(est.bin_counts_, ref.bin_counts)
+    assert np.allclose(est.R_, ref.R, rtol=1e-5, atol=1e-12) and np.allclose(est.P_, ref.P, rtol=1e-5, atol=1e-300)
     assert np.allclose(scores, ref.scores, rtol=1e-5, atol=1e-12)
