@@ -194,6 +194,16 @@ int phet_step1_geometry(phet_ctx *ctx, int32_t out[5]);
 /* Kernel family of the last Step-3 launch: 1 full-warp sort, 2 half-warp sort, 3 bound-and-prune. */
 int phet_step3_path(phet_ctx *ctx);
 
+/* Whole-vector statistics of every resident gene, for the reference's sibling IQR scorers
+ * (replaces the per-gene Python loops of src/model/hvf.py:86-93 [HIQR] and
+ * src/model/deltaiqrmean.py:53-85 [DeltaIQRMean]: scipy.stats.iqr, np.mean and the moments that
+ * scipy.stats.ttest_ind needs, over ALL cells of a class / of the data set).
+ * q3[0], q3[1], q3[2]: sorted positions of the two percentiles for n0, n1 and n0+n1 elements
+ * (scipy's 'linear' rule, as phet_step1_params.q).  out: host double[7][G] =
+ * iqr(class 0), iqr(class 1), iqr(all cells), mean(class 0), mean(class 1),
+ * sum of squared deviations (class 0), (class 1).  Order statistics are exact (radix select). */
+int phet_class_stats(phet_ctx *ctx, const phet_quantile_pos *q3, double *out);
+
 /* One-call convenience: everything above on one device with host buffers (used by C callers
  * and by the end-to-end benchmark leg).  perm_mode/seed as in phet_step3; with PHET_PERM_HOST
  * perm_ctrl/perm_case must be given.  scores_out: host double[G]. */

@@ -7,5 +7,6 @@ Host side in Python (like the reference), device side in hand-written CUDA behin
 ``include/phet_b200.h`` (``phet_b200/libphet_b200.so``, built by ``python -m phet_b200.build``).
 """
 from .phet import PHet  # noqa: F401
+from .siblings import HIQR, DeltaIQRMean  # noqa: F401
 
-__all__ = ["PHet"]
+__all__ = ["PHet", "HIQR", "DeltaIQRMean"]

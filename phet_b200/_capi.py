@@ -25,7 +25,7 @@ EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
-    "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host",
+    "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -107,6 +107,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_step1_geometry.argtypes = [vp, C.POINTER(i32)]
     lib.phet_fit_host.argtypes = [vp, vp, C.c_int, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp,
                                   C.POINTER(FitParams), vp, vp]
+    lib.phet_class_stats.argtypes = [vp, C.POINTER(QuantilePos), vp]
     lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
     lib.phet_host_p_two_sided_t.restype = dbl
     lib.phet_host_p_two_sided_z.argtypes = [dbl]
@@ -178,6 +179,14 @@ class Context:
         st = dtype if storage is None else storage
         _check(self.lib.phet_load_matrix(self.h, C.c_void_p(dev_ptr), 1, N, G, dtype, normalize, st))
         self.N, self.G = N, G
+
+    def class_stats(self, q3):
+        """q3: three QuantilePos (class 0, class 1, all cells).  Returns float64 (7, G): iqr0, iqr1, iqr_all,
+        mean0, mean1, ss0, ss1 (include/phet_b200.h: phet_class_stats)."""
+        arr = (QuantilePos * 3)(*q3)
+        out = np.empty((7, self.G), dtype=np.float64)
+        _check(self.lib.phet_class_stats(self.h, arr, _ptr(out)))
+        return out
 
     def set_index_sets(self, idx: np.ndarray):
         """idx: int32 (S, 2, m), original row numbers; [:, 0] control draw, [:, 1] case draw."""

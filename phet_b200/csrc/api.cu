@@ -348,6 +348,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->edges.release();
     c->weights.release();
     c->counts.release();
+    c->class_stats.release();
     c->stage[0].release();
     c->stage[1].release();
     for (int i = 0; i < 2; ++i) {
@@ -753,6 +754,27 @@ int phet_finalize(phet_ctx *c, int64_t S_total, const double *weights, int32_t B
     PHET_CUDA(cudaMemcpyAsync(c->weights.p, weights, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
     c->n_bins = B;
     return launch_finalize(c, S_total, B, scores_out, counts_out, edges_out);  // synchronises: weights is a host buffer
+}
+
+int phet_class_stats(phet_ctx *c, const phet_quantile_pos *q3, double *out) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set && c->classes_set, "load the classes and the matrix before phet_class_stats");
+    PHET_REQUIRE(q3 != nullptr && out != nullptr, "q3/out NULL");
+    PHET_REQUIRE(c->n0 >= 1 && c->n1 >= 1, "both classes need at least one cell");
+    PHET_REQUIRE(c->n0 + c->n1 < (int64_t(1) << 25), "phet_class_stats: at most 2^25 - 1 cells (16-bit per-thread digit counters)");
+    PHET_REQUIRE(c->xg_g0 == 0 && c->xg_rows == c->G, "phet_class_stats needs every gene resident");
+    const int64_t nv[3] = {c->n0, c->n1, c->n0 + c->n1};
+    for (int i = 0; i < 3; ++i) {
+        const phet_quantile_pos &q = q3[i];
+        PHET_REQUIRE(q.j_lo >= 0 && q.j_lo <= q.k_lo && q.k_lo <= q.j_lo + 1 && q.k_lo < nv[i] && q.j_hi >= 0 &&
+                         q.j_hi <= q.k_hi && q.k_hi <= q.j_hi + 1 && q.k_hi < nv[i],
+                     "quantile positions outside the vector");
+    }
+    PHET_CUDA(cudaSetDevice(c->device));
+    if (int e = c->class_stats.alloc((size_t)7 * c->G)) return e;
+    if (int e = launch_class_stats(c, 0, c->G, q3, c->class_stats.p)) return e;
+    PHET_CUDA(cudaMemcpyAsync(out, c->class_stats.p, sizeof(double) * 7 * c->G, cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
 }
 
 static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {

@@ -1,0 +1,271 @@
+// Whole-vector statistics per gene: exact order statistics (for the IQR), mean and sum of squared
+// deviations of the control cells, the case cells and all cells of every gene.  This is what the two
+// sibling IQR scorers of the reference need:
+//
+//   HIQR           src/model/hvf.py:59-96          iqr(X[:, g]) or sum over classes of iqr(X[class, g])
+//   DeltaIQRMean   src/model/deltaiqrmean.py:53-85 iqr / mean / ttest_ind of class 0 against class 1
+//
+// They are the S = 1, m = class-size corner of PHet's Step 1, where sorting networks and the
+// thread-per-sample select do not apply (m is 10^4 .. 10^5); the kernel is a block-wide exact MSB radix
+// select instead.
+//
+// One CTA per gene.  The gene's row of the gene-major, class-grouped matrix ([control | case]) is read
+// from global memory with coalesced loads; after the first pass it sits in L2/L1.  Six selections run at
+// once ("tracks": low and high percentile of control, case and pooled); a pass consumes 4 bits of the
+// order-preserving key of every element.  Every thread counts the digits of its elements in private
+// 16-bit counters (6 tracks x 16 digits, words interleaved by lane: bank == lane, conflict-free, no
+// atomics, deterministic); the CTA reduces them (REDUX + one SMEM hop) and one thread per track fixes the
+// next digit.  After 8 (f32) / 16 (f64) passes each track holds the exact key of y[j]; one more pass gives
+// y[j+1] (the smallest value above y[j], or y[j] itself when the tie group reaches rank j+1).
+// Moments: two passes in fp64 (sum, then squared deviations from the mean) with fixed-order reductions.
+#include "common.cuh"
+#include "warp_prims.cuh"
+
+namespace phet {
+
+constexpr int kCsThreads = 512;
+constexpr int kCsTracks = 6;   // (class 0, class 1, pooled) x (low, high)
+
+template <typename T> struct CsKey;
+template <> struct CsKey<float> {
+    typedef uint32_t type;
+    static constexpr int bits = 32;
+    static __device__ __forceinline__ uint32_t of(float v) {
+        const uint32_t u = __float_as_uint(v);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    }
+    static __device__ __forceinline__ float back(uint32_t k) {
+        return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+    }
+};
+template <> struct CsKey<double> {
+    typedef unsigned long long type;
+    static constexpr int bits = 64;
+    static __device__ __forceinline__ unsigned long long of(double v) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    }
+    static __device__ __forceinline__ double back(unsigned long long k) {
+        return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+    }
+};
+
+// (1 - g) * y[j] + g * y[j+1] and the difference of the two percentiles, in X's dtype and scipy's operation
+// order (scipy.stats._quantile._quantile_hf last line; iqr = pct[1] - pct[0]), no contraction.
+__device__ __forceinline__ double cs_iqr(float yjl, float ykl, float yjh, float ykh, double g_lo, double g_hi) {
+    const float gl = (float)g_lo, gh = (float)g_hi;
+    const float ql = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, gl), yjl), __fmul_rn(gl, ykl));
+    const float qh = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, gh), yjh), __fmul_rn(gh, ykh));
+    return (double)__fsub_rn(qh, ql);
+}
+__device__ __forceinline__ double cs_iqr(double yjl, double ykl, double yjh, double ykh, double g_lo, double g_hi) {
+    const double ql = __dadd_rn(__dmul_rn(__dsub_rn(1.0, g_lo), yjl), __dmul_rn(g_lo, ykl));
+    const double qh = __dadd_rn(__dmul_rn(__dsub_rn(1.0, g_hi), yjh), __dmul_rn(g_hi, ykh));
+    return __dsub_rn(qh, ql);
+}
+
+struct ClassStatsArgs {
+    const void *xg;
+    int64_t n_pad, xg_g0, g_begin, g_end, n0, n1;
+    phet_quantile_pos q[3];   // positions for n0, n1 and n0 + n1 elements
+    double *out;              // [7][G]: iqr0, iqr1, iqr_all, mean0, mean1, ss0, ss1
+    int64_t G;
+};
+
+// fixed-order block sum of one double per thread; result broadcast to all threads
+__device__ __forceinline__ double cs_block_sum(double v, double *red, int tid) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kCsThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsArgs a) {
+    typedef typename CsKey<T>::type K;
+    constexpr int NPASS = CsKey<T>::bits / 4;
+    extern __shared__ __align__(16) uint32_t cnt[];              // [warp][word][lane], two 16-bit counters per word (96 KB)
+    __shared__ uint32_t wpart[kCsThreads / 32][kCsTracks * 16]; // per-warp digit counts
+    __shared__ double red[kCsThreads / 32];
+    __shared__ K prefix[kCsTracks];
+    __shared__ int64_t rank[kCsTracks];
+    __shared__ unsigned long long cle[kCsTracks];   // elements <= y[j]
+    __shared__ K kmin[kCsTracks];                   // smallest key above y[j]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *mine = cnt + (size_t)warp * (kCsTracks * 8 * 32) + lane;   // word w of this thread at mine[32 * w]
+    const int64_t n0 = a.n0, n = a.n0 + a.n1;
+    const int64_t nvec[3] = {a.n0, a.n1, n};
+
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
+        // ---- moments: mean, then squared deviations (two passes, like numpy's mean / var)
+        double s0 = 0.0, s1 = 0.0;
+        for (int64_t i = tid; i < n; i += kCsThreads) {
+            const double v = (double)__ldg(row + i);
+            if (i < n0) s0 += v; else s1 += v;
+        }
+        const double mean0 = cs_block_sum(s0, red, tid) / (double)a.n0;
+        const double mean1 = cs_block_sum(s1, red, tid) / (double)a.n1;
+        double d0 = 0.0, d1 = 0.0;
+        for (int64_t i = tid; i < n; i += kCsThreads) {
+            const double v = (double)__ldg(row + i);
+            if (i < n0) { const double d = v - mean0; d0 = fma(d, d, d0); }
+            else { const double d = v - mean1; d1 = fma(d, d, d1); }
+        }
+        const double ss0 = cs_block_sum(d0, red, tid);
+        const double ss1 = cs_block_sum(d1, red, tid);
+
+        // ---- radix select of y[j_lo] and y[j_hi] of the three vectors
+        if (tid < kCsTracks) {
+            prefix[tid] = 0;
+            const phet_quantile_pos &q = a.q[tid >> 1];
+            rank[tid] = (tid & 1) ? q.j_hi : q.j_lo;
+        }
+        for (int w = 0; w < kCsTracks * 8; ++w) mine[32 * w] = 0u;
+        __syncthreads();
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const int shift = CsKey<T>::bits - 4 * (pass + 1);
+            K pf[kCsTracks];
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
+            for (int64_t i = tid; i < n; i += kCsThreads) {
+                const K key = CsKey<T>::of(__ldg(row + i));
+                const uint32_t dig = (uint32_t)(key >> shift) & 15u;
+                const K hi = (pass == 0) ? K(0) : (key >> (shift + 4));   // digits already fixed
+                const int c = (i < n0) ? 0 : 1;
+#pragma unroll
+                for (int t = 0; t < kCsTracks; ++t) {
+                    const bool member = (t >> 1) == 2 || (t >> 1) == c;
+                    const K want = (pass == 0) ? K(0) : (pf[t] >> (shift + 4));
+                    if (member && hi == want) mine[32 * (t * 8 + (dig >> 1))] += (dig & 1u) ? 0x10000u : 1u;
+                }
+            }
+            // warp totals of the 96 counters (a thread sees at most n / 512 + 1 elements: no 16-bit overflow
+            // for n < 2^25), then the CTA totals, then one thread per track picks the digit
+            for (int w = 0; w < kCsTracks * 8; ++w) {
+                const uint32_t x = mine[32 * w];
+                mine[32 * w] = 0u;
+                const uint32_t lo = __reduce_add_sync(kFull, x & 0xFFFFu), hi = __reduce_add_sync(kFull, x >> 16);
+                if (lane == 0) {
+                    wpart[warp][2 * w] = lo;
+                    wpart[warp][2 * w + 1] = hi;
+                }
+            }
+            __syncthreads();
+            if (tid < kCsTracks) {
+                int64_t r = rank[tid], cum = 0;
+                int d = 0;
+                for (; d < 16; ++d) {
+                    int64_t cd = 0;
+                    for (int w = 0; w < kCsThreads / 32; ++w) cd += wpart[w][tid * 16 + d];
+                    if (cum + cd > r || d == 15) break;
+                    cum += cd;
+                }
+                rank[tid] = r - cum;
+                prefix[tid] |= (K)d << shift;
+            }
+            __syncthreads();
+        }
+        // ---- y[j+1]: count of elements <= y[j] and the smallest key above it, per track
+        {
+            K pf[kCsTracks];
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
+            unsigned long long le[kCsTracks];
+            K mn[kCsTracks];
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) {
+                le[t] = 0ull;
+                mn[t] = ~K(0);
+            }
+            for (int64_t i = tid; i < n; i += kCsThreads) {
+                const K key = CsKey<T>::of(__ldg(row + i));
+                const int c = (i < n0) ? 0 : 1;
+#pragma unroll
+                for (int t = 0; t < kCsTracks; ++t) {
+                    const bool member = (t >> 1) == 2 || (t >> 1) == c;
+                    if (member) {
+                        if (key <= pf[t]) ++le[t];
+                        else if (key < mn[t]) mn[t] = key;
+                    }
+                }
+            }
+            if (tid < kCsTracks) {
+                cle[tid] = 0ull;
+                kmin[tid] = ~K(0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) {
+                unsigned long long l = le[t];
+                K mk = mn[t];
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    l += __shfl_xor_sync(kFull, l, o);
+                    const K other = __shfl_xor_sync(kFull, mk, o);
+                    mk = other < mk ? other : mk;
+                }
+                if (lane == 0) {
+                    atomicAdd(&cle[t], l);       // integer sum / min: order-independent, deterministic
+                    atomicMin(&kmin[t], mk);
+                }
+            }
+            __syncthreads();
+        }
+        if (tid < 3) {
+            const phet_quantile_pos &q = a.q[tid];
+            T y[2][2];
+            for (int h = 0; h < 2; ++h) {
+                const int t = tid * 2 + h;
+                const int64_t j = h ? q.j_hi : q.j_lo, k = h ? q.k_hi : q.k_lo;
+                const T yj = CsKey<T>::back(prefix[t]);
+                T yk = yj;
+                if (k > j && (int64_t)cle[t] < j + 2) yk = CsKey<T>::back(kmin[t]);
+                y[h][0] = yj;
+                y[h][1] = yk;
+            }
+            a.out[(size_t)tid * a.G + g] = (nvec[tid] > 0) ? cs_iqr(y[0][0], y[0][1], y[1][0], y[1][1], q.g_lo, q.g_hi) : 0.0;
+        }
+        if (tid == 0) {
+            a.out[(size_t)3 * a.G + g] = mean0;
+            a.out[(size_t)4 * a.G + g] = mean1;
+            a.out[(size_t)5 * a.G + g] = ss0;
+            a.out[(size_t)6 * a.G + g] = ss1;
+        }
+        __syncthreads();
+    }
+}
+
+int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_quantile_pos *q3, double *out_dev) {
+    ClassStatsArgs a;
+    a.xg = c->xg.p;
+    a.n_pad = c->n_pad;
+    a.xg_g0 = c->xg_g0;
+    a.g_begin = g_begin;
+    a.g_end = g_end;
+    a.n0 = c->n0;
+    a.n1 = c->n1;
+    for (int i = 0; i < 3; ++i) a.q[i] = q3[i];
+    a.out = out_dev;
+    a.G = c->G;
+    const int64_t ng = g_end - g_begin;
+    if (ng < 1) return PHET_OK;
+    int64_t grid = c->num_sms;
+    if (grid > ng) grid = ng;
+    const int smem = kCsTracks * 8 * kCsThreads * (int)sizeof(uint32_t);
+    if (c->storage == PHET_F32) {
+        PHET_CUDA(cudaFuncSetAttribute(k_class_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_class_stats<float><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
+    } else {
+        PHET_CUDA(cudaFuncSetAttribute(k_class_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_class_stats<double><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
+    }
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return PHET_OK;
+}
+
+}  // namespace phet

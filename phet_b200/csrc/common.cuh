@@ -129,6 +129,7 @@ struct phet_ctx {
     phet::DevBuf<double> scalars;        // small scratch: sums, min/max
     phet::DevBuf<double> edges, weights;
     phet::DevBuf<unsigned long long> counts;
+    phet::DevBuf<double> class_stats;    // [7][G] (phet_class_stats)
 
     int32_t step1_geom[5] = {0, 0, 0, 0, 0};
 };
@@ -143,6 +144,7 @@ int launch_step1(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t s_begin, i
 int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, uint64_t seed,
                  int64_t n_last);
 int launch_fisher(phet_ctx *c, int64_t S_total);
+int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_quantile_pos *q3, double *out_dev);
 int launch_o_minmax(phet_ctx *c, double out[2]);
 int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
