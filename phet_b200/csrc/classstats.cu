@@ -15,9 +15,12 @@
 // order-preserving key of every element.  Every thread counts the digits of its elements in private
 // 16-bit counters (6 tracks x 16 digits, words interleaved by lane: bank == lane, conflict-free, no
 // atomics, deterministic); the CTA reduces them (REDUX + one SMEM hop) and one thread per track fixes the
-// next digit.  After 8 (f32) / 16 (f64) passes each track holds the exact key of y[j]; one more pass gives
-// y[j+1] (the smallest value above y[j], or y[j] itself when the tie group reaches rank j+1).
-// Moments: two passes in fp64 (sum, then squared deviations from the mean) with fixed-order reductions.
+// next digit.  Three passes over the row fix 12 bits (sign, exponent, 3 mantissa bits); a fourth pass
+// compacts the few per cent of the elements that share those bits with a track into a shared-memory list
+// per track (warp-aggregated appends), and the remaining digits and y[j+1] (the smallest value above y[j],
+// or y[j] itself when its tie group reaches rank j+1) come from the lists.  A list that overflows (a tie
+// group of thousands of equal values) sends the gene back to passes over the whole row: always exact.
+// Moments ride on the first pass in fp64 (deviations from the first cell of the class), fixed-order sums.
 #include "common.cuh"
 #include "warp_prims.cuh"
 
@@ -83,68 +86,46 @@ __device__ __forceinline__ double cs_block_sum(double v, double *red, int tid) {
     return t;
 }
 
+template <typename T> struct CsList { static constexpr int cap = 4096; };   // keys per track kept in shared memory
+template <> struct CsList<double> { static constexpr int cap = 2048; };
+constexpr int kCsFullPasses = 3;   // digits fixed by passes over the whole row before the candidates are compacted
+
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsArgs a) {
     typedef typename CsKey<T>::type K;
     constexpr int NPASS = CsKey<T>::bits / 4;
+    constexpr int LCAP = CsList<T>::cap;
     extern __shared__ __align__(16) uint32_t cnt[];              // [warp][word][lane], two 16-bit counters per word (96 KB)
+    K *lists = reinterpret_cast<K *>(cnt + kCsTracks * 8 * kCsThreads);   // [track][LCAP] candidate keys (96 KB)
     __shared__ uint32_t wpart[kCsThreads / 32][kCsTracks * 16]; // per-warp digit counts
     __shared__ double red[kCsThreads / 32];
     __shared__ K prefix[kCsTracks];
     __shared__ int64_t rank[kCsTracks];
-    __shared__ unsigned long long cle[kCsTracks];   // elements <= y[j]
+    __shared__ unsigned long long cle[kCsTracks];   // elements <= y[j] (of the row, or of the candidate list)
     __shared__ K kmin[kCsTracks];                   // smallest key above y[j]
+    __shared__ K nmin[kCsTracks];                   // smallest key of the vector above the candidates' 12-bit bucket
+    __shared__ int llen[kCsTracks];                 // candidates appended (may exceed LCAP: overflow -> full passes)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *mine = cnt + (size_t)warp * (kCsTracks * 8 * 32) + lane;   // word w of this thread at mine[32 * w]
     const int64_t n0 = a.n0, n = a.n0 + a.n1;
     const int64_t nvec[3] = {a.n0, a.n1, n};
 
+    for (int w = 0; w < kCsTracks * 8; ++w) mine[32 * w] = 0u;
+
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
         const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
-        // ---- moments: mean, then squared deviations (two passes, like numpy's mean / var)
-        double s0 = 0.0, s1 = 0.0;
-        for (int64_t i = tid; i < n; i += kCsThreads) {
-            const double v = (double)__ldg(row + i);
-            if (i < n0) s0 += v; else s1 += v;
-        }
-        const double mean0 = cs_block_sum(s0, red, tid) / (double)a.n0;
-        const double mean1 = cs_block_sum(s1, red, tid) / (double)a.n1;
-        double d0 = 0.0, d1 = 0.0;
-        for (int64_t i = tid; i < n; i += kCsThreads) {
-            const double v = (double)__ldg(row + i);
-            if (i < n0) { const double d = v - mean0; d0 = fma(d, d, d0); }
-            else { const double d = v - mean1; d1 = fma(d, d, d1); }
-        }
-        const double ss0 = cs_block_sum(d0, red, tid);
-        const double ss1 = cs_block_sum(d1, red, tid);
-
-        // ---- radix select of y[j_lo] and y[j_hi] of the three vectors
         if (tid < kCsTracks) {
             prefix[tid] = 0;
             const phet_quantile_pos &q = a.q[tid >> 1];
             rank[tid] = (tid & 1) ? q.j_hi : q.j_lo;
+            llen[tid] = 0;
+            nmin[tid] = ~K(0);
         }
-        for (int w = 0; w < kCsTracks * 8; ++w) mine[32 * w] = 0u;
         __syncthreads();
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const int shift = CsKey<T>::bits - 4 * (pass + 1);
-            K pf[kCsTracks];
-#pragma unroll
-            for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
-            for (int64_t i = tid; i < n; i += kCsThreads) {
-                const K key = CsKey<T>::of(__ldg(row + i));
-                const uint32_t dig = (uint32_t)(key >> shift) & 15u;
-                const K hi = (pass == 0) ? K(0) : (key >> (shift + 4));   // digits already fixed
-                const int c = (i < n0) ? 0 : 1;
-#pragma unroll
-                for (int t = 0; t < kCsTracks; ++t) {
-                    const bool member = (t >> 1) == 2 || (t >> 1) == c;
-                    const K want = (pass == 0) ? K(0) : (pf[t] >> (shift + 4));
-                    if (member && hi == want) mine[32 * (t * 8 + (dig >> 1))] += (dig & 1u) ? 0x10000u : 1u;
-                }
-            }
-            // warp totals of the 96 counters (a thread sees at most n / 512 + 1 elements: no 16-bit overflow
-            // for n < 2^25), then the CTA totals, then one thread per track picks the digit
+
+        // CTA totals of the private counters, then one thread per track fixes the next digit
+        auto pick_digit = [&](int shift) {
+            // (a thread sees at most n / 512 + 1 elements: no 16-bit overflow for n < 2^25)
             for (int w = 0; w < kCsTracks * 8; ++w) {
                 const uint32_t x = mine[32 * w];
                 mine[32 * w] = 0u;
@@ -168,19 +149,177 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 prefix[tid] |= (K)d << shift;
             }
             __syncthreads();
-        }
-        // ---- y[j+1]: count of elements <= y[j] and the smallest key above it, per track
-        {
+        };
+        // one digit from a pass over the whole row; pass 0 also gathers the moments (deviations from the
+        // first cell of each class, fp64: exact zero variance for a constant vector, no cancellation trouble)
+        const double K0 = (double)__ldg(row), K1 = (double)__ldg(row + n0);
+        double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
+        auto full_pass = [&](int pass) {
+            const int shift = CsKey<T>::bits - 4 * (pass + 1);
             K pf[kCsTracks];
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
-            unsigned long long le[kCsTracks];
-            K mn[kCsTracks];
+#pragma unroll 4
+            for (int64_t i = tid; i < n; i += kCsThreads) {
+                const T v = __ldg(row + i);
+                const K key = CsKey<T>::of(v);
+                const uint32_t dig = (uint32_t)(key >> shift) & 15u;
+                const int c = (i < n0) ? 0 : 1;
+                if (pass == 0) {
+                    const double d = (double)v - (c ? K1 : K0);
+                    if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
+                    // nothing is fixed yet: the low and the high track of a vector see the same digits
+                    const uint32_t inc = (dig & 1u) ? 0x10000u : 1u;
+                    mine[32 * ((2 * c) * 8 + (dig >> 1))] += inc;
+                    mine[32 * (4 * 8 + (dig >> 1))] += inc;
+                } else {
+                    const K hi = key >> (shift + 4);   // digits already fixed
+#pragma unroll
+                    for (int t = 0; t < kCsTracks; ++t) {
+                        const bool member = (t >> 1) == 2 || (t >> 1) == c;
+                        if (member && hi == (pf[t] >> (shift + 4))) mine[32 * (t * 8 + (dig >> 1))] += (dig & 1u) ? 0x10000u : 1u;
+                    }
+                }
+            }
+            if (pass == 0) {   // copy the shared histograms to the high tracks
+                for (int w = 0; w < 8; ++w) {
+                    mine[32 * (1 * 8 + w)] = mine[32 * (0 * 8 + w)];
+                    mine[32 * (3 * 8 + w)] = mine[32 * (2 * 8 + w)];
+                    mine[32 * (5 * 8 + w)] = mine[32 * (4 * 8 + w)];
+                }
+            }
+            pick_digit(shift);
+        };
+
+        int next_pass = 0;
+        for (; next_pass < kCsFullPasses && next_pass < NPASS; ++next_pass) full_pass(next_pass);
+        const double sum0 = cs_block_sum(s0, red, tid), sum1 = cs_block_sum(s1, red, tid);
+        const double sq0 = cs_block_sum(d0, red, tid), sq1 = cs_block_sum(d1, red, tid);
+        const double mean0 = K0 + sum0 / (double)a.n0, mean1 = K1 + sum1 / (double)a.n1;
+        double ss0 = sq0 - sum0 * sum0 / (double)a.n0, ss1 = sq1 - sum1 * sum1 / (double)a.n1;
+        if (ss0 < 0.0) ss0 = 0.0;
+        if (ss1 < 0.0) ss1 = 0.0;
+
+        // ---- compaction: the elements that share a track's leading 12 bits go to the track's list
+        {
+            constexpr int shiftc = CsKey<T>::bits - 4 * kCsFullPasses;
+            K pf[kCsTracks], nm[kCsTracks];
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) {
-                le[t] = 0ull;
-                mn[t] = ~K(0);
+                pf[t] = prefix[t] >> shiftc;
+                nm[t] = ~K(0);
             }
+#pragma unroll 2
+            for (int64_t b = 0; b < n; b += kCsThreads) {   // warp-uniform trip count (ballots inside)
+                const int64_t i = b + tid;
+                const bool valid = i < n;
+                const K key = valid ? CsKey<T>::of(__ldg(row + i)) : K(0);
+                const K kp = key >> shiftc;
+                const int c = (i < n0) ? 0 : 1;
+#pragma unroll
+                for (int t = 0; t < kCsTracks; ++t) {
+                    const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
+                    const bool match = member && kp == pf[t];
+                    if (member && kp > pf[t] && key < nm[t]) nm[t] = key;
+                    const unsigned mask = __ballot_sync(kFull, match);
+                    if (mask) {
+                        int base = 0;
+                        if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(&llen[t], __popc(mask));
+                        base = __shfl_sync(kFull, base, __ffs((int)mask) - 1);
+                        const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                        if (match && pos < LCAP) lists[t * LCAP + pos] = key;
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) {
+                K mk = nm[t];
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const K other = __shfl_xor_sync(kFull, mk, o);
+                    mk = other < mk ? other : mk;
+                }
+                if (lane == 0) atomicMin(&nmin[t], mk);
+            }
+            __syncthreads();
+        }
+        bool overflow = false;
+#pragma unroll
+        for (int t = 0; t < kCsTracks; ++t) overflow = overflow || llen[t] > LCAP;   // CTA-uniform
+
+        if (tid < kCsTracks) {
+            cle[tid] = 0ull;
+            kmin[tid] = ~K(0);
+        }
+        unsigned long long le[kCsTracks];
+        K mn[kCsTracks];
+#pragma unroll
+        for (int t = 0; t < kCsTracks; ++t) {
+            le[t] = 0ull;
+            mn[t] = ~K(0);
+        }
+        int64_t r0 = 0;   // (threads < kCsTracks) rank of y[j] inside the candidate list
+        if (!overflow) {
+            if (tid < kCsTracks) r0 = rank[tid];
+            __syncthreads();   // r0 is read before the track warps move rank[] on
+            // ---- remaining digits and y[j+1] from the lists: ONE WARP PER TRACK, no CTA-wide step.  A lane counts
+            //      the digits of its share of the list in its private counters; 16 REDUX give the warp the digit.
+            if (warp < kCsTracks) {
+                const int t = warp;
+                const int len = llen[t];
+                const K *lt = lists + t * LCAP;
+                K pk = prefix[t];
+                int64_t r = rank[t];
+                for (int pass = next_pass; pass < NPASS; ++pass) {
+                    const int shift = CsKey<T>::bits - 4 * (pass + 1);
+                    const K want = pk >> (shift + 4);
+                    for (int e = lane; e < len; e += 32) {
+                        const K key = lt[e];
+                        const uint32_t dig = (uint32_t)(key >> shift) & 15u;
+                        if ((key >> (shift + 4)) == want) mine[32 * (dig >> 1)] += (dig & 1u) ? 0x10000u : 1u;
+                    }
+                    int64_t cum = 0;
+                    int d = 0;
+                    bool done = false;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const uint32_t x = mine[32 * w];
+                        mine[32 * w] = 0u;
+                        const int64_t c0 = __reduce_add_sync(kFull, x & 0xFFFFu), c1 = __reduce_add_sync(kFull, x >> 16);
+                        if (!done) {
+                            if (cum + c0 > r) { d = 2 * w; done = true; }
+                            else {
+                                cum += c0;
+                                if (cum + c1 > r || w == 7) { d = 2 * w + 1; done = true; }
+                                else cum += c1;
+                            }
+                        }
+                    }
+                    r -= cum;
+                    pk |= (K)d << shift;
+                }
+                unsigned long long l = 0ull;
+                K mk = ~K(0);
+                for (int e = lane; e < len; e += 32) {
+                    const K key = lt[e];
+                    if (key <= pk) ++l;
+                    else if (key < mk) mk = key;
+                }
+#pragma unroll
+                for (int tt = 0; tt < kCsTracks; ++tt) {   // (static indices: le[] / mn[] stay in registers)
+                    if (tt == t) {
+                        le[tt] = l;
+                        mn[tt] = mk;
+                    }
+                }
+                if (lane == 0) prefix[t] = pk;
+            }
+        } else {
+            // ---- a tie group (or a very dense bucket) larger than the list: keep passing over the whole row
+            for (int pass = next_pass; pass < NPASS; ++pass) full_pass(pass);
+            K pf[kCsTracks];
+#pragma unroll
+            for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
             for (int64_t i = tid; i < n; i += kCsThreads) {
                 const K key = CsKey<T>::of(__ldg(row + i));
                 const int c = (i < n0) ? 0 : 1;
@@ -193,41 +332,41 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                     }
                 }
             }
-            if (tid < kCsTracks) {
-                cle[tid] = 0ull;
-                kmin[tid] = ~K(0);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int t = 0; t < kCsTracks; ++t) {
-                unsigned long long l = le[t];
-                K mk = mn[t];
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) {
-                    l += __shfl_xor_sync(kFull, l, o);
-                    const K other = __shfl_xor_sync(kFull, mk, o);
-                    mk = other < mk ? other : mk;
-                }
-                if (lane == 0) {
-                    atomicAdd(&cle[t], l);       // integer sum / min: order-independent, deterministic
-                    atomicMin(&kmin[t], mk);
-                }
-            }
-            __syncthreads();
         }
+#pragma unroll
+        for (int t = 0; t < kCsTracks; ++t) {
+            unsigned long long l = le[t];
+            K mk = mn[t];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                l += __shfl_xor_sync(kFull, l, o);
+                const K other = __shfl_xor_sync(kFull, mk, o);
+                mk = other < mk ? other : mk;
+            }
+            if (lane == 0) {
+                atomicAdd(&cle[t], l);       // integer sum / min: order-independent, deterministic
+                atomicMin(&kmin[t], mk);
+            }
+        }
+        __syncthreads();
+        if (tid < kCsTracks) {
+            // y[j+1] = y[j] when the tie group of y[j] reaches rank j+1, else the next larger key
+            const phet_quantile_pos &q = a.q[tid >> 1];
+            const int64_t j = (tid & 1) ? q.j_hi : q.j_lo, k = (tid & 1) ? q.k_hi : q.k_lo;
+            const int64_t need = overflow ? j + 2 : r0 + 2;
+            K kk = prefix[tid];
+            if (k > j && (int64_t)cle[tid] < need) {
+                kk = kmin[tid];
+                if (!overflow && nmin[tid] < kk) kk = nmin[tid];
+            }
+            kmin[tid] = kk;   // key of y[k]
+        }
+        __syncthreads();
         if (tid < 3) {
             const phet_quantile_pos &q = a.q[tid];
-            T y[2][2];
-            for (int h = 0; h < 2; ++h) {
-                const int t = tid * 2 + h;
-                const int64_t j = h ? q.j_hi : q.j_lo, k = h ? q.k_hi : q.k_lo;
-                const T yj = CsKey<T>::back(prefix[t]);
-                T yk = yj;
-                if (k > j && (int64_t)cle[t] < j + 2) yk = CsKey<T>::back(kmin[t]);
-                y[h][0] = yj;
-                y[h][1] = yk;
-            }
-            a.out[(size_t)tid * a.G + g] = (nvec[tid] > 0) ? cs_iqr(y[0][0], y[0][1], y[1][0], y[1][1], q.g_lo, q.g_hi) : 0.0;
+            const T yjl = CsKey<T>::back(prefix[2 * tid]), ykl = CsKey<T>::back(kmin[2 * tid]);
+            const T yjh = CsKey<T>::back(prefix[2 * tid + 1]), ykh = CsKey<T>::back(kmin[2 * tid + 1]);
+            a.out[(size_t)tid * a.G + g] = (nvec[tid] > 0) ? cs_iqr(yjl, ykl, yjh, ykh, q.g_lo, q.g_hi) : 0.0;
         }
         if (tid == 0) {
             a.out[(size_t)3 * a.G + g] = mean0;
@@ -255,7 +394,7 @@ int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_q
     if (ng < 1) return PHET_OK;
     int64_t grid = c->num_sms;
     if (grid > ng) grid = ng;
-    const int smem = kCsTracks * 8 * kCsThreads * (int)sizeof(uint32_t);
+    const int smem = kCsTracks * 8 * kCsThreads * (int)sizeof(uint32_t) + kCsTracks * 4096 * (int)sizeof(uint32_t);  // counters + lists
     if (c->storage == PHET_F32) {
         PHET_CUDA(cudaFuncSetAttribute(k_class_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         k_class_stats<float><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
