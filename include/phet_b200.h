@@ -58,6 +58,8 @@ typedef enum {
     PHET_BUF_STD = 11,     /* double[G] column population sd */
     PHET_BUF_ROWS = 12,    /* int32[N]: original row held at each position of a gene-major row (the layout) */
     PHET_BUF_ACC_O = 14,   /* double[3][G]: PHET_BUF_ACC followed by PHET_BUF_O, contiguous (one all-reduce for both)    */
+    PHET_BUF_STAGED = 15,  /* float32 [cells kept][genes kept], row-major: the matrix phet_mtx_stage left in HBM */
+    PHET_BUF_RANK_ORDER = 16, /* int32[G]: gene index at each rank, descending score (phet_rank)                        */
     PHET_BUF_PROFILE = 13  /* uint64[16]: per-phase cycle counters of the Step-3 kernel, only with env PHET_PROFILE=1 */
 } phet_buffer;
 
@@ -203,6 +205,36 @@ int phet_step3_path(phet_ctx *ctx);
  * iqr(class 0), iqr(class 1), iqr(all cells), mean(class 0), mean(class 1),
  * sum of squared deviations (class 0), (class 1).  Order statistics are exact (radix select). */
 int phet_class_stats(phet_ctx *ctx, const phet_quantile_pos *q3, double *out);
+
+/* Input path.  phet_mtx_parse replaces src/train.py:82-83 (sc.read_mtx: scipy.io.mmread,
+ * float32): a multi-threaded host parse of a MatrixMarket `coordinate` file (real | integer | pattern, general |
+ * symmetric) into zero-based triplets; values are rounded text -> double -> float like mmread(...).astype("float32").
+ * threads <= 0: one per hardware thread.  dims_out: rows (cells), columns (genes), entries read.  No GPU needed. */
+typedef struct phet_mtx phet_mtx;
+int phet_mtx_parse(const char *path, int threads, phet_mtx **out, int64_t dims_out[3]);
+/* Borrowed views of the parsed triplets (valid until phet_mtx_free); any out pointer may be NULL. */
+int phet_mtx_triplets(const phet_mtx *m, const int32_t **rows, const int32_t **cols, const float **vals,
+                      int64_t *count, int *symmetric);
+int phet_mtx_free(phet_mtx *m);
+/* Uploads the triplets (12 bytes per entry instead of the dense matrix), scatters them into a dense float32
+ * cells x genes matrix in HBM (duplicates add up, as coo -> csr does), zeroes NaN / +-inf cells (np.nan_to_num,
+ * train.py:85) and, with do_filter != 0, applies train.py:88-118 on the device: cells with sum|x| >= 5 are kept
+ * (row sums in NumPy's pairwise fp32 order, so the decision is the reference's), then genes whose counts per
+ * million exceed 1 in at least `minimum_samples` kept cells (train.py's local default is 5; lowered to
+ * cells/2 under the reference's rule, train.py:108-109).  dims_out: cells kept, genes kept.  The result is
+ * PHET_BUF_STAGED, to be handed to phet_load_matrix / phet_run_pipeline with is_device = 1. */
+int phet_mtx_stage(phet_ctx *ctx, const phet_mtx *m, int do_filter, int64_t minimum_samples, int64_t dims_out[2]);
+/* Ascending row / column numbers the filter kept (examples_ids, feature_ids of train.py:92,111): the caller
+ * filters y and the feature names with them.  rows_out: int32[cells kept], cols_out: int32[genes kept]. */
+int phet_mtx_kept(phet_ctx *ctx, int32_t *rows_out, int32_t *cols_out);
+
+/* Ranking: replaces the ordering of src/utility/utils.py:107-136 (sort_features:
+ * df.sort_values(by=["score"], ascending=False)).  scores: host double[G], or NULL to rank the resident
+ * PHET_BUF_SCORES (G may then be 0).  The first k entries are returned: order_out[r] = gene index at rank r,
+ * sorted_out[r] = its score (either may be NULL); the whole order stays in PHET_BUF_RANK_ORDER.  Descending;
+ * equal scores keep ascending gene order (pandas kind="stable"; the reference's default quicksort leaves the
+ * order inside a tie group unspecified); NaN last. */
+int phet_rank(phet_ctx *ctx, const double *scores, int64_t G, int64_t k, int32_t *order_out, double *sorted_out);
 
 /* One-call convenience: everything above on one device with host buffers (used by C callers
  * and by the end-to-end benchmark leg).  perm_mode/seed as in phet_step3; with PHET_PERM_HOST

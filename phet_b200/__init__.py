@@ -8,5 +8,6 @@ Host side in Python (like the reference), device side in hand-written CUDA behin
 """
 from .phet import PHet  # noqa: F401
 from .siblings import HIQR, DeltaIQRMean  # noqa: F401
+from .ingest import StagedMatrix, load_mtx  # noqa: F401
 
-__all__ = ["PHet", "HIQR", "DeltaIQRMean"]
+__all__ = ["PHet", "HIQR", "DeltaIQRMean", "StagedMatrix", "load_mtx"]

@@ -19,13 +19,14 @@ TEST_T, TEST_Z = 0, 1
 PERM_HOST, PERM_DEVICE = 0, 1
 OPT_KEEP_H = 1
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
- BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O) = range(15)
+ BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O, BUF_STAGED, BUF_RANK_ORDER) = range(17)
 
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
+    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -108,6 +109,12 @@ def load_library(build_if_missing: bool = True):
     lib.phet_fit_host.argtypes = [vp, vp, C.c_int, i64, i64, vp, i64, vp, i64, vp, i64, vp, vp,
                                   C.POINTER(FitParams), vp, vp]
     lib.phet_class_stats.argtypes = [vp, C.POINTER(QuantilePos), vp]
+    lib.phet_mtx_parse.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    lib.phet_mtx_triplets.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.phet_mtx_free.argtypes = [vp]
+    lib.phet_mtx_stage.argtypes = [vp, vp, C.c_int, i64, C.POINTER(i64)]
+    lib.phet_mtx_kept.argtypes = [vp, vp, vp]
+    lib.phet_rank.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
     lib.phet_host_p_two_sided_t.restype = dbl
     lib.phet_host_p_two_sided_z.argtypes = [dbl]
@@ -129,6 +136,44 @@ def _check(rc):
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class MtxFile:
+    """A MatrixMarket coordinate file parsed by the library's multi-threaded host reader (phet_mtx_parse;
+    replaces sc.read_mtx at src/train.py:82).  ``shape`` = (cells, genes); no GPU involved."""
+
+    def __init__(self, path: str, threads: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        dims = (C.c_int64 * 3)()
+        _check(self.lib.phet_mtx_parse(os.fsencode(path), int(threads), C.byref(h), dims))
+        self.h = h
+        self.shape = (int(dims[0]), int(dims[1]))
+        self.entries = int(dims[2])
+
+    def triplets(self):
+        """(rows, cols, vals, symmetric): copies of the zero-based triplets in file order."""
+        r, c, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, sym = C.c_int64(), C.c_int()
+        _check(self.lib.phet_mtx_triplets(self.h, C.byref(r), C.byref(c), C.byref(v), C.byref(n), C.byref(sym)))
+        k = n.value
+        if k == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), bool(sym.value)
+        rows = np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_int32)), (k,)).copy()
+        cols = np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_int32)), (k,)).copy()
+        vals = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_float)), (k,)).copy()
+        return rows, cols, vals, bool(sym.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phet_mtx_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -187,6 +232,31 @@ class Context:
         out = np.empty((7, self.G), dtype=np.float64)
         _check(self.lib.phet_class_stats(self.h, arr, _ptr(out)))
         return out
+
+    def stage_mtx(self, mtx: "MtxFile", do_filter: bool = True, minimum_samples: int = 5):
+        """Dense float32 matrix of ``mtx`` in HBM, filtered like src/train.py:88-118 when ``do_filter``.
+        Returns (cells kept, genes kept, kept row numbers, kept column numbers); the matrix is BUF_STAGED."""
+        dims = (C.c_int64 * 2)()
+        _check(self.lib.phet_mtx_stage(self.h, mtx.h, 1 if do_filter else 0, int(minimum_samples), dims))
+        n, g = int(dims[0]), int(dims[1])
+        rows = np.empty(n, dtype=np.int32)
+        cols = np.empty(g, dtype=np.int32)
+        _check(self.lib.phet_mtx_kept(self.h, _ptr(rows), _ptr(cols)))
+        return n, g, rows, cols
+
+    def rank(self, scores=None, k=None):
+        """Descending order of the scores (host vector, or the resident BUF_SCORES when None):
+        (gene index per rank int32[k], score per rank float64[k]) -- include/phet_b200.h: phet_rank."""
+        if scores is None:
+            G, sp, keep = self.G, None, None
+        else:
+            keep = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
+            G, sp = keep.size, _ptr(keep)
+        k = G if k is None else int(k)
+        order = np.empty(k, dtype=np.int32)
+        srt = np.empty(k, dtype=np.float64)
+        _check(self.lib.phet_rank(self.h, sp, G, k, _ptr(order), _ptr(srt)))
+        return order, srt
 
     def set_index_sets(self, idx: np.ndarray):
         """idx: int32 (S, 2, m), original row numbers; [:, 0] control draw, [:, 1] case draw."""

@@ -349,6 +349,20 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->weights.release();
     c->counts.release();
     c->class_stats.release();
+    c->mtx_out.release();
+    c->mtx_dense.release();
+    c->mtx_v.release();
+    c->mtx_rowsum.release();
+    c->mtx_r.release();
+    c->mtx_c.release();
+    c->mtx_prog.release();
+    c->mtx_rows.release();
+    c->mtx_cols.release();
+    c->mtx_cnt.release();
+    c->rank_keys.release();
+    c->rank_order.release();
+    c->rank_sorted.release();
+    c->rank_in.release();
     c->stage[0].release();
     c->stage[1].release();
     for (int i = 0; i < 2; ++i) {
@@ -777,6 +791,96 @@ int phet_class_stats(phet_ctx *c, const phet_quantile_pos *q3, double *out) {
     return PHET_OK;
 }
 
+// ---- input path: MatrixMarket -> device (mtx.cu)
+int phet_mtx_parse(const char *path, int threads, phet_mtx **out, int64_t dims_out[3]) {
+    PHET_REQUIRE(path != nullptr && out != nullptr, "NULL argument");
+    *out = nullptr;
+    phet_mtx *m = new (std::nothrow) phet_mtx();
+    if (!m) {
+        set_error("out of host memory");
+        return PHET_ERR_NOMEM;
+    }
+    int rc = PHET_OK;
+    try {
+        rc = mtx_parse(path, threads, *m);
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory while reading the MatrixMarket file");
+        rc = PHET_ERR_NOMEM;
+    }
+    if (rc != PHET_OK) {
+        delete m;
+        return rc;
+    }
+    if (dims_out) {
+        dims_out[0] = m->rows;
+        dims_out[1] = m->cols;
+        dims_out[2] = (int64_t)m->v.size();
+    }
+    *out = m;
+    return PHET_OK;
+}
+
+int phet_mtx_triplets(const phet_mtx *m, const int32_t **rows, const int32_t **cols, const float **vals, int64_t *count,
+                      int *symmetric) {
+    PHET_REQUIRE(m != nullptr, "NULL argument");
+    if (rows) *rows = m->r.data();
+    if (cols) *cols = m->c.data();
+    if (vals) *vals = m->v.data();
+    if (count) *count = (int64_t)m->v.size();
+    if (symmetric) *symmetric = m->symmetric ? 1 : 0;
+    return PHET_OK;
+}
+
+int phet_mtx_free(phet_mtx *m) {
+    delete m;
+    return PHET_OK;
+}
+
+int phet_mtx_stage(phet_ctx *c, const phet_mtx *m, int do_filter, int64_t minimum_samples, int64_t dims_out[2]) {
+    PHET_REQUIRE(c != nullptr && m != nullptr && dims_out != nullptr, "NULL argument");
+    PHET_REQUIRE(minimum_samples >= 0, "minimum_samples must be >= 0");
+    try {
+        return mtx_stage(c, *m, do_filter, minimum_samples, dims_out);
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory while staging the matrix");
+        return PHET_ERR_NOMEM;
+    }
+}
+
+int phet_mtx_kept(phet_ctx *c, int32_t *rows_out, int32_t *cols_out) {
+    PHET_REQUIRE(c != nullptr, "NULL argument");
+    PHET_REQUIRE((int64_t)c->mtx_rows_host.size() == c->mtx_N && (int64_t)c->mtx_cols_host.size() == c->mtx_G,
+                 "no staged matrix (call phet_mtx_stage first)");
+    if (rows_out && c->mtx_N) memcpy(rows_out, c->mtx_rows_host.data(), sizeof(int32_t) * (size_t)c->mtx_N);
+    if (cols_out && c->mtx_G) memcpy(cols_out, c->mtx_cols_host.data(), sizeof(int32_t) * (size_t)c->mtx_G);
+    return PHET_OK;
+}
+
+// ---- ranking (rank.cu)
+int phet_rank(phet_ctx *c, const double *scores, int64_t G, int64_t k, int32_t *order_out, double *sorted_out) {
+    PHET_REQUIRE(c != nullptr, "NULL argument");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const double *src = nullptr;
+    if (scores == nullptr) {
+        PHET_REQUIRE(c->scores.p != nullptr && c->G >= 1, "no scores on the device yet (phet_combine / phet_finalize first)");
+        PHET_REQUIRE(G == 0 || G == c->G, "G does not match the resident scores");
+        G = c->G;
+        src = c->scores.p;
+    } else {
+        PHET_REQUIRE(G >= 1, "G must be >= 1");
+        if (int e = c->rank_in.alloc((size_t)G)) return e;
+        PHET_CUDA(cudaMemcpyAsync(c->rank_in.p, scores, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, c->stream));
+        src = c->rank_in.p;
+    }
+    PHET_REQUIRE(G <= INT32_MAX, "too many genes");
+    PHET_REQUIRE(k >= 0 && k <= G, "need 0 <= k <= G");
+    if (int e = launch_rank(c, src, G)) return e;
+    if (order_out && k) PHET_CUDA(cudaMemcpyAsync(order_out, c->rank_order.p, sizeof(int32_t) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+    if (sorted_out && k) PHET_CUDA(cudaMemcpyAsync(sorted_out, c->rank_sorted.p, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
 static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
     switch (which) {
         case PHET_BUF_ACC: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 2 * c->G; break;
@@ -793,6 +897,8 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;
         case PHET_BUF_ACC_O: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 3 * c->G; break;
+        case PHET_BUF_STAGED: *p = c->mtx_out.p; *bytes = (int64_t)sizeof(float) * c->mtx_N * c->mtx_G; break;
+        case PHET_BUF_RANK_ORDER: *p = c->rank_order.p; *bytes = (int64_t)sizeof(int32_t) * (int64_t)c->rank_order.n; break;
         case PHET_BUF_PROFILE: *p = c->prof.p; *bytes = 16 * (int64_t)sizeof(unsigned long long); break;
         default:
             set_error("invalid: unknown buffer id");

@@ -66,6 +66,14 @@ struct DevBuf {
 
 }  // namespace phet
 
+// A parsed MatrixMarket file (mtx.cu): zero-based triplets in file order.
+struct phet_mtx {
+    int64_t rows = 0, cols = 0, declared = 0;
+    bool symmetric = false, pattern = false;
+    std::vector<int32_t> r, c;
+    std::vector<float> v;
+};
+
 // The context.  Plain struct: the C ABI only ever hands out pointers to it.
 struct phet_ctx {
     int device = 0;
@@ -131,6 +139,16 @@ struct phet_ctx {
     phet::DevBuf<unsigned long long> counts;
     phet::DevBuf<double> class_stats;    // [7][G] (phet_class_stats)
 
+    // MatrixMarket ingestion (mtx.cu): triplets, the dense matrix as read, what the filter keeps
+    phet::DevBuf<float> mtx_dense, mtx_out, mtx_v, mtx_rowsum;
+    phet::DevBuf<int32_t> mtx_r, mtx_c, mtx_prog, mtx_rows, mtx_cols, mtx_cnt;
+    std::vector<int32_t> mtx_rows_host, mtx_cols_host;   // kept cells / genes, ascending (train.py:92,111)
+    int64_t mtx_N = 0, mtx_G = 0;                        // shape of mtx_out
+    // ranking (rank.cu)
+    phet::DevBuf<unsigned long long> rank_keys;
+    phet::DevBuf<int32_t> rank_order;
+    phet::DevBuf<double> rank_sorted, rank_in;
+
     int32_t step1_geom[5] = {0, 0, 0, 0, 0};
 };
 
@@ -149,5 +167,8 @@ int launch_o_minmax(phet_ctx *c, double out[2]);
 int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
 int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
+int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
+int mtx_parse(const char *path, int threads, phet_mtx &m);
+int mtx_stage(phet_ctx *c, const phet_mtx &m, int do_filter, int64_t minimum_samples, int64_t dims_out[2]);
 
 }  // namespace phet

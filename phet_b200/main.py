@@ -38,6 +38,17 @@ def load_dataset(dspath: str, file_name: str):
     return X, y, names
 
 
+def load_dataset_device(dspath: str, file_name: str, do_filter: bool = True, device=None, minimum_samples: int = 5):
+    """train.py:47-118 with the matrix never materialised on the host: C++ reader -> triplets -> B200
+    (phet_b200.ingest.load_mtx); y and the feature names are filtered with the kept row / column numbers."""
+    from .ingest import load_mtx
+    X = load_mtx(os.path.join(dspath, file_name + "_matrix.mtx"), do_filter=do_filter, minimum_samples=minimum_samples,
+                 device=device)
+    y = pd.read_csv(os.path.join(dspath, file_name + "_classes.csv"), sep=",").iloc[:, 0].to_numpy().astype(np.int64)
+    names = pd.read_csv(os.path.join(dspath, file_name + "_feature_names.csv"), sep=",").iloc[:, 0].to_list()
+    return X, y[X.kept_rows], np.array(names)[X.kept_cols].tolist()
+
+
 def filter_data(X, y, features_name, minimum_samples: int = 5):
     """train.py:88-118: cells with sum |x| >= 5; genes with CPM > 1 in >= minimum_samples cells."""
     example_sums = np.absolute(X).sum(1)
@@ -76,6 +87,11 @@ def build_parser():
     p.add_argument("--top-k-features", type=int, default=100)
     p.add_argument("--device", type=int, default=None)
     p.add_argument("--permutation", type=str, default="reference", choices=["reference", "device"])
+    p.add_argument("--loader", type=str, default="native", choices=["native", "scipy"],
+                   help="native: multi-threaded C++ MatrixMarket reader + filter on the B200 (the matrix never "
+                        "exists on the host); scipy: mmread + NumPy filter on the host (train.py:82-118 as written)")
+    p.add_argument("--ranking", type=str, default="device", choices=["device", "pandas"],
+                   help="device: order of the scores from phet_rank; pandas: DataFrame.sort_values (utils.py:107-136)")
     return p
 
 
@@ -83,9 +99,14 @@ def run(args) -> pd.DataFrame:
     from . import PHet
     from .select import significant_features, sort_features
     np.random.seed(seed=SEED)
-    X, y, names = load_dataset(args.dspath, args.file_name)
-    if not args.no_filtering:
-        X, y, names = filter_data(X, y, names)
+    t0 = time.perf_counter()
+    if args.loader == "native":
+        X, y, names = load_dataset_device(args.dspath, args.file_name, not args.no_filtering, args.device)
+    else:
+        X, y, names = load_dataset(args.dspath, args.file_name)
+        if not args.no_filtering:
+            X, y, names = filter_data(X, y, names)
+    print("## loader %s: %.3f s" % (args.loader, time.perf_counter() - t0))
     print("## %s: %d examples x %d features; classes %s" % (args.file_name, X.shape[0], X.shape[1],
                                                             np.bincount(y).tolist()))
     t0 = time.perf_counter()
@@ -95,11 +116,12 @@ def run(args) -> pd.DataFrame:
     scores = estimator.fit_predict(X=X, y=y)
     print("## PHet fit_predict: %.3f s (host draws %.3f s), %d kernel launches" % (
         time.perf_counter() - t0, estimator.timings_.get("host_draws_s", 0.0), estimator.launches_))
+    order = estimator.ranking_ if args.ranking == "device" else None
     if not args.no_sort_by_pvalue:
         df = significant_features(X=scores, features_name=names, alpha=args.alpha, fit_type=args.fit_type,
-                                  per=args.per)
+                                  per=args.per, order=order)
     else:
-        df = sort_features(X=scores, features_name=names)
+        df = sort_features(X=scores, features_name=names, order=order)
     os.makedirs(args.rspath, exist_ok=True)
     out = os.path.join(args.rspath, args.file_name + "_phet_br_features.csv")
     df.to_csv(out, sep=",", index=False)

@@ -139,7 +139,10 @@ class PHet:
         """Feature scores, shape (num_features, 1), float64 -- see phet.py:163-209."""
         import time
         t_all = time.perf_counter()
-        X = np.asarray(X)
+        from .ingest import StagedMatrix
+        staged = X if isinstance(X, StagedMatrix) else None   # already in HBM (phet_b200.ingest.load_mtx)
+        if staged is None:
+            X = np.asarray(X)
         num_examples, num_features = X.shape
         y = np.asarray(y)
         unique_classes = np.unique(y)
@@ -198,18 +201,21 @@ class PHet:
         # ---- device
         dev = self._resolve_device()
         stream = None
+        if staged is not None and dist is not None:
+            raise NotImplementedError("a StagedMatrix is fitted by the process that staged it (single device)")
         if dist is not None:
             import torch
             torch.cuda.set_device(dev)
             self._torch_stream = torch.cuda.Stream(dev)   # non-default: handle 0 would mean "own stream"
             torch.cuda.set_stream(self._torch_stream)
             stream = self._torch_stream.cuda_stream
-        ctx = _capi.Context(dev, stream)
+        ctx = staged.ctx if staged is not None else _capi.Context(dev, stream)
         try:
             scores = self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices,
                                       n_last, rank, world, dist)
         finally:
-            ctx.close()
+            if staged is None:
+                ctx.close()
         self.timings_["fit_s"] = time.perf_counter() - t_all
         return scores
 
@@ -230,9 +236,12 @@ class PHet:
     def _run_device(self, ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
                     rank, world, dist):
         N, G = X.shape
-        if X.dtype not in (np.float32, np.float64):
-            X = X.astype(np.float64)
-        X = np.ascontiguousarray(X)
+        from .ingest import StagedMatrix
+        staged = isinstance(X, StagedMatrix)
+        if not staged:
+            if X.dtype not in (np.float32, np.float64):
+                X = X.astype(np.float64)
+            X = np.ascontiguousarray(X)
         dtype = _capi.PHET_F32 if X.dtype == np.float32 else _capi.PHET_F64
         storage = {"auto": None, "f32": _capi.PHET_F32, "f64": _capi.PHET_F64}[self.storage]
         from .distributed import shard_range
@@ -246,8 +255,8 @@ class PHet:
         ctx.set_index_sets(idx)
         prm = self._step1_params(X.dtype, m)
         # Stage 0 + Step 1 + Step 3, gene-block pipelined with the H2D copy (phet.py:291-299, 397-432, 473-498)
-        ctx.run_pipeline(X, N, G, dtype, prm, m, hostmath.ks_exact_table(m), hostmath.ks_exact_table(n_last), n_last,
-                         g_range=g_range, s_range=s_range, g3_range=g3_range,
+        ctx.run_pipeline(X.device_ptr if staged else X, N, G, dtype, prm, m, hostmath.ks_exact_table(m),
+                         hostmath.ks_exact_table(n_last), n_last, is_device=staged, g_range=g_range, s_range=s_range, g3_range=g3_range,
                          normalize=_capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE,
                          storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed)
         if dist is not None:
@@ -257,6 +266,8 @@ class PHet:
         # Fisher standardisation, KBinsDiscretizer('uniform') on o, weights and combine (phet.py:435-462, 500-516)
         scores, counts, edges = ctx.finalize(S, self.feature_weight)
         self.bin_counts_ = counts
+        # descending order of the scores, ties in ascending gene order (utils.py:107-136 on the device: phet_rank)
+        self.ranking_, _ = ctx.rank()
         self.m_ = m
         self.index_sets_ = idx
         self.launches_ = ctx.launch_count()
