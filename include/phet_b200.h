@@ -178,7 +178,11 @@ int phet_finalize(phet_ctx *ctx, int64_t S_total, const double *weights, int32_t
  * with the integer KS statistic of EVERY slice (parity / debugging; the sorting kernels run); 0 = only
  * o[g] = min p is produced, which lets Step 3 bound h per slice from bucket histograms and evaluate
  * exactly only the slices that can attain the gene's minimum p (phet.py:496 takes the min). */
-typedef enum { PHET_OPT_KEEP_H = 1 } phet_option;
+/* PHET_OPT_STEP3_MIN_SIZE (default 0 = min(n0, n1)): the Step-3 slices cover positions [0, value) of each permuted
+ * class column.  A multi-class fit slices every (class i, other cells) pair over the smallest of ALL classes
+ * (phet.py:466-471, min_size), which is smaller than min(n0, n1) of the pair; host permutations are then
+ * uint32 [G][value]. */
+typedef enum { PHET_OPT_KEEP_H = 1, PHET_OPT_STEP3_MIN_SIZE = 2 } phet_option;
 int phet_set_option(phet_ctx *ctx, int option, int64_t value);
 
 /* Raw device pointer / element count of a context buffer (for wrapping, no ownership change). */
@@ -205,6 +209,15 @@ int phet_step3_path(phet_ctx *ctx);
  * iqr(class 0), iqr(class 1), iqr(all cells), mean(class 0), mean(class 1),
  * sum of squared deviations (class 0), (class 1).  Order statistics are exact (radix select). */
 int phet_class_stats(phet_ctx *ctx, const phet_quantile_pos *q3, double *out);
+
+/* Multi-class Step 1: replaces phet.py:348-382 with group_test="anova" -- for each of S
+ * subsamples, scipy.stats.f_oneway over K groups of m cells per gene, nan_to_num(p), and Fisher's sum
+ * sum_s -2 ln p (p == 0 dropped, phet.py:449-451), written to PHET_BUF_ACC[0 .. G) (and p to PHET_BUF_P when
+ * capture_debug != 0).  idx: host int32[S][K][m], ORIGINAL row numbers (any grouping of the cells into the two
+ * phet_set_classes lists works: only the layout depends on it).  ln_beta = ln B((K m - K)/2, (K - 1)/2) (host
+ * lgamma).  p_flush_below: p-values <= this become 0 (float32 fdtrc underflow for float32 input; 0 = off). */
+int phet_anova(phet_ctx *ctx, const int32_t *idx, int64_t S, int64_t K, int64_t m, double ln_beta,
+               double p_flush_below, int capture_debug);
 
 /* Input path.  phet_mtx_parse replaces src/train.py:82-83 (sc.read_mtx: scipy.io.mmread,
  * float32): a multi-threaded host parse of a MatrixMarket `coordinate` file (real | integer | pattern, general |

@@ -18,6 +18,7 @@ NORM_NONE, NORM_ZSCORE = 0, 1
 TEST_T, TEST_Z = 0, 1
 PERM_HOST, PERM_DEVICE = 0, 1
 OPT_KEEP_H = 1
+OPT_STEP3_MIN_SIZE = 2
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
  BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O, BUF_STAGED, BUF_RANK_ORDER) = range(17)
 
@@ -26,7 +27,7 @@ EXPORTS = [
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
-    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank",
+    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -115,6 +116,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mtx_stage.argtypes = [vp, vp, C.c_int, i64, C.POINTER(i64)]
     lib.phet_mtx_kept.argtypes = [vp, vp, vp]
     lib.phet_rank.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.phet_anova.argtypes = [vp, vp, i64, i64, i64, dbl, dbl, C.c_int]
     lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
     lib.phet_host_p_two_sided_t.restype = dbl
     lib.phet_host_p_two_sided_z.argtypes = [dbl]
@@ -257,6 +259,12 @@ class Context:
         srt = np.empty(k, dtype=np.float64)
         _check(self.lib.phet_rank(self.h, sp, G, k, _ptr(order), _ptr(srt)))
         return order, srt
+
+    def anova(self, idx: np.ndarray, ln_beta: float, p_flush_below: float = 0.0, capture: bool = False):
+        """idx: int32 (S, K, m) original rows.  Fisher's sum of the one-way ANOVA p-values -> BUF_ACC[0:G]."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        S, K, m = idx.shape
+        _check(self.lib.phet_anova(self.h, _ptr(idx), S, K, m, float(ln_beta), float(p_flush_below), 1 if capture else 0))
 
     def set_index_sets(self, idx: np.ndarray):
         """idx: int32 (S, 2, m), original row numbers; [:, 0] control draw, [:, 1] case draw."""

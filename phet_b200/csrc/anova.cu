@@ -1,0 +1,209 @@
+// Multi-class Step 1: one-way ANOVA p-value per (gene, subsample) over K groups of m
+// cells, accumulated into Fisher's sum.  Replaces /root/reference/src/model/phet.py:348-382 with
+// group_test="anova": scipy.stats.f_oneway(*subsamples) (_stats_py.py f_oneway, equal_var=True: sums of squares
+// about the pooled mean, F = (SSB/(K-1)) / (SSW/(K m - K)), p = special.fdtrc(K-1, K m - K, F)), then
+// nan_to_num(p) (phet.py:378) and the Fisher term -2 ln p with p == 0 dropped (phet.py:449-451).
+//
+// Same shape as the two-class Step 1: a CTA owns a gene, stages its whole cell vector in shared memory once
+// (coalesced loads) and serves every subsample from there -- one thread per subsample walks the K*m positions of
+// that subsample (transposed index table: consecutive threads read consecutive words) and gathers from SMEM.
+// No order statistics here, only moments: per group the sum of deviations from the vector's first cell, and the
+// pooled sum of squared deviations; fp32 running sums for float storage (m <= 512 terms each, combined in fp64),
+// fp64 throughout for double storage.  The per-gene Fisher sum is reduced in a fixed order (deterministic).
+#include "common.cuh"
+#include "pvalue.cuh"
+
+namespace phet {
+
+constexpr int kAnovaThreads = 512;
+
+struct AnovaArgs {
+    const void *xg;
+    int64_t n_pad, xg_g0, g_begin, g_end, N;
+    const uint32_t *idxT;   // [K * m][S]: grouped position of element e of group k in subsample s
+    int64_t S;
+    int K, m;
+    double dfn, dfd, ln_beta, p_flush;
+    double *acc_f;          // [G]
+    double *dbgP;           // [G][S] or NULL
+};
+
+// original rows [S][K][m] -> grouped positions, transposed to [K*m][S]
+__global__ void k_anova_index(const int32_t *__restrict__ idx, int64_t S, int64_t KM, const int32_t *__restrict__ pos_of_row,
+                              int64_t N, uint32_t *__restrict__ idxT, int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [K*m][S]
+    if (i >= S * KM) return;
+    const int64_t e = i / S, s = i - e * S;
+    const int32_t r = idx[s * KM + e];
+    if (r < 0 || r >= N) {
+        *bad = 1;
+        idxT[i] = 0u;
+    } else {
+        idxT[i] = (uint32_t)pos_of_row[r];
+    }
+}
+
+// Upper tail of the F distribution, cephes fdtrc(a, b, x) = incbet(b/2, a/2, b / (b + a x)); NaN for x < 0
+// (cephes' domain error), which the caller turns into "no contribution" like the reference's nan_to_num.
+__device__ __forceinline__ double p_f_upper(double f, double dfn, double dfd, double ln_beta) {
+    if (!(f == f) || f < 0.0) return __builtin_nan("");
+    if (isinf(f)) return 0.0;
+    const double den = dfd + dfn * f;
+    const double x = dfd / den, y = dfn * f / den;
+    if (y <= 0.0) return 1.0;
+    if (x <= 0.0) return 0.0;
+    const double a = 0.5 * dfd, b = 0.5 * dfn;
+    const double lnx = (y < 0.5) ? log1p(-y) : log(x);
+    const double lny = (x < 0.5) ? log1p(-x) : log(y);
+    const double front = exp(a * lnx + b * lny - ln_beta);
+    if (x < (a + 1.0) / (a + b + 2.0)) return front * betacf(a, b, x) / a;
+    return 1.0 - front * betacf(b, a, y) / b;
+}
+
+template <typename T> struct AnovaAcc { typedef double type; };
+template <> struct AnovaAcc<float> { typedef float type; };
+
+template <typename T, bool STAGED>
+__global__ void __launch_bounds__(kAnovaThreads, 1) k_anova(const AnovaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *vec = reinterpret_cast<T *>(smem_raw);
+    __shared__ double red[kAnovaThreads / 32];
+    typedef typename AnovaAcc<T>::type A;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K, m = a.m;
+    const double bign = (double)K * (double)m;
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
+        const T *src = row;
+        if (STAGED) {
+            __syncthreads();   // the previous gene's gathers are done
+            for (int64_t i = tid; i < a.N; i += kAnovaThreads) vec[i] = row[i];
+            __syncthreads();
+            src = vec;
+        }
+        const T c0 = src[0];
+        double fisher = 0.0;
+        for (int64_t s = tid; s < a.S; s += kAnovaThreads) {
+            const uint32_t *ix = a.idxT + s;
+            double ssb_raw = 0.0, tot = 0.0, q = 0.0;   // sum_k s_k^2 / m, sum of all deviations, sum of squares
+            bool all_const = true;                        // every group constant (f_oneway: F = inf -> p = 0)
+            T first_all = T(0);
+            bool all_same = true;                         // every value identical (F = nan -> p = nan -> 0)
+            for (int k = 0; k < K; ++k) {
+                A sk = A(0), qk = A(0);
+                T first = T(0);
+                bool cst = true;
+#pragma unroll 4
+                for (int e = 0; e < m; ++e) {
+                    const uint32_t pos = __ldg(ix + (int64_t)(k * m + e) * a.S);
+                    const T v = src[pos];
+                    if (e == 0) first = v;
+                    cst = cst && (v == first);
+                    const A d = (A)(v - c0);
+                    sk += d;
+                    qk = fma(d, d, qk);
+                }
+                if (k == 0) first_all = first;
+                all_const = all_const && cst;
+                all_same = all_same && cst && (first == first_all);
+                const double sd = (double)sk;
+                ssb_raw += sd * sd / (double)m;
+                tot += sd;
+                q += (double)qk;
+            }
+            // about the pooled mean (the shift by c0 cancels): sstot = q - tot^2/n, ssbn = sum s_k^2/m - tot^2/n
+            const double nss = tot * tot / bign;
+            const double sstot = q - nss;
+            const double ssbn = ssb_raw - nss;
+            const double sswn = sstot - ssbn;
+            double f = (ssbn / a.dfn) / (sswn / a.dfd);
+            if (all_const) f = CUDART_INF;
+            if (all_same) f = __builtin_nan("");
+            double p = p_f_upper(f, a.dfn, a.dfd, a.ln_beta);
+            if (p <= a.p_flush) p = 0.0;              // float32 fdtrc underflow (float input: scipy returns float32)
+            if (!(p == p) || isinf(p)) p = 0.0;       // phet.py:378 nan_to_num
+            if (a.dbgP) a.dbgP[(size_t)g * (size_t)a.S + (size_t)s] = p;
+            fisher += fisher_term(p);
+        }
+        // fixed-order CTA reduction
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) fisher += __shfl_xor_sync(0xFFFFFFFFu, fisher, o);
+        __syncthreads();
+        if (lane == 0) red[warp] = fisher;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kAnovaThreads / 32; ++w) t += red[w];
+            a.acc_f[g] = t;
+        }
+    }
+}
+
+int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
+                 int capture_debug) {
+    const int64_t KM = K * m, N = c->n0 + c->n1;
+    if (int e = c->anova_idx.alloc((size_t)(S * KM))) return e;
+    if (int e = c->anova_idxT.alloc((size_t)(S * KM))) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->anova_idx.p, idx_host, sizeof(int32_t) * (size_t)(S * KM), cudaMemcpyHostToDevice, c->stream));
+    int *bad = reinterpret_cast<int *>(c->scalars.p + 12);
+    PHET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    k_anova_index<<<(unsigned)((S * KM + 255) / 256), 256, 0, c->stream>>>(c->anova_idx.p, S, KM, c->pos_of_row.p, N, c->anova_idxT.p,
+                                                                          bad);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    int hbad = 0;
+    PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));   // also: idx_host is the caller's buffer
+    PHET_REQUIRE(hbad == 0, "index sets contain a row number outside [0, N)");
+
+    AnovaArgs a;
+    a.xg = c->xg.p;
+    a.n_pad = c->n_pad;
+    a.xg_g0 = c->xg_g0;
+    a.g_begin = c->xg_g0;
+    a.g_end = c->xg_g0 + c->xg_rows;
+    a.N = N;
+    a.idxT = c->anova_idxT.p;
+    a.S = S;
+    a.K = (int)K;
+    a.m = (int)m;
+    a.dfn = (double)(K - 1);
+    a.dfd = (double)(KM - K);
+    a.ln_beta = ln_beta;
+    a.p_flush = p_flush;
+    a.acc_f = c->acc.p;
+    a.dbgP = nullptr;
+    if (capture_debug) {
+        const size_t need = (size_t)c->G * (size_t)S;
+        if (int e = c->dbgP.alloc(need)) return e;
+        PHET_CUDA(cudaMemsetAsync(c->dbgP.p, 0, need * sizeof(double), c->stream));
+        a.dbgP = c->dbgP.p;
+        c->S_local = S;
+    }
+    const int64_t ng = a.g_end - a.g_begin;
+    if (ng < 1) return PHET_OK;
+    const size_t e_st = c->storage == PHET_F32 ? 4 : 8;
+    const size_t smem = (size_t)c->n_pad * e_st;
+    const bool staged = smem <= (size_t)kMaxSmemOptin - 1024;
+    int64_t grid = c->num_sms < ng ? c->num_sms : ng;
+    if (c->storage == PHET_F32) {
+        if (staged) {
+            PHET_CUDA(cudaFuncSetAttribute(k_anova<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_anova<float, true><<<(unsigned)grid, kAnovaThreads, smem, c->stream>>>(a);
+        } else {
+            k_anova<float, false><<<(unsigned)grid, kAnovaThreads, 0, c->stream>>>(a);
+        }
+    } else {
+        if (staged) {
+            PHET_CUDA(cudaFuncSetAttribute(k_anova<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_anova<double, true><<<(unsigned)grid, kAnovaThreads, smem, c->stream>>>(a);
+        } else {
+            k_anova<double, false><<<(unsigned)grid, kAnovaThreads, 0, c->stream>>>(a);
+        }
+    }
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return PHET_OK;
+}
+
+}  // namespace phet

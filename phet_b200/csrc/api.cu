@@ -223,10 +223,11 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.xg_g0 = c->xg_g0;
     a.n0 = c->n0;
     a.n1 = c->n1;
-    a.min_c = c->n0 < c->n1 ? c->n0 : c->n1;
     a.m = m;
     a.n_slices = c->n_slices;
     a.n_last = n_last;
+    a.min_c = (c->n_slices - 1) * m + n_last;
+    a.cap = m > n_last ? m : n_last;
     a.g_begin = g_begin;
     a.g_end = g_end;
     a.perm_mode = perm_mode;
@@ -359,6 +360,8 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->mtx_rows.release();
     c->mtx_cols.release();
     c->mtx_cnt.release();
+    c->anova_idx.release();
+    c->anova_idxT.release();
     c->rank_keys.release();
     c->rank_order.release();
     c->rank_sorted.release();
@@ -558,9 +561,19 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
     PHET_REQUIRE(m >= 1 && m <= 512, "slice length m must be in [1, 512]");
     PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE, "bad perm_mode");
     PHET_REQUIRE(table_full && table_last, "KS tables are NULL");
-    const int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
-    const int64_t n_slices = (min_c + m - 1) / m;
-    PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");
+    int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
+    int64_t n_slices = (min_c + m - 1) / m;
+    if (c->step3_min_size > 0) {
+        // multi-class fit (phet.py:466-492): slice starts cover [0, min_size) of the smallest of ALL classes, and the
+        // last slice runs to the end of the shorter column of the pair, so n_last may exceed m
+        PHET_REQUIRE(c->step3_min_size <= min_c, "PHET_OPT_STEP3_MIN_SIZE exceeds min(n0, n1)");
+        n_slices = (c->step3_min_size + m - 1) / m;
+        PHET_REQUIRE(n_last >= 1 && (n_slices - 1) * m + n_last <= min_c, "n_last runs past the shorter class");
+        PHET_REQUIRE(n_last <= 512, "last slice longer than 512 cells is not supported by the slice sorters");
+        min_c = (n_slices - 1) * m + n_last;
+    } else {
+        PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");
+    }
     c->n_slices = n_slices;
     {   // h0: table_full is non-increasing on [h0, m] and table_full[h0] <= every earlier entry (the exact
         // formula is only "essentially" monotone: rounding noise of 1 ulp at h = 1, 2 for some n)
@@ -856,6 +869,16 @@ int phet_mtx_kept(phet_ctx *c, int32_t *rows_out, int32_t *cols_out) {
     return PHET_OK;
 }
 
+// ---- multi-class Step 1 (anova.cu)
+int phet_anova(phet_ctx *c, const int32_t *idx, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush_below,
+               int capture_debug) {
+    PHET_REQUIRE(c != nullptr && idx != nullptr, "NULL argument");
+    PHET_REQUIRE(c->matrix_set && c->classes_set, "load the classes and the matrix before phet_anova");
+    PHET_REQUIRE(S >= 1 && K >= 2 && m >= 2 && m <= 512 && K <= 1024, "need S >= 1, 2 <= K <= 1024, 2 <= m <= 512");
+    PHET_CUDA(cudaSetDevice(c->device));
+    return launch_anova(c, idx, S, K, m, ln_beta, p_flush_below, capture_debug);
+}
+
 // ---- ranking (rank.cu)
 int phet_rank(phet_ctx *c, const double *scores, int64_t G, int64_t k, int32_t *order_out, double *sorted_out) {
     PHET_REQUIRE(c != nullptr, "NULL argument");
@@ -944,6 +967,10 @@ int phet_set_option(phet_ctx *c, int option, int64_t value) {
     PHET_REQUIRE(c != nullptr, "ctx is NULL");
     switch (option) {
         case PHET_OPT_KEEP_H: c->keep_H = value != 0; return PHET_OK;
+        case PHET_OPT_STEP3_MIN_SIZE:
+            PHET_REQUIRE(value >= 0, "PHET_OPT_STEP3_MIN_SIZE must be >= 0");
+            c->step3_min_size = value;
+            return PHET_OK;
         default: set_error("invalid: unknown option"); return PHET_ERR_INVALID;
     }
 }

@@ -144,6 +144,10 @@ struct phet_ctx {
     phet::DevBuf<int32_t> mtx_r, mtx_c, mtx_prog, mtx_rows, mtx_cols, mtx_cnt;
     std::vector<int32_t> mtx_rows_host, mtx_cols_host;   // kept cells / genes, ascending (train.py:92,111)
     int64_t mtx_N = 0, mtx_G = 0;                        // shape of mtx_out
+    // multi-class Step 1 (anova.cu) and the Step-3 slicing range of a multi-class fit
+    phet::DevBuf<int32_t> anova_idx;
+    phet::DevBuf<uint32_t> anova_idxT;
+    int64_t step3_min_size = 0;          // phet_set_option(PHET_OPT_STEP3_MIN_SIZE): slices cover [0, this) instead of [0, min(n0, n1))
     // ranking (rank.cu)
     phet::DevBuf<unsigned long long> rank_keys;
     phet::DevBuf<int32_t> rank_order;
@@ -168,6 +172,8 @@ int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
 int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
 int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
+int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
+                 int capture_debug);
 int mtx_parse(const char *path, int threads, phet_mtx &m);
 int mtx_stage(phet_ctx *c, const phet_mtx &m, int do_filter, int64_t minimum_samples, int64_t dims_out[2]);
 

@@ -24,7 +24,8 @@ constexpr int kThreads3 = 512;
 struct Step3Args {
     const void *xg;  // row of gene g starts at xg + (g - xg_g0) * n_pad elements
     int64_t n_pad, G, xg_g0;
-    int64_t n0, n1, min_c, m, n_slices, n_last;
+    int64_t n0, n1, min_c, m, n_slices, n_last;   // min_c: positions covered by the slices = (n_slices - 1) m + n_last
+    int64_t cap;   // max(m, n_last): what a slice sorter must hold (n_last > m only in multi-class fits, phet.py:488-492)
     int64_t g_begin, g_end;
     int perm_mode;
     const uint32_t *perm0, *perm1;  // [G][min_c] class-relative grouped positions (host mode, remapped at upload)
@@ -225,7 +226,7 @@ static int launch_step3_E(phet_ctx *c, const Step3Args &args) {
 
 template <typename T>
 static int run_step3_T(phet_ctx *c, const Step3Args &args) {
-    const int need = (int)((args.m + 31) / 32);
+    const int need = (int)((args.cap + 31) / 32);
     // slices of length <= 256 are served by the half-warp path (step3h_impl.cuh)
     if (need <= 10) return launch_step3_E<T, 10>(c, args);
     if (need <= 12) return launch_step3_E<T, 12>(c, args);

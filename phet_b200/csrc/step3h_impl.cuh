@@ -180,8 +180,8 @@ static int run_step3_any(phet_ctx *c, const Step3Args &args) {
         const int rc = run_step3_prune<T>(c, args);
         if (rc != 1) return rc;
     }
-    if (args.m > 256) return run_step3_T<T>(c, args);
-    const int need = (int)((args.m + 15) / 16);
+    if (args.cap > 256) return run_step3_T<T>(c, args);
+    const int need = (int)((args.cap + 15) / 16);
     if (need <= 1) return launch_step3h_E<T, 1>(c, args);
     if (need <= 2) return launch_step3h_E<T, 2>(c, args);
     if (need <= 3) return launch_step3h_E<T, 3>(c, args);

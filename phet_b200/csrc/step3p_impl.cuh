@@ -485,7 +485,7 @@ static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
 
 template <typename T>
 int run_step3_prune(phet_ctx *c, const Step3Args &args) {
-    if (c->keep_H || c->step3_impl == 1 || c->tab_h0 < 0) return 1;
+    if (c->keep_H || c->step3_impl == 1 || c->tab_h0 < 0 || args.n_last > args.m) return 1;
     const int need = (int)((args.m + 15) / 16);
     if (need <= 1) return launch_step3p_E<T, 1>(c, args);
     if (need <= 2) return launch_step3p_E<T, 2>(c, args);

@@ -84,8 +84,10 @@ class PHet:
     # ------------------------------------------------------------------------------------
     def _check_scope(self, num_classes, sample_ids):
         if num_classes > 2:
-            raise NotImplementedError("phet_b200 covers the two-condition path; the multi-class branch "
-                                      "(phet.py:304-306,348-382) is out of scope")
+            if self.multiconditions_strategy not in ("one_vs_all", "pairwise"):
+                raise ValueError("multiconditions_strategy must be 'one_vs_all' or 'pairwise'")
+            if self.multiconditions_aggregation not in ("max", "mean"):
+                raise ValueError("multiconditions_aggregation must be 'max' or 'mean'")
         if sample_ids:
             raise NotImplementedError("pseudobulk branch (phet.py:224-253) is out of scope")
         if self.delta_type != "iqr":
@@ -158,6 +160,11 @@ class PHet:
         if len(y) != num_examples:
             raise Exception("The number of labels does not match the number of examples!")
         y = np.searchsorted(unique_classes, y)  # LabelEncoder, phet.py:220
+        if num_classes > 2:
+            from .multiclass import fit_multiclass
+            scores = fit_multiclass(self, X, y, num_classes, staged)
+            self.timings_["fit_s"] = time.perf_counter() - t_all
+            return scores
 
         examples_i = np.where(y == 0)[0]
         examples_j = np.where(y == 1)[0]

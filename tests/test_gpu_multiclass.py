@@ -1,0 +1,113 @@
+"""GPU: multi-class branch through the C ABI against the fixtures produced by the unmodified
+reference (tests/golden/make_golden_multiclass.py).  Integer outputs (KS statistics, bins, bin counts, ranking)
+must be identical; floating-point outputs agree within rtol 1e-5 for float64 input and 1e-3 for float32 input."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(os.path.basename(p)[len("multi_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "multi_*.npz")))
+
+
+def _fit(z, **kw):
+    from phet_b200 import PHet
+    est = PHet(num_subsamples=int(z["S"]), percentiles=tuple(z["percentiles"]), multiconditions_strategy=str(z["strategy"]),
+               multiconditions_aggregation=str(z["aggregation"]), capture=True, device=0, **kw)
+    np.random.seed(12345)
+    scores = est.fit_predict(z["X"], z["y"].astype(np.int64))
+    return est, scores
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_multiclass_matches_reference(name):
+    z = np.load(os.path.join(GOLDEN_DIR, "multi_%s.npz" % name))
+    f32 = z["X"].dtype == np.float32
+    rtol = 1e-3 if f32 else 1e-5
+    est, scores = _fit(z)
+    assert est.m_ == int(z["m"])
+    # Step 1a: ANOVA p-values and Fisher sums
+    P = z["P"]
+    big = P > 1e-290
+    assert np.array_equal(est.P_ == 0, P == 0) or f32
+    assert np.allclose(est.P_[big], P[big], rtol=5e-3 if f32 else 1e-9, atol=0)
+    assert np.allclose(est.fsum_, z["fsum"], rtol=rtol, atol=1e-9)
+    # Step 1b: delta-IQR sums per combination
+    assert np.allclose(est.rsum_combo_, z["rsum"], rtol=1e-5 if f32 else 1e-12, atol=1e-12)
+    # Step 3: integer KS statistics per combination and slice, and the p-values looked up from them
+    for c in range(z["H"].shape[1]):
+        assert np.array_equal(est.H_combo_[c], z["H"][:, c, :]), c
+    assert np.array_equal(est.o_combo_, z["o_combo"])
+    assert np.array_equal(est.o_, z["o"])
+    assert np.array_equal(est.bins_, z["bins"])
+    assert np.array_equal(est.bin_counts_, z["bin_counts"])
+    assert np.allclose(est.edges_, z["edges"], rtol=0, atol=0)
+    assert np.allclose(est.r_, z["r"], rtol=1e-5 if f32 else 1e-12, atol=1e-15)
+    assert np.allclose(est.f_, z["f"], rtol=rtol, atol=1e-9)
+    assert scores.shape == z["scores_ref"].shape
+    assert np.allclose(scores, z["scores_ref"], rtol=rtol, atol=1e-12)
+    if not f32:
+        order = np.argsort(-z["scores_ref"][:, 0], kind="stable")
+        assert np.array_equal(est.ranking_[:10], order[:10])
+
+
+def test_multiclass_without_capture_and_device_permutations():
+    """The production configuration: no per-slice capture (the pruning kernel may run), device-side permutations.
+    The permutation stream differs from NumPy's, so only the permutation-independent parts are compared."""
+    z = np.load(os.path.join(GOLDEN_DIR, "multi_k3_sqrt.npz"))
+    from phet_b200 import PHet
+    np.random.seed(12345)
+    est = PHet(num_subsamples=int(z["S"]), device=0)
+    ref_scores = est.fit_predict(z["X"], z["y"].astype(np.int64))
+    assert np.allclose(ref_scores, z["scores_ref"], rtol=1e-5, atol=1e-12)
+    np.random.seed(12345)
+    dev = PHet(num_subsamples=int(z["S"]), device=0, permutation="device")
+    s2 = dev.fit_predict(z["X"], z["y"].astype(np.int64))
+    assert s2.shape == ref_scores.shape and np.isfinite(s2).all() and abs(s2.sum() - 2.0) < 1e-9
+    assert dev.bin_counts_.sum() == z["X"].shape[1]
+
+
+def test_anova_constant_groups_and_large_statistics():
+    """f_oneway's constant-input rules (all groups constant -> p = 0; everything identical -> NaN -> 0) and p-values
+    far down the tail, straight through phet_anova against scipy."""
+    from scipy import stats
+    import math
+    from phet_b200 import _capi
+    rng = np.random.default_rng(0)
+    K, m, S, G = 3, 12, 16, 8
+    N = 90
+    y = np.repeat(np.arange(K), N // K)
+    X = rng.normal(size=(N, G))
+    X[:, 0] = 2.0                                  # identical everywhere
+    X[:, 1] = y * 1.5                              # constant inside each class
+    X[:, 2] += y * 8.0                             # very large F
+    X[:, 3] += y * 40.0                            # p far below 1e-30
+    idx = np.empty((S, K, m), dtype=np.int32)
+    for s in range(S):
+        for c in range(K):
+            idx[s, c] = rng.choice(np.where(y == c)[0], m, replace=False)
+    ctx = _capi.Context(0)
+    try:
+        ctx.set_classes(np.where(y == 0)[0], np.where(y != 0)[0])
+        ctx.load_matrix(X, _capi.NORM_NONE)
+        a, b = 0.5 * (K * m - K), 0.5 * (K - 1)
+        ctx.anova(idx, math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b), 0.0, capture=True)
+        P = ctx.read(_capi.BUF_P, np.float64, (G, S))
+        fsum = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[0]
+    finally:
+        ctx.close()
+    want = np.zeros((G, S))
+    for s in range(S):
+        with np.errstate(all="ignore"):
+            _, p = stats.f_oneway(*[X[idx[s, c]] for c in range(K)])
+        want[:, s] = np.nan_to_num(p, nan=0.0, posinf=0.0, neginf=0.0)
+    assert np.array_equal(P[:2], np.zeros((2, S))) and np.array_equal(want[:2], np.zeros((2, S)))
+    assert np.allclose(P, want, rtol=1e-9, atol=0)
+    with np.errstate(divide="ignore"):
+        t = -2 * np.log(want)
+    t[t == np.inf] = 0
+    assert np.allclose(fsum, t.sum(1), rtol=1e-10, atol=1e-9)
