@@ -111,6 +111,8 @@ def fit_multiclass(est, X, y, K, staged):
         raise NotImplementedError("the multi-class branch runs on one device")
     if est.group_test not in ("anova", "kruskal"):
         raise ValueError("group_test must be 'anova' or 'kruskal'")
+    if est.multiconditions_strategy == "pairwise" and est.permutation == "device":
+        raise NotImplementedError("pairwise combinations need permutation='reference' (the device walk covers a whole group)")
     agg = est.multiconditions_aggregation
     N, G = X.shape
     S = int(est.num_subsamples)
@@ -143,7 +145,10 @@ def fit_multiclass(est, X, y, K, staged):
         ctx.set_option(_capi.OPT_KEEP_H, 1 if est.capture else 0)
         for c, (ei, ej) in enumerate(members):
             ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, 0)
-            ctx.set_classes(ei, ej)
+            # pairwise: the cells of the other classes ride behind the second group (the layout must hold every
+            # cell: the z-score is over all of them and the ANOVA draws address them); nothing ever indexes them
+            rest = np.setdiff1d(np.arange(N), np.concatenate([ei, ej]))
+            ctx.set_classes(ei, np.concatenate([ej, rest]) if rest.size else ej)
             if is_staged:
                 ctx.load_matrix_device(X.device_ptr, N, G, dtype, norm, storage)
             else:
