@@ -60,6 +60,7 @@ typedef enum {
     PHET_BUF_ACC_O = 14,   /* double[3][G]: PHET_BUF_ACC followed by PHET_BUF_O, contiguous (one all-reduce for both)    */
     PHET_BUF_STAGED = 15,  /* float32 [cells kept][genes kept], row-major: the matrix phet_mtx_stage left in HBM */
     PHET_BUF_RANK_ORDER = 16, /* int32[G]: gene index at each rank, descending score (phet_rank)                        */
+    PHET_BUF_RAW = 17,     /* the caller's matrix as given to phet_stage_matrix (row-major cells x genes)                 */
     PHET_BUF_PROFILE = 13  /* uint64[16]: per-phase cycle counters of the Step-3 kernel, only with env PHET_PROFILE=1 */
 } phet_buffer;
 
@@ -103,6 +104,11 @@ int phet_set_classes(phet_ctx *ctx, const int32_t *ctrl_rows, int64_t n0,
  * storage: element type of the normalised gene-major copy kept in HBM and staged to SMEM. */
 int phet_load_matrix(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G,
                      int dtype, int normalize, int storage);
+
+/* Copy a host matrix (row-major cells x genes, `dtype`) to HBM once, unchanged: PHET_BUF_RAW.  For callers that
+ * lay the same matrix out several times with phet_load_matrix(is_device = 1) -- the multi-class fit regroups the
+ * cells once per combination (phet.py:387-392) and should cross PCIe once. */
+int phet_stage_matrix(phet_ctx *ctx, const void *X, int64_t N, int64_t G, int dtype);
 
 /* Subsample index sets (phet.py:401-402), host memory, int32[S][2][m]: for each subsample the
  * control draw then the case draw, ORIGINAL row numbers (duplicates allowed: replace=True). */

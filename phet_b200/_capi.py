@@ -20,14 +20,14 @@ PERM_HOST, PERM_DEVICE = 0, 1
 OPT_KEEP_H = 1
 OPT_STEP3_MIN_SIZE = 2
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
- BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O, BUF_STAGED, BUF_RANK_ORDER) = range(17)
+ BUF_STD, BUF_ROWS, BUF_PROFILE, BUF_ACC_O, BUF_STAGED, BUF_RANK_ORDER, BUF_RAW) = range(18)
 
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
-    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova",
+    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_stage_matrix",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -116,6 +116,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mtx_stage.argtypes = [vp, vp, C.c_int, i64, C.POINTER(i64)]
     lib.phet_mtx_kept.argtypes = [vp, vp, vp]
     lib.phet_rank.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.phet_stage_matrix.argtypes = [vp, vp, i64, i64, C.c_int]
     lib.phet_anova.argtypes = [vp, vp, i64, i64, i64, dbl, dbl, C.c_int]
     lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
     lib.phet_host_p_two_sided_t.restype = dbl
@@ -221,6 +222,12 @@ class Context:
         st = dt if storage is None else storage
         _check(self.lib.phet_load_matrix(self.h, _ptr(X), 0, X.shape[0], X.shape[1], dt, normalize, st))
         self.N, self.G = X.shape
+
+    def stage_matrix(self, X: np.ndarray) -> int:
+        """Copy a C-contiguous float32 / float64 host matrix to HBM once (BUF_RAW); returns the device pointer."""
+        assert X.flags.c_contiguous and X.dtype in (np.float32, np.float64)
+        _check(self.lib.phet_stage_matrix(self.h, _ptr(X), X.shape[0], X.shape[1], PHET_F32 if X.dtype == np.float32 else PHET_F64))
+        return self.device_ptr(BUF_RAW)[0]
 
     def load_matrix_device(self, dev_ptr: int, N: int, G: int, dtype: int, normalize=NORM_ZSCORE, storage=None):
         st = dtype if storage is None else storage

@@ -360,6 +360,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->mtx_rows.release();
     c->mtx_cols.release();
     c->mtx_cnt.release();
+    c->raw_keep.release();
     c->anova_idx.release();
     c->anova_idxT.release();
     c->rank_keys.release();
@@ -869,6 +870,23 @@ int phet_mtx_kept(phet_ctx *c, int32_t *rows_out, int32_t *cols_out) {
     return PHET_OK;
 }
 
+// Copy a host matrix to HBM once, as given (row-major cells x genes): PHET_BUF_RAW.  For callers that lay the same
+// matrix out several times (a multi-class fit regroups the cells once per combination).
+int phet_stage_matrix(phet_ctx *c, const void *X, int64_t N, int64_t G, int dtype) {
+    PHET_REQUIRE(c != nullptr && X != nullptr, "NULL argument");
+    PHET_REQUIRE(N >= 1 && G >= 1, "N, G must be >= 1");
+    PHET_REQUIRE(dtype == PHET_F32 || dtype == PHET_F64, "dtype must be PHET_F32 or PHET_F64");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)N * (size_t)G * (dtype == PHET_F32 ? 4 : 8);
+    if (int e = c->raw_keep.alloc(bytes)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->raw_keep.p, X, bytes, cudaMemcpyHostToDevice, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    c->raw_N = N;
+    c->raw_G = G;
+    c->raw_dtype = dtype;
+    return PHET_OK;
+}
+
 // ---- multi-class Step 1 (anova.cu)
 int phet_anova(phet_ctx *c, const int32_t *idx, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush_below,
                int capture_debug) {
@@ -920,6 +938,7 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;
         case PHET_BUF_ACC_O: *p = c->acc.p; *bytes = (int64_t)sizeof(double) * 3 * c->G; break;
+        case PHET_BUF_RAW: *p = c->raw_keep.p; *bytes = c->raw_N * c->raw_G * (c->raw_dtype == PHET_F32 ? 4 : 8); break;
         case PHET_BUF_STAGED: *p = c->mtx_out.p; *bytes = (int64_t)sizeof(float) * c->mtx_N * c->mtx_G; break;
         case PHET_BUF_RANK_ORDER: *p = c->rank_order.p; *bytes = (int64_t)sizeof(int32_t) * (int64_t)c->rank_order.n; break;
         case PHET_BUF_PROFILE: *p = c->prof.p; *bytes = 16 * (int64_t)sizeof(unsigned long long); break;

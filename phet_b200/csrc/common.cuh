@@ -144,6 +144,9 @@ struct phet_ctx {
     phet::DevBuf<int32_t> mtx_r, mtx_c, mtx_prog, mtx_rows, mtx_cols, mtx_cnt;
     std::vector<int32_t> mtx_rows_host, mtx_cols_host;   // kept cells / genes, ascending (train.py:92,111)
     int64_t mtx_N = 0, mtx_G = 0;                        // shape of mtx_out
+    phet::DevBuf<unsigned char> raw_keep;   // phet_stage_matrix: the caller's matrix as given, kept for repeated layouts
+    int64_t raw_N = 0, raw_G = 0;
+    int raw_dtype = PHET_F32;
     // multi-class Step 1 (anova.cu) and the Step-3 slicing range of a multi-class fit
     phet::DevBuf<int32_t> anova_idx;
     phet::DevBuf<uint32_t> anova_idxT;

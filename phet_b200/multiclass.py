@@ -143,16 +143,14 @@ def fit_multiclass(est, X, y, K, staged):
     H = []
     try:
         ctx.set_option(_capi.OPT_KEEP_H, 1 if est.capture else 0)
+        raw_ptr = X.device_ptr if is_staged else ctx.stage_matrix(X)          # the matrix crosses PCIe once
         for c, (ei, ej) in enumerate(members):
             ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, 0)
             # pairwise: the cells of the other classes ride behind the second group (the layout must hold every
             # cell: the z-score is over all of them and the ANOVA draws address them); nothing ever indexes them
             rest = np.setdiff1d(np.arange(N), np.concatenate([ei, ej]))
             ctx.set_classes(ei, np.concatenate([ej, rest]) if rest.size else ej)
-            if is_staged:
-                ctx.load_matrix_device(X.device_ptr, N, G, dtype, norm, storage)
-            else:
-                ctx.load_matrix(X, norm, storage)
+            ctx.load_matrix_device(raw_ptr, N, G, dtype, norm, storage)
             if c == 0:
                 ctx.anova(idx_anova, ln_beta, p_flush, capture=est.capture)
                 fsum = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[0].copy()

@@ -1,0 +1,82 @@
+"""Measurement of the multi-class branch on the GPU box: a K = 3 fit on a synthetic
+matrix (classes of N/3 cells, S subsamples, device-side Step-3 permutations), the ANOVA kernel alone, and the
+reference's CPU arithmetic for the same ANOVA step (scipy f_oneway, one core) on a bounded sample.
+usage: python scripts/bench_multiclass.py [N G S]"""
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from phet_b200 import PHet, _capi  # noqa: E402
+
+
+def main():
+    N, G, S = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (10000, 30000, 1000)
+    K = 3
+    dev = torch.device("cuda", 0)
+    Xd = bench.synth_matrix_device(N, G, dev)
+    y = (np.arange(N) * K // N).astype(np.int64)
+    Xd[torch.from_numpy(y == 2).to(dev), : G // 20] += 0.5
+    X = Xd.cpu().numpy()
+    sizes = [int((y == c).sum()) for c in range(K)]
+    # whole fit through the model class (host draws, K layouts, ANOVA, K x (delta-IQR, KS), finalize)
+    best = None
+    for it in range(2):
+        np.random.seed(12345)
+        est = PHet(num_subsamples=S, device=0, permutation="device")
+        t0 = time.perf_counter()
+        scores = est.fit_predict(X, y)
+        t1 = time.perf_counter()
+        if best is None or t1 - t0 < best[0]:
+            best = (t1 - t0, est.timings_.get("host_draws_s", 0.0), est.launches_)
+    m = est.m_
+    # the ANOVA kernel alone, CUDA events around phet_anova's launches (index upload included)
+    ctx = _capi.Context(0)
+    ctx.set_classes(np.where(y == 0)[0], np.where(y != 0)[0])
+    ctx.load_matrix_device(Xd.data_ptr(), N, G, _capi.PHET_F32, _capi.NORM_ZSCORE, _capi.PHET_F32)
+    rng = np.random.default_rng(0)
+    idx = np.stack([np.stack([rng.choice(np.where(y == c)[0], m, replace=False) for c in range(K)]) for _ in range(S)]).astype(np.int32)
+    a, b = 0.5 * (K * m - K), 0.5 * (K - 1)
+    lnb = math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b)
+    ctx.anova(idx, lnb, 2.0 ** -150)
+    ctx.sync()
+    ts = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        ctx.anova(idx, lnb, 2.0 ** -150)
+        ctx.sync()
+        ts.append(time.perf_counter() - t0)
+    anova_ms = min(ts) * 1e3
+    fsum = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[0]
+    # CPU: scipy f_oneway on z-scored float32 data, a bounded sample of subsamples over 2048 genes, one core
+    from scipy import stats
+    Gs, Ss = min(G, 2048), min(S, 20)
+    Xz = stats.zscore(X[:, :Gs].astype(np.float32), axis=0)
+    t0 = time.perf_counter()
+    want = np.zeros(Gs)
+    for s in range(Ss):
+        with np.errstate(all="ignore"):
+            _, p = stats.f_oneway(*[Xz[idx[s, c]] for c in range(K)])
+        p = np.nan_to_num(np.asarray(p, dtype=np.float64), nan=0.0, posinf=0.0, neginf=0.0)
+    cpu_s = time.perf_counter() - t0
+    cpu_units = Gs * Ss / cpu_s
+    ctx.close()
+    units = G * S
+    smem_bytes = units * K * m * 4
+    print(json.dumps({
+        "what": "multi-class PHet fit (K=3, one_vs_all, anova, device permutations)", "cells": N, "genes": G, "subsamples": S,
+        "class_sizes": sizes, "m": m, "fit_wall_s": best[0], "host_draws_s": best[1], "gpu_launches": best[2],
+        "score_sum": float(scores.sum()), "anova_ms": anova_ms, "anova_units_per_s": units / (anova_ms * 1e-3),
+        "anova_smem_gather_gbs": smem_bytes / (anova_ms * 1e-3) / 1e9,
+        "cpu_f_oneway_units_per_s_1core": cpu_units, "cpu_sample": "%d subsamples x %d genes" % (Ss, Gs),
+        "anova_speedup_vs_1core": units / (anova_ms * 1e-3) / cpu_units, "fsum_finite": bool(np.isfinite(fsum).all())}))
+
+
+if __name__ == "__main__":
+    main()
