@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libphet_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "normalize.cu", "finalize.cu", "classstats.cu", "rank.cu", "mtx.cu", "anova.cu", "step1_f32.cu", "step1_f64.cu", "step3_f32.cu", "step3_f64.cu",
+SOURCES = ["api.cu", "normalize.cu", "finalize.cu", "classstats.cu", "rank.cu", "mtx.cu", "anova.cu", "step3big.cu", "step1_f32.cu", "step1_f64.cu", "step3_f32.cu", "step3_f64.cu",
            "step3p_f32.cu", "step3p_f64.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", 

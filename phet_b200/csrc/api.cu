@@ -31,6 +31,7 @@ int run_step1_f32(phet_ctx *c, const Step1Args &a);
 int run_step1_f64(phet_ctx *c, const Step1Args &a);
 int run_step3_f32(phet_ctx *c, const Step3Args &a);
 int run_step3_f64(phet_ctx *c, const Step3Args &a);
+int launch_ks_big(phet_ctx *c, const Step3Args &a, int fold);
 
 // original row numbers -> class-grouped positions, in place
 __global__ void k_remap_idx(int32_t *__restrict__ idx, int64_t n, const int32_t *__restrict__ pos_of_row, int64_t N,
@@ -228,6 +229,7 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.n_last = n_last;
     a.min_c = (c->n_slices - 1) * m + n_last;
     a.cap = m > n_last ? m : n_last;
+    a.h_ld = c->n_slices;
     a.g_begin = g_begin;
     a.g_end = g_end;
     a.perm_mode = perm_mode;
@@ -240,6 +242,17 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.tab_last = c->tab_last.p;
     a.o = c->o.p;
     a.H = c->H.p;
+    if (n_last > 512) {
+        // multi-class fit with unbalanced classes: the slice sorters take the full slices, the block sorter the last one
+        if (c->n_slices > 1) {
+            Step3Args f = a;
+            f.n_slices = c->n_slices - 1;
+            f.n_last = m;
+            f.cap = m;
+            if (int e = c->storage == PHET_F32 ? run_step3_f32(c, f) : run_step3_f64(c, f)) return e;
+        }
+        return launch_ks_big(c, a, c->n_slices > 1 ? 1 : 0);
+    }
     return c->storage == PHET_F32 ? run_step3_f32(c, a) : run_step3_f64(c, a);
 }
 
@@ -570,7 +583,6 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
         PHET_REQUIRE(c->step3_min_size <= min_c, "PHET_OPT_STEP3_MIN_SIZE exceeds min(n0, n1)");
         n_slices = (c->step3_min_size + m - 1) / m;
         PHET_REQUIRE(n_last >= 1 && (n_slices - 1) * m + n_last <= min_c, "n_last runs past the shorter class");
-        PHET_REQUIRE(n_last <= 512, "last slice longer than 512 cells is not supported by the slice sorters");
         min_c = (n_slices - 1) * m + n_last;
     } else {
         PHET_REQUIRE(n_last == min_c - (n_slices - 1) * m, "n_last does not match min(n0,n1) and m");

@@ -25,6 +25,7 @@ struct Step3Args {
     const void *xg;  // row of gene g starts at xg + (g - xg_g0) * n_pad elements
     int64_t n_pad, G, xg_g0;
     int64_t n0, n1, min_c, m, n_slices, n_last;   // min_c: positions covered by the slices = (n_slices - 1) m + n_last
+    int64_t h_ld;  // row length of H (slices of the fit; a launch may cover fewer: see step3big.cu)
     int64_t cap;   // max(m, n_last): what a slice sorter must hold (n_last > m only in multi-class fits, phet.py:488-492)
     int64_t g_begin, g_end;
     int perm_mode;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
             h = __reduce_max_sync(kFull, h);
             const double pv = (n == (int)a.m) ? __ldg(a.tab_full + h) : __ldg(a.tab_last + h);
             omin = fmin(omin, pv);
-            if (a.H != nullptr && lane == 0) a.H[g * a.n_slices + k] = h;
+            if (a.H != nullptr && lane == 0) a.H[g * a.h_ld + k] = h;
             __syncwarp();
         }
         if (lane == 0) part[warp] = omin;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
             hmax = __reduce_max_sync(kFull, hmax);
             const double pv = (n == (int)a.m) ? __ldg(a.tab_full + hmax) : __ldg(a.tab_last + hmax);
             omin = fmin(omin, pv);
-            if (a.H != nullptr && lane == 0) a.H[g * a.n_slices + k] = hmax;
+            if (a.H != nullptr && lane == 0) a.H[g * a.h_ld + k] = hmax;
             __syncwarp();
         }
         if (lane == 0) part[warp] = omin;

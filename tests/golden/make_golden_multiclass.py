@@ -50,6 +50,8 @@ CASES = [
     ("k3_pairwise_mean", (70, 64, 80), 40, 20, "f64", dict(multiconditions_strategy="pairwise",
                                                              multiconditions_aggregation="mean")),
     ("k3_counts_p1090", (81, 90, 100), 60, 30, "f64", dict(percentiles=(10, 90), kind="counts")),
+    ("k3_unbalanced", (2500, 160, 1400), 24, 10, "f64", {}),      # m = 12; last slices of 1404 / 4 / 1244 cells
+    ("k3_oneslice_big", (700, 40, 650), 20, 10, "f32", {}),       # m = 40 = min_size: one slice of 690 / 40 / 650 cells
 ]
 
 
