@@ -225,6 +225,12 @@ int phet_class_stats(phet_ctx *ctx, const phet_quantile_pos *q3, double *out);
 int phet_anova(phet_ctx *ctx, const int32_t *idx, int64_t S, int64_t K, int64_t m, double ln_beta,
                double p_flush_below, int capture_debug);
 
+/* The same with group_test="kruskal" (phet.py:373-375, taken when m > 5): scipy.stats.kruskal over the K groups --
+ * average ranks of the pooled K m values (exact, by counting), H with the tie correction, p = chi2.sf(H, K - 1).
+ * K <= 64, K m <= 3072 (float storage) / 1536 (double storage). */
+int phet_kruskal(phet_ctx *ctx, const int32_t *idx, int64_t S, int64_t K, int64_t m, double p_flush_below,
+                 int capture_debug);
+
 /* Input path.  phet_mtx_parse replaces src/train.py:82-83 (sc.read_mtx: scipy.io.mmread,
  * float32): a multi-threaded host parse of a MatrixMarket `coordinate` file (real | integer | pattern, general |
  * symmetric) into zero-based triplets; values are rounded text -> double -> float like mmread(...).astype("float32").

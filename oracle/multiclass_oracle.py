@@ -76,9 +76,30 @@ def anova_p_plain(groups):
     return special.fdtrc(K - 1, bign - K, f)
 
 
+def kruskal_p_plain(groups):
+    """scipy.stats.kruskal(*groups) along axis 0, formula restatement: average ranks of the pooled values,
+    H = 12/(n(n+1)) sum_k R_k^2/n_k - 3(n+1), tie correction 1 - sum(t^3 - t)/(n^3 - n), p = chi2.sf(H, K-1)."""
+    alldata = np.concatenate(groups, axis=0)
+    n, G = alldata.shape
+    K = len(groups)
+    H = np.empty(G)
+    for g in range(G):
+        col = alldata[:, g]
+        ranked = _stats.rankdata(col)
+        _, cnt = np.unique(col, return_counts=True)
+        ties = 1 - np.sum(cnt.astype(np.float64) ** 3 - cnt) / (float(n) ** 3 - n)
+        ssbn, j = 0.0, 0
+        for gs in groups:
+            ssbn += ranked[j:j + gs.shape[0]].sum() ** 2 / gs.shape[0]
+            j += gs.shape[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            H[g] = (12.0 / (n * (n + 1)) * ssbn - 3 * (n + 1)) / ties
+    return _stats.chi2.sf(H, K - 1), H
+
+
 def fit_predict_multiclass_oracle(X, y, normalize="zscore", percentiles=(25, 75), num_subsamples=1000,
                                   subsampling_size="sqrt", feature_weight=None, strategy="one_vs_all",
-                                  aggregation="max", rng=np.random, library=True):
+                                  aggregation="max", rng=np.random, library=True, group_test="anova"):
     """Replay of PHet.fit_predict for K >= 3 classes, consuming ``rng`` in the reference's order:
     S x K ANOVA draws; per combination S x (i draw, j draw); per gene, per combination (i perm, j perm).
     Returns a dict of every stage."""
@@ -110,7 +131,9 @@ def fit_predict_multiclass_oracle(X, y, normalize="zscore", percentiles=(25, 75)
             t = rng.choice(a=range(sizes[c]), size=m, replace=replace)
             idx_anova[s, c] = rows[c][t]
             groups.append(Xz[idx_anova[s, c]])
-        if library:
+        if group_test == "kruskal" and m > 5:          # phet.py:372-377
+            p = _stats.kruskal(*groups)[1] if library else kruskal_p_plain(groups)[0]
+        elif library:
             _, p = _stats.f_oneway(*groups)
         else:
             p = anova_p_plain(groups)

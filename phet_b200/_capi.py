@@ -27,7 +27,7 @@ EXPORTS = [
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
-    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_stage_matrix",
+    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -117,6 +117,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mtx_kept.argtypes = [vp, vp, vp]
     lib.phet_rank.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.phet_stage_matrix.argtypes = [vp, vp, i64, i64, C.c_int]
+    lib.phet_kruskal.argtypes = [vp, vp, i64, i64, i64, dbl, C.c_int]
     lib.phet_anova.argtypes = [vp, vp, i64, i64, i64, dbl, dbl, C.c_int]
     lib.phet_host_p_two_sided_t.argtypes = [dbl, dbl, dbl]
     lib.phet_host_p_two_sided_t.restype = dbl
@@ -272,6 +273,12 @@ class Context:
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         S, K, m = idx.shape
         _check(self.lib.phet_anova(self.h, _ptr(idx), S, K, m, float(ln_beta), float(p_flush_below), 1 if capture else 0))
+
+    def kruskal(self, idx: np.ndarray, p_flush_below: float = 0.0, capture: bool = False):
+        """idx: int32 (S, K, m) original rows.  Fisher's sum of the Kruskal-Wallis p-values -> BUF_ACC[0:G]."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        S, K, m = idx.shape
+        _check(self.lib.phet_kruskal(self.h, _ptr(idx), S, K, m, float(p_flush_below), 1 if capture else 0))
 
     def set_index_sets(self, idx: np.ndarray):
         """idx: int32 (S, 2, m), original row numbers; [:, 0] control draw, [:, 1] case draw."""

@@ -139,8 +139,143 @@ __global__ void __launch_bounds__(kAnovaThreads, 1) k_anova(const AnovaArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Kruskal-Wallis H (phet.py:373-375, group_test="kruskal" with m > 5): scipy.stats.kruskal(*subsamples) --
+// average ranks of the pooled K*m values, H = 12/(n(n+1)) * sum_k R_k^2/m - 3(n+1), divided by the tie correction
+// 1 - sum(t^3 - t)/(n^3 - n), p = chi2.sf(H, K-1).  One warp per (gene, subsample): the pooled values sit in the
+// warp's shared-memory strip and every element is ranked by counting (#{x < v}, #{x <= v}: 128-bit broadcast
+// loads, four own elements per pass) -- n^2 comparisons per unit but no sort, no payload, and exact integer
+// (doubled) ranks, rank sums and tie sums, so H is the reference's up to its last few floating-point operations.
+constexpr int kKwThreads = 512;
+constexpr int kKwMaxGroups = 64;
+
+// chi2.sf(x, df) = igamc(df/2, x/2), df a small positive integer: finite sums (no cancellation)
+__device__ __forceinline__ double chi2_sf_int(double x, int df) {
+    if (!(x == x)) return __builtin_nan("");
+    if (x < 0.0) return 1.0;   // cephes chdtrc
+    const double y = 0.5 * x;
+    if (isinf(y)) return 0.0;
+    const double ey = exp(-y);
+    if ((df & 1) == 0) {       // a = df/2 integer: e^-y sum_{i<a} y^i / i!
+        double term = 1.0, sum = 1.0;
+        for (int i = 1; i < df / 2; ++i) {
+            term *= y / (double)i;
+            sum += term;
+        }
+        return ey * sum;
+    }
+    // a = j + 1/2: erfc(sqrt y) + e^-y sum_{i=1..j} y^(i-1/2) / Gamma(i+1/2)
+    const double sy = sqrt(y);
+    double res = erfc(sy);
+    double term = sy / 0.88622692545275801365;   // y^(1/2) / Gamma(3/2)
+    for (int i = 1; i <= df / 2; ++i) {
+        res += ey * term;
+        term *= y / ((double)i + 0.5);
+    }
+    return res;
+}
+
+template <typename T> struct KwVec;
+template <> struct KwVec<float> {
+    typedef float4 type;
+    static constexpr int width = 4;
+    static __device__ __forceinline__ void get(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct KwVec<double> {
+    typedef double2 type;
+    static constexpr int width = 2;
+    static __device__ __forceinline__ void get(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kKwThreads, 1) k_kruskal(const AnovaArgs a, int n_pad4) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = kKwThreads / 32;
+    constexpr int W = KwVec<T>::width;
+    T *pool_all = reinterpret_cast<T *>(smem_raw);                                  // [NW][n_pad4]
+    int *gsum_all = reinterpret_cast<int *>(smem_raw + (size_t)NW * n_pad4 * sizeof(T));   // [NW][K] doubled rank sums
+    __shared__ double red[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K, m = a.m, n = K * m;
+    T *pool = pool_all + (size_t)warp * n_pad4;
+    int *gsum = gsum_all + warp * K;
+    const double dn = (double)n;
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
+        double fisher = 0.0;
+        for (int64_t s = warp; s < a.S; s += NW) {
+            for (int e = lane; e < n_pad4; e += 32)
+                pool[e] = (e < n) ? __ldg(row + __ldg(a.idxT + (int64_t)e * a.S + s)) : (T)CUDART_INF;
+            for (int k = lane; k < K; k += 32) gsum[k] = 0;
+            __syncwarp();
+            long long tie = 0;   // sum over elements of (t^2 - 1), t = size of the element's tie group
+            for (int base = 0; base < n; base += 128) {
+                T v[4];
+                int lo[4], hi[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = base + lane + 32 * q;
+                    v[q] = pool[e < n ? e : 0];
+                    lo[q] = 0;
+                    hi[q] = 0;
+                }
+                const typename KwVec<T>::type *pv = reinterpret_cast<const typename KwVec<T>::type *>(pool);
+                for (int j = 0; j < n_pad4 / W; ++j) {
+                    T x[W];
+                    KwVec<T>::get(pv[j], x);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            lo[q] += (x[w] < v[q]) ? 1 : 0;
+                            hi[q] += (x[w] <= v[q]) ? 1 : 0;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = base + lane + 32 * q;
+                    if (e < n) {
+                        atomicAdd(&gsum[e / m], lo[q] + hi[q] + 1);   // twice the average rank
+                        const long long t = hi[q] - lo[q];
+                        tie += t * t - 1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) tie += __shfl_xor_sync(0xFFFFFFFFu, tie, o);
+            __syncwarp();
+            if (lane == 0) {
+                double ssbn = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    const double r = 0.5 * (double)gsum[k];
+                    ssbn += r * r / (double)m;
+                }
+                double h = 12.0 / (dn * (dn + 1.0)) * ssbn - 3.0 * (dn + 1.0);
+                const double ties = 1.0 - (double)tie / (dn * dn * dn - dn);
+                h /= ties;
+                double p = chi2_sf_int(h, K - 1);
+                if (p <= a.p_flush) p = 0.0;
+                if (!(p == p) || isinf(p)) p = 0.0;       // phet.py:378 nan_to_num
+                if (a.dbgP) a.dbgP[(size_t)g * (size_t)a.S + (size_t)s] = p;
+                fisher += fisher_term(p);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (lane == 0) red[warp] = fisher;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NW; ++w) t += red[w];
+            a.acc_f[g] = t;
+        }
+    }
+}
+
 int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
-                 int capture_debug) {
+                 int capture_debug, int kruskal) {
     const int64_t KM = K * m, N = c->n0 + c->n1;
     if (int e = c->anova_idx.alloc((size_t)(S * KM))) return e;
     if (int e = c->anova_idxT.alloc((size_t)(S * KM))) return e;
@@ -183,6 +318,23 @@ int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int
     const int64_t ng = a.g_end - a.g_begin;
     if (ng < 1) return PHET_OK;
     const size_t e_st = c->storage == PHET_F32 ? 4 : 8;
+    if (kruskal) {
+        PHET_REQUIRE(K <= kKwMaxGroups, "phet_group_test: Kruskal-Wallis takes at most 64 groups");
+        const int n_pad4 = (int)((KM + 3) / 4 * 4);
+        const size_t smem_kw = (size_t)(kKwThreads / 32) * ((size_t)n_pad4 * e_st + (size_t)K * sizeof(int));
+        PHET_REQUIRE(smem_kw <= (size_t)kMaxSmemOptin - 1024, "phet_group_test: K * m too large for the per-warp rank strips");
+        int64_t gridk = c->num_sms < ng ? c->num_sms : ng;
+        if (c->storage == PHET_F32) {
+            PHET_CUDA(cudaFuncSetAttribute(k_kruskal<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kw));
+            k_kruskal<float><<<(unsigned)gridk, kKwThreads, smem_kw, c->stream>>>(a, n_pad4);
+        } else {
+            PHET_CUDA(cudaFuncSetAttribute(k_kruskal<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kw));
+            k_kruskal<double><<<(unsigned)gridk, kKwThreads, smem_kw, c->stream>>>(a, n_pad4);
+        }
+        c->launches++;
+        PHET_CUDA(cudaGetLastError());
+        return PHET_OK;
+    }
     const size_t smem = (size_t)c->n_pad * e_st;
     const bool staged = smem <= (size_t)kMaxSmemOptin - 1024;
     int64_t grid = c->num_sms < ng ? c->num_sms : ng;

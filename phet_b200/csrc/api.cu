@@ -906,7 +906,15 @@ int phet_anova(phet_ctx *c, const int32_t *idx, int64_t S, int64_t K, int64_t m,
     PHET_REQUIRE(c->matrix_set && c->classes_set, "load the classes and the matrix before phet_anova");
     PHET_REQUIRE(S >= 1 && K >= 2 && m >= 2 && m <= 512 && K <= 1024, "need S >= 1, 2 <= K <= 1024, 2 <= m <= 512");
     PHET_CUDA(cudaSetDevice(c->device));
-    return launch_anova(c, idx, S, K, m, ln_beta, p_flush_below, capture_debug);
+    return launch_anova(c, idx, S, K, m, ln_beta, p_flush_below, capture_debug, 0);
+}
+
+int phet_kruskal(phet_ctx *c, const int32_t *idx, int64_t S, int64_t K, int64_t m, double p_flush_below, int capture_debug) {
+    PHET_REQUIRE(c != nullptr && idx != nullptr, "NULL argument");
+    PHET_REQUIRE(c->matrix_set && c->classes_set, "load the classes and the matrix before phet_kruskal");
+    PHET_REQUIRE(S >= 1 && K >= 2 && m >= 1 && m <= 512, "need S >= 1, K >= 2, 1 <= m <= 512");
+    PHET_CUDA(cudaSetDevice(c->device));
+    return launch_anova(c, idx, S, K, m, 0.0, p_flush_below, capture_debug, 1);
 }
 
 // ---- ranking (rank.cu)

@@ -176,7 +176,7 @@ int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
 int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
 int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
 int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
-                 int capture_debug);
+                 int capture_debug, int kruskal);
 int mtx_parse(const char *path, int threads, phet_mtx &m);
 int mtx_stage(phet_ctx *c, const phet_mtx &m, int do_filter, int64_t minimum_samples, int64_t dims_out[2]);
 

@@ -15,7 +15,7 @@ Mirrors ``/root/reference/src/model/phet.py`` for that branch, with the referenc
 
 Each combination regroups the cells (class i first), so the matrix is laid out once per combination; the K ANOVA
 groups are addressed through the first layout.  Labels must be 0..K-1 already (the reference mixes pre- and
-post-LabelEncoder labels).  Kruskal-Wallis (``group_test="kruskal"`` with m > 5) is not built and raises.
+post-LabelEncoder labels).  ``group_test="kruskal"`` (taken when m > 5, phet.py:372-377) -> ``phet_kruskal``.
 """
 from __future__ import annotations
 
@@ -67,8 +67,6 @@ def plan_and_draw(est, y, K, G):
     m = subsample_size_multi(y, K, est.subsampling_size, strategy)
     if m < 2:
         raise ValueError("subsampling size must be >= 2 for the multi-class branch")
-    if est.group_test == "kruskal" and m > 5:
-        raise NotImplementedError("group_test='kruskal' (phet.py:373-375) is not built; use group_test='anova'")
     min_size = int(np.min(sizes))
     n_slices = (min_size + m - 1) // m
     start_last = (n_slices - 1) * m
@@ -152,7 +150,10 @@ def fit_multiclass(est, X, y, K, staged):
             ctx.set_classes(ei, np.concatenate([ej, rest]) if rest.size else ej)
             ctx.load_matrix_device(raw_ptr, N, G, dtype, norm, storage)
             if c == 0:
-                ctx.anova(idx_anova, ln_beta, p_flush, capture=est.capture)
+                if est.group_test == "kruskal" and m > 5:                    # phet.py:372-377
+                    ctx.kruskal(idx_anova, p_flush, capture=est.capture)
+                else:
+                    ctx.anova(idx_anova, ln_beta, p_flush, capture=est.capture)
                 fsum = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[0].copy()
                 if est.capture:
                     est.P_ = ctx.read(_capi.BUF_P, np.float64, (G, S))

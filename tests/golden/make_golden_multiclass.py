@@ -52,6 +52,9 @@ CASES = [
     ("k3_counts_p1090", (81, 90, 100), 60, 30, "f64", dict(percentiles=(10, 90), kind="counts")),
     ("k3_unbalanced", (2500, 160, 1400), 24, 10, "f64", {}),      # m = 12; last slices of 1404 / 4 / 1244 cells
     ("k3_oneslice_big", (700, 40, 650), 20, 10, "f32", {}),       # m = 40 = min_size: one slice of 690 / 40 / 650 cells
+    ("k3_kruskal", (150, 100, 120), 60, 30, "f64", dict(group_test="kruskal")),              # m = 10 > 5 -> kruskal
+    ("k4_kruskal_counts_f32", (90, 70, 100, 64), 50, 25, "f32", dict(group_test="kruskal", kind="counts")),  # heavy ties
+    ("k3_kruskal_m37", (40, 55, 37), 40, 20, "f64", dict(group_test="kruskal")),            # n = 111: partial last pass
 ]
 
 
@@ -64,26 +67,28 @@ def main():
         percentiles = kw.pop("percentiles", (25, 75))
         strategy = kw.get("multiconditions_strategy", "one_vs_all")
         agg = kw.get("multiconditions_aggregation", "max")
+        gt = kw.get("group_test", "anova")
         np.random.seed(SEED)
         ref = PHet(normalize="zscore", percentiles=percentiles, num_subsamples=S, subsampling_size="sqrt",
-                   delta_type="iqr", group_test="anova", adjust_pvalue=False, feature_weight=[0.4, 0.3, 0.2, 0.1],
-                   **kw).fit_predict(X=np.array(X, copy=True), y=y)
+                   delta_type="iqr", adjust_pvalue=False, feature_weight=[0.4, 0.3, 0.2, 0.1],
+                   **dict(dict(group_test="anova"), **kw)).fit_predict(X=np.array(X, copy=True), y=y)
         np.random.seed(SEED)
         o = mo.fit_predict_multiclass_oracle(X, y, percentiles=percentiles, num_subsamples=S, strategy=strategy,
-                                             aggregation=agg)
+                                             aggregation=agg, group_test=gt)
         diff = float(np.max(np.abs(o["scores"] - ref)))
         print("%-20s m=%d K=%d combos=%d slices=%d  max|oracle-reference| = %g" % (name, o["m"], o["K"], len(o["combos"]),
                                                                                  len(o["slices"]), diff))
         assert diff == 0.0, name
         np.random.seed(SEED)
         o2 = mo.fit_predict_multiclass_oracle(X, y, percentiles=percentiles, num_subsamples=S, strategy=strategy,
-                                              aggregation=agg, library=False)
+                                              aggregation=agg, library=False, group_test=gt)
         print("    plain-formula flavour: max rel diff P = %g, scores = %g" % (
             float(np.max(np.abs(o2["P"] - o["P"]) / np.maximum(o["P"], 1e-300))), float(np.max(np.abs(o2["scores"] - ref)))))
         C = len(o["combos"])
         np.savez_compressed(
             os.path.join(HERE, "multi_%s.npz" % name), X=X, y=y.astype(np.int8), S=np.int64(S), m=np.int64(o["m"]),
             percentiles=np.array(percentiles), strategy=np.array(strategy), aggregation=np.array(agg),
+            group_test=np.array(gt),
             scores_ref=ref, idx_anova=o["idx_anova"].astype(np.int32), P=o["P"], fsum=o["fsum"], rsum=o["rsum"],
             r=o["r"], f=o["f"], H=o["H"], o_combo=o["o_combo"], o=o["o"], bins=o["bins"].astype(np.int8),
             edges=o["edges"], bin_counts=o["bin_counts"], min_size=np.int64(o["min_size"]),

@@ -83,8 +83,9 @@ def test_constructor_mirrors_reference():
         PHet(feature_weight=[1.0])
     with pytest.raises(Exception, match="valid groups"):
         PHet().fit_predict(np.zeros((4, 3)), np.zeros(4))
-    with pytest.raises(NotImplementedError):       # Kruskal-Wallis (m > 5) is not built
-        PHet(group_test="kruskal").fit_predict(np.zeros((24, 3)), np.repeat([0, 1, 2], 8))
+    from phet_b200._capi import PhetError
+    with pytest.raises(PhetError):                 # multi-class is built, but there is no CPU fallback
+        PHet().fit_predict(np.zeros((24, 3)), np.repeat([0, 1, 2], 8))
     with pytest.raises(NotImplementedError):
         PHet(delta_type="hvf").fit_predict(np.zeros((4, 3)), [0, 0, 1, 1])
 

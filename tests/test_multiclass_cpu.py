@@ -24,14 +24,14 @@ def test_oracle_reproduces_reference_scores(name):
     np.random.seed(12345)
     o = mo.fit_predict_multiclass_oracle(z["X"], z["y"].astype(np.int64), percentiles=tuple(z["percentiles"]),
                                          num_subsamples=int(z["S"]), strategy=str(z["strategy"]),
-                                         aggregation=str(z["aggregation"]))
+                                         aggregation=str(z["aggregation"]), group_test=str(z["group_test"]))
     assert np.array_equal(o["scores"], z["scores_ref"])
     assert np.array_equal(o["bins"], z["bins"]) and np.array_equal(o["H"], z["H"])
     # the formula restatement the device follows agrees with scipy's f_oneway
     np.random.seed(12345)
     p = mo.fit_predict_multiclass_oracle(z["X"], z["y"].astype(np.int64), percentiles=tuple(z["percentiles"]),
                                          num_subsamples=int(z["S"]), strategy=str(z["strategy"]),
-                                         aggregation=str(z["aggregation"]), library=False)
+                                         aggregation=str(z["aggregation"]), library=False, group_test=str(z["group_test"]))
     tol = 1e-4 if z["X"].dtype == np.float32 else 1e-11
     assert np.allclose(p["P"], o["P"], rtol=tol, atol=1e-300)
 
@@ -44,7 +44,8 @@ def test_host_draws_replay_the_reference_stream(name):
     y = z["y"].astype(np.int64)
     K = len(np.unique(y))
     est = PHet(num_subsamples=int(z["S"]), percentiles=tuple(z["percentiles"]),
-               multiconditions_strategy=str(z["strategy"]), multiconditions_aggregation=str(z["aggregation"]))
+               multiconditions_strategy=str(z["strategy"]), multiconditions_aggregation=str(z["aggregation"]),
+               group_test=str(z["group_test"]))
     np.random.seed(12345)
     plan = plan_and_draw(est, y, K, z["X"].shape[1])
     assert plan["m"] == int(z["m"]) and plan["min_size"] == int(z["min_size"])
@@ -55,11 +56,3 @@ def test_host_draws_replay_the_reference_stream(name):
         assert np.array_equal(plan["idx_combo"][c][:, 1], z["idx_j_%d" % c])
         assert np.array_equal(plan["perms"][c][0], z["perm_i_%d" % c])
         assert np.array_equal(plan["perms"][c][1], z["perm_j_%d" % c])
-
-
-def test_kruskal_is_a_loud_error():
-    from phet_b200 import PHet
-    from phet_b200.multiclass import plan_and_draw
-    y = np.repeat(np.arange(3), 40)
-    with pytest.raises(NotImplementedError):
-        plan_and_draw(PHet(group_test="kruskal"), y, 3, 5)
