@@ -54,6 +54,16 @@ def main():
         ts.append(time.perf_counter() - t0)
     anova_ms = min(ts) * 1e3
     fsum = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[0]
+    # the Kruskal-Wallis kernel on the same index sets
+    ctx.kruskal(idx, 2.0 ** -150)
+    ctx.sync()
+    tk = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        ctx.kruskal(idx, 2.0 ** -150)
+        ctx.sync()
+        tk.append(time.perf_counter() - t0)
+    kruskal_ms = min(tk) * 1e3
     # CPU: scipy f_oneway on z-scored float32 data, a bounded sample of subsamples over 2048 genes, one core
     from scipy import stats
     Gs, Ss = min(G, 2048), min(S, 20)
@@ -75,7 +85,9 @@ def main():
         "score_sum": float(scores.sum()), "anova_ms": anova_ms, "anova_units_per_s": units / (anova_ms * 1e-3),
         "anova_smem_gather_gbs": smem_bytes / (anova_ms * 1e-3) / 1e9,
         "cpu_f_oneway_units_per_s_1core": cpu_units, "cpu_sample": "%d subsamples x %d genes" % (Ss, Gs),
-        "anova_speedup_vs_1core": units / (anova_ms * 1e-3) / cpu_units, "fsum_finite": bool(np.isfinite(fsum).all())}))
+        "anova_speedup_vs_1core": units / (anova_ms * 1e-3) / cpu_units,
+        "kruskal_ms": kruskal_ms, "kruskal_units_per_s": units / (kruskal_ms * 1e-3),
+        "kruskal_comparisons_per_s": units * float(K * m) ** 2 / (kruskal_ms * 1e-3), "fsum_finite": bool(np.isfinite(fsum).all())}))
 
 
 if __name__ == "__main__":
