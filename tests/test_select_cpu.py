@@ -31,3 +31,18 @@ def test_cli_filter_and_parser():
     y = np.array([0] * 20 + [1] * 20)
     Xf, yf, nf = filter_data(X, y, ["g%d" % i for i in range(30)])
     assert Xf.shape[0] == 39 and len(yf) == 39 and "g5" not in nf and Xf.shape[1] == len(nf)
+
+
+def test_device_order_argument_reproduces_the_sorted_frames():
+    """``order=`` (what phet_rank returns: descending, ties in gene order) yields the frames the pandas sort yields."""
+    from phet_b200.select import significant_features, sort_features
+    z = np.load(os.path.join(GOLDEN_DIR, "cli_srbct.npz"))
+    scores, names = z["scores"], z["names"].tolist()
+    order = np.argsort(-scores[:, 0], kind="stable").astype(np.int32)
+    full = sort_features(X=scores, features_name=names, order=order)
+    assert full["features"].to_list() == z["rank_features"].tolist()
+    sig = significant_features(X=scores, features_name=names, alpha=0.05, fit_type="gamma", per=95, order=order)
+    assert sig["features"].to_list() == z["sig_features"].tolist()
+    assert np.array_equal(sig["score"].to_numpy(), z["sig_scores"])
+    asc = sort_features(X=scores, features_name=names, order=order, ascending=True)
+    assert asc["features"].to_list() == z["rank_features"].tolist()[::-1]
