@@ -92,7 +92,15 @@ def ks_exact_table(n: int) -> np.ndarray:
     if n in _KS_CACHE:
         return _KS_CACHE[n]
     if n > 10000:
-        raise ValueError("slice length > 10000: scipy switches ks_2samp to the asymptotic formula")
+        # ks_2samp(method="auto") switches to the asymptotic formula above 10000 cells (_stats_py.py:8146-8180):
+        # kstwo.sf(d, round(n1 n2 / (n1 + n2))) -- only a multi-class fit's long last slice gets here.  scipy feeds
+        # it d = |ca/n - cb/n| (two rounded quotients), the table h/n: equal up to the last ulp of d, i.e. ~1e-14
+        # relative in p (the exact branch below is a function of the integer h and is bit-identical)
+        from scipy.stats import distributions
+        d = np.arange(n + 1, dtype=np.float64) / n
+        tab = np.clip(distributions.kstwo.sf(d, np.round(float(n) * float(n) / (float(n) + float(n)))), 0, 1)
+        _KS_CACHE[n] = tab
+        return tab
     tab = np.empty(n + 1, dtype=np.float64)
     tab[0] = 1.0
     for h in range(1, n + 1):

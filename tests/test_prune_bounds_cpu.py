@@ -60,3 +60,20 @@ def test_ks_table_is_non_increasing_after_a_small_h0(n):
         h0 += 1
     assert h0 <= 8, "the prune threshold h0 must stay tiny (below it every slice is evaluated exactly)"
     assert np.all(np.diff(t[h0:]) <= 0)
+
+
+def test_ks_table_above_10000_cells_follows_scipys_asymptotic_branch():
+    """ks_2samp(method='auto') is asymptotic above 10000 cells; the table reproduces it to ~1e-14 (a multi-class
+    fit's long last slice is the only caller that can get there)."""
+    import numpy as np
+    from scipy import stats
+    from phet_b200 import hostmath
+    rng = np.random.default_rng(0)
+    n = 10007
+    tab = hostmath.ks_exact_table(n)
+    assert tab.shape == (n + 1,) and tab[0] == 1.0 and np.all(np.diff(tab) <= 0)
+    for shift in (0.0, 0.01, 0.03, 0.1):
+        a, b = rng.normal(size=n), rng.normal(size=n) + shift
+        r = stats.ks_2samp(a, b)
+        h = int(round(r.statistic * n))
+        assert np.isclose(tab[h], r.pvalue, rtol=1e-12, atol=0)
