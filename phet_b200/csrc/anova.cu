@@ -15,7 +15,7 @@
 
 namespace phet {
 
-constexpr int kAnovaThreads = 512;
+constexpr int kAnovaThreads = 1024;
 
 struct AnovaArgs {
     const void *xg;
