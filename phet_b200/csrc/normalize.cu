@@ -164,12 +164,11 @@ static int run_normalize(phet_ctx *c, const Tin *X, int64_t ldx, int64_t g0, int
     int chunks = 1;
     if (normalize) {
         const int64_t gx = (G + kTile - 1) / kTile;
-        // enough blocks for ~8 per SM, chunks of at least 256 rows
-        chunks = (int)((8LL * c->num_sms + gx - 1) / gx);
-        const int64_t max_chunks = (N + 255) / 256;
-        if (chunks > max_chunks) chunks = (int)max_chunks;
-        if (chunks < 1) chunks = 1;
-        const int64_t rows_per_chunk = (N + chunks - 1) / chunks;
+        // Row chunks are a function of N ALONE: the merge order of the column sums -- and with it every bit of the
+        // mean and sd -- must not depend on how many genes are normalised together (gene blocks of the pipelined
+        // path, gene shards of a multi-GPU fit), so that any partition of the genes gives the same z-scores.
+        int64_t rows_per_chunk = 2048;
+        if ((N + rows_per_chunk - 1) / rows_per_chunk > 64) rows_per_chunk = (N + 63) / 64;
         chunks = (int)((N + rows_per_chunk - 1) / rows_per_chunk);
         if (int e = c->colpart.alloc((size_t)chunks * 2 * G)) return e;
         dim3 blk(kTile, kRowsPerBlock);
