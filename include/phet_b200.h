@@ -105,6 +105,13 @@ int phet_set_classes(phet_ctx *ctx, const int32_t *ctrl_rows, int64_t n0,
 int phet_load_matrix(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G,
                      int dtype, int normalize, int storage);
 
+/* The same for a gene range only (a rank of a gene-sharded fit): X_dev is a DEVICE pointer to element (0, g_begin)
+ * of a row-major matrix with leading dimension ldx (>= g_end - g_begin; a rank may hold just its columns).
+ * Genes [g_begin, g_end) become resident; G stays the gene count of the whole problem, so accumulators, gene
+ * numbering and the keyed Step-3 permutations are those of the unsharded fit. */
+int phet_load_matrix_genes(phet_ctx *ctx, const void *X_dev, int64_t ldx, int64_t N, int64_t G, int dtype,
+                           int normalize, int storage, int64_t g_begin, int64_t g_end);
+
 /* Copy a host matrix (row-major cells x genes, `dtype`) to HBM once, unchanged: PHET_BUF_RAW.  For callers that
  * lay the same matrix out several times with phet_load_matrix(is_device = 1) -- the multi-class fit regroups the
  * cells once per combination (phet.py:387-392) and should cross PCIe once. */

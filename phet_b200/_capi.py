@@ -27,7 +27,7 @@ EXPORTS = [
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
     "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
-    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix",
+    "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix", "phet_load_matrix_genes",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
 ]
 
@@ -116,6 +116,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mtx_stage.argtypes = [vp, vp, C.c_int, i64, C.POINTER(i64)]
     lib.phet_mtx_kept.argtypes = [vp, vp, vp]
     lib.phet_rank.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.phet_load_matrix_genes.argtypes = [vp, vp, i64, i64, i64, C.c_int, C.c_int, C.c_int, i64, i64]
     lib.phet_stage_matrix.argtypes = [vp, vp, i64, i64, C.c_int]
     lib.phet_kruskal.argtypes = [vp, vp, i64, i64, i64, dbl, C.c_int]
     lib.phet_anova.argtypes = [vp, vp, i64, i64, i64, dbl, dbl, C.c_int]
@@ -233,6 +234,13 @@ class Context:
     def load_matrix_device(self, dev_ptr: int, N: int, G: int, dtype: int, normalize=NORM_ZSCORE, storage=None):
         st = dtype if storage is None else storage
         _check(self.lib.phet_load_matrix(self.h, C.c_void_p(dev_ptr), 1, N, G, dtype, normalize, st))
+        self.N, self.G = N, G
+
+    def load_matrix_genes(self, dev_ptr: int, ldx: int, N: int, G: int, dtype: int, g_begin: int, g_end: int,
+                          normalize=NORM_ZSCORE, storage=None):
+        """Lay out genes [g_begin, g_end) only; dev_ptr addresses element (0, g_begin), leading dimension ldx."""
+        st = dtype if storage is None else storage
+        _check(self.lib.phet_load_matrix_genes(self.h, C.c_void_p(dev_ptr), ldx, N, G, dtype, normalize, st, g_begin, g_end))
         self.N, self.G = N, G
 
     def class_stats(self, q3):

@@ -510,6 +510,18 @@ int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64
     return PHET_OK;
 }
 
+int phet_load_matrix_genes(phet_ctx *c, const void *X_dev, int64_t ldx, int64_t N, int64_t G, int dtype, int normalize,
+                           int storage, int64_t g_begin, int64_t g_end) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(X_dev != nullptr, "X is NULL");
+    PHET_REQUIRE(0 <= g_begin && g_begin < g_end && g_end <= G, "gene range outside [0, G)");
+    PHET_REQUIRE(ldx >= g_end - g_begin, "leading dimension shorter than the gene range");
+    if (int e = prepare_matrix(c, N, G, dtype, normalize, storage, g_begin, g_end)) return e;
+    if (int e = launch_normalize(c, X_dev, ldx, g_begin, g_end - g_begin, dtype, normalize)) return e;
+    c->matrix_set = true;
+    return PHET_OK;
+}
+
 int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
     PHET_REQUIRE(c != nullptr, "ctx is NULL");
     PHET_REQUIRE(c->classes_set, "phet_set_classes must be called first");

@@ -105,8 +105,8 @@ def plan_and_draw(est, y, K, G):
 def fit_multiclass(est, X, y, K, staged):
     """Scores (G, 1) float64 for K >= 3 classes.  ``est``: the PHet instance (parameters in, attributes out)."""
     rank, world, dist = est._dist()
-    if dist is not None:
-        raise NotImplementedError("the multi-class branch runs on one device")
+    if dist is not None and staged is not None:
+        raise NotImplementedError("a StagedMatrix is fitted by the process that staged it (single device)")
     if est.group_test not in ("anova", "kruskal"):
         raise ValueError("group_test must be 'anova' or 'kruskal'")
     if est.multiconditions_strategy == "pairwise" and est.permutation == "device":
@@ -115,7 +115,17 @@ def fit_multiclass(est, X, y, K, staged):
     N, G = X.shape
     S = int(est.num_subsamples)
     t0 = time.perf_counter()
-    plan = plan_and_draw(est, y, K, G)
+    if dist is None or rank == 0:
+        plan = plan_and_draw(est, y, K, G)
+    if dist is not None:
+        # only rank 0's NumPy stream matters (as in the two-class path): its draws are broadcast
+        from .distributed import broadcast_numpy
+        import pickle
+        blob = np.frombuffer(pickle.dumps(plan), dtype=np.uint8) if rank == 0 else np.zeros(0, dtype=np.uint8)
+        size = int(broadcast_numpy(np.array([blob.size], dtype=np.int64), dist)[0])
+        if rank != 0:
+            blob = np.zeros(size, dtype=np.uint8)
+        plan = pickle.loads(broadcast_numpy(blob, dist).tobytes())
     members, m, min_size, n_slices, n_last = plan["members"], plan["m"], plan["min_size"], plan["n_slices"], plan["n_last"]
     idx_anova, idx_combo, perms, seed = plan["idx_anova"], plan["idx_combo"], plan["perms"], plan["seed"]
     C = len(members)
@@ -141,14 +151,28 @@ def fit_multiclass(est, X, y, K, staged):
     H = []
     try:
         ctx.set_option(_capi.OPT_KEEP_H, 1 if est.capture else 0)
-        raw_ptr = X.device_ptr if is_staged else ctx.stage_matrix(X)          # the matrix crosses PCIe once
+        # gene sharding (the capacity layout): a rank lays out, and computes, only its gene slice; gene
+        # numbering stays global, so the accumulators and the keyed permutations are those of the one-GPU fit
+        from .distributed import shard_range
+        g_lo, g_hi = shard_range(G, rank, world) if dist is not None else (0, G)
+        if g_hi <= g_lo:
+            raise ValueError("gene sharding needs at least one gene per rank")
+        if is_staged:
+            raw_ptr, ldx = X.device_ptr, G
+        elif dist is None:
+            raw_ptr, ldx = ctx.stage_matrix(X), G                            # the matrix crosses PCIe once
+        else:
+            raw_ptr, ldx = ctx.stage_matrix(np.ascontiguousarray(X[:, g_lo:g_hi])), g_hi - g_lo
         for c, (ei, ej) in enumerate(members):
             ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, 0)
             # pairwise: the cells of the other classes ride behind the second group (the layout must hold every
             # cell: the z-score is over all of them and the ANOVA draws address them); nothing ever indexes them
             rest = np.setdiff1d(np.arange(N), np.concatenate([ei, ej]))
             ctx.set_classes(ei, np.concatenate([ej, rest]) if rest.size else ej)
-            ctx.load_matrix_device(raw_ptr, N, G, dtype, norm, storage)
+            if dist is None:
+                ctx.load_matrix_device(raw_ptr, N, G, dtype, norm, storage)
+            else:
+                ctx.load_matrix_genes(raw_ptr, ldx, N, G, dtype, g_lo, g_hi, norm, storage)
             if c == 0:
                 if est.group_test == "kruskal" and m > 5:                    # phet.py:372-377
                     ctx.kruskal(idx_anova, p_flush, capture=est.capture)
@@ -161,13 +185,21 @@ def fit_multiclass(est, X, y, K, staged):
             ctx.step1(0, S, prm)
             rsum[:, c] = ctx.read(_capi.BUF_ACC, np.float64, (2, G))[1]
             ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, min_size)
-            ctx.step3(0, G, m, hostmath.ks_exact_table(m), hostmath.ks_exact_table(n_last[c]), n_last[c],
+            ctx.step3(g_lo, g_hi, m, hostmath.ks_exact_table(m), hostmath.ks_exact_table(n_last[c]), n_last[c],
                       perm_ctrl=perms[c][0] if perms is not None else None,
                       perm_case=perms[c][1] if perms is not None else None, seed=seed + c)
             o_combo[:, c] = ctx.read(_capi.BUF_O, np.float64, (G,))
             if est.capture:
                 H.append(ctx.read(_capi.BUF_H, np.int32, (G, n_slices)))
         ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, 0)
+        if dist is not None:
+            # ranks hold zeros outside their gene slice: SUM completes the vectors exactly (one small all-reduce)
+            from .distributed import allreduce_numpy
+            packed = allreduce_numpy(np.concatenate([fsum[:, None], rsum, o_combo], axis=1), dist)
+            fsum, rsum, o_combo = packed[:, 0].copy(), packed[:, 1:1 + C].copy(), packed[:, 1 + C:].copy()
+            if est.capture:
+                H = [allreduce_numpy(h, dist) for h in H]
+                est.P_ = allreduce_numpy(est.P_, dist)
         # phet.py:435-444
         r = rsum / S
         r = np.mean(r, axis=1) if agg == "mean" else np.max(r, axis=1)

@@ -19,7 +19,29 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank()
-    for name in sys.argv[1:]:
+    for name in [a for a in sys.argv[1:] if a.startswith("multi_")]:
+        # multi-class branch (K >= 3), gene-sharded: fixtures of tests/golden/make_golden_multiclass.py
+        from conftest import GOLDEN_DIR
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        for capture in (True, False):
+            np.random.seed(12345 if rank == 0 else 999 + rank)
+            est = PHet(num_subsamples=int(z["S"]), percentiles=tuple(z["percentiles"]),
+                       multiconditions_strategy=str(z["strategy"]), multiconditions_aggregation=str(z["aggregation"]),
+                       group_test=str(z["group_test"]), capture=capture, distributed=True)
+            scores = est.fit_predict(z["X"], z["y"].astype(np.int64))
+            f32 = z["X"].dtype == np.float32
+            assert np.array_equal(est.o_, z["o"]), "o differs after the all-reduce"
+            assert np.array_equal(est.bin_counts_, z["bin_counts"])
+            if capture:
+                assert np.array_equal(est.index_sets_anova_, z["idx_anova"]), "broadcast draws differ"
+                assert np.array_equal(est.o_combo_, z["o_combo"])
+                for c in range(z["H"].shape[1]):
+                    assert np.array_equal(est.H_combo_[c], z["H"][:, c, :])
+                assert np.allclose(est.fsum_, z["fsum"], rtol=1e-3 if f32 else 1e-5, atol=1e-9)
+            assert np.allclose(scores, z["scores_ref"], rtol=1e-3 if f32 else 1e-5, atol=1e-12)
+        if rank == 0:
+            print("rank0 ok", name, "world", dist.get_world_size(), flush=True)
+    for name in [a for a in sys.argv[1:] if not a.startswith("multi_")]:
         g = load_golden(name)
         X = np.ascontiguousarray(g["X"].astype(np.float64))
         ref = g["scores_f64"]
