@@ -15,12 +15,16 @@
 // order-preserving key of every element.  Every thread counts the digits of its elements in private
 // 16-bit counters (6 tracks x 16 digits, words interleaved by lane: bank == lane, conflict-free, no
 // atomics, deterministic); the CTA reduces them (REDUX + one SMEM hop) and one thread per track fixes the
-// next digit.  Three passes over the row fix 12 bits (sign, exponent, 3 mantissa bits); a fourth pass
-// compacts the few per cent of the elements that share those bits with a track into a shared-memory list
-// per track (warp-aggregated appends), and the remaining digits and y[j+1] (the smallest value above y[j],
-// or y[j] itself when its tie group reaches rank j+1) come from the lists.  A list that overflows (a tie
-// group of thousands of equal values) sends the gene back to passes over the whole row: always exact.
-// Moments ride on the first pass in fp64 (deviations from the first cell of the class), fixed-order sums.
+// next digit (the general path, 8 / 16 passes: always exact).  The fast path reads the row twice: pass A drops every
+// cell into one of 256 value buckets (a linear map of the range of a 2 x 512 cell sample -- the cells of a class sit
+// in a fixed pseudo-random order, so the first 512 are a random sample -- shared-memory atomics, two histograms) and
+// gathers the moments in fp64 (deviations from the first cell of the class, fixed-order sums); the bucket holding
+// each of the six ranks follows from the histograms; pass B compacts the cells of those buckets (about 1 % of the
+// vector each) into a shared-memory list per track (warp-aggregated appends), and the order statistic y[j] and
+// y[j+1] (the smallest value above y[j], or y[j] itself when its tie group reaches rank j+1) come from the lists
+// by radix select, one warp per track.  The bucket map is monotone in the value, so buckets partition the order
+// statistics exactly; a list that overflows (a tie group of thousands of equal values, a heavy-tailed gene whose
+// sample range is huge) sends the gene to the general path.
 #include "common.cuh"
 #include "warp_prims.cuh"
 
@@ -88,7 +92,7 @@ __device__ __forceinline__ double cs_block_sum(double v, double *red, int tid) {
 
 template <typename T> struct CsList { static constexpr int cap = 4096; };   // keys per track kept in shared memory
 template <> struct CsList<double> { static constexpr int cap = 2048; };
-constexpr int kCsFullPasses = 3;   // digits fixed by passes over the whole row before the candidates are compacted
+constexpr int kCsBuckets = 256;    // value buckets of the first pass (a linear map of the range of a 2 x 512 cell sample)
 
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsArgs a) {
@@ -105,12 +109,16 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
     __shared__ K kmin[kCsTracks];                   // smallest key above y[j]
     __shared__ K nmin[kCsTracks];                   // smallest key of the vector above the candidates' 12-bit bucket
     __shared__ int llen[kCsTracks];                 // candidates appended (may exceed LCAP: overflow -> full passes)
+    __shared__ unsigned int hist[2][kCsBuckets + 2];   // per class: cells per value bucket (below, 0 .. kCsBuckets-1, above)
+    __shared__ int bsel[kCsTracks];                 // bucket (index into hist) that holds the track's rank
+    __shared__ double bmap[2];                      // bucket = floor((v - bmap[0]) * bmap[1])
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *mine = cnt + (size_t)warp * (kCsTracks * 8 * 32) + lane;   // word w of this thread at mine[32 * w]
     const int64_t n0 = a.n0, n = a.n0 + a.n1;
     const int64_t nvec[3] = {a.n0, a.n1, n};
 
     for (int w = 0; w < kCsTracks * 8; ++w) mine[32 * w] = 0u;
+    for (int i = tid; i < 2 * (kCsBuckets + 2); i += kCsThreads) (&hist[0][0])[i] = 0u;
 
     for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
         const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
@@ -154,6 +162,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
         // first cell of each class, fp64: exact zero variance for a constant vector, no cancellation trouble)
         const double K0 = (double)__ldg(row), K1 = (double)__ldg(row + n0);
         double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
+        auto bucket_of = [&](double dv) {   // monotone non-decreasing in the value: buckets partition the order statistics
+            double tb = floor((dv - bmap[0]) * bmap[1]);
+            tb = fmin(fmax(tb, -1.0), (double)kCsBuckets);
+            return (int)tb + 1;
+        };
         auto full_pass = [&](int pass) {
             const int shift = CsKey<T>::bits - 4 * (pass + 1);
             K pf[kCsTracks];
@@ -166,8 +179,6 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 const uint32_t dig = (uint32_t)(key >> shift) & 15u;
                 const int c = (i < n0) ? 0 : 1;
                 if (pass == 0) {
-                    const double d = (double)v - (c ? K1 : K0);
-                    if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
                     // nothing is fixed yet: the low and the high track of a vector see the same digits
                     const uint32_t inc = (dig & 1u) ? 0x10000u : 1u;
                     mine[32 * ((2 * c) * 8 + (dig >> 1))] += inc;
@@ -191,8 +202,60 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
             pick_digit(shift);
         };
 
-        int next_pass = 0;
-        for (; next_pass < kCsFullPasses && next_pass < NPASS; ++next_pass) full_pass(next_pass);
+        // ---- pass A: value buckets.  The cells of a class sit in a fixed pseudo-random order (phet_set_classes), so
+        //      the first 512 of each class are a random sample: its range, cut into kCsBuckets equal parts, is the map.
+        {
+            double mn_s = CUDART_INF, mx_s = -CUDART_INF;
+            if (tid < n0) { const double v = (double)__ldg(row + tid); mn_s = fmin(mn_s, v); mx_s = fmax(mx_s, v); }
+            if (tid < a.n1) { const double v = (double)__ldg(row + n0 + tid); mn_s = fmin(mn_s, v); mx_s = fmax(mx_s, v); }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                mn_s = fmin(mn_s, __shfl_xor_sync(kFull, mn_s, o));
+                mx_s = fmax(mx_s, __shfl_xor_sync(kFull, mx_s, o));
+            }
+            __syncthreads();
+            if (lane == 0) {
+                red[warp] = mn_s;
+                wpart[warp][0] = __double2hiint(mx_s);
+                wpart[warp][1] = __double2loint(mx_s);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double lo = CUDART_INF, hi = -CUDART_INF;
+                for (int w = 0; w < kCsThreads / 32; ++w) {
+                    lo = fmin(lo, red[w]);
+                    hi = fmax(hi, __hiloint2double((int)wpart[w][0], (int)wpart[w][1]));
+                }
+                bmap[0] = lo;
+                bmap[1] = (hi > lo) ? (double)kCsBuckets / (hi - lo) : 0.0;
+                if (!isfinite(bmap[1])) bmap[1] = 0.0;
+            }
+            __syncthreads();
+        }
+#pragma unroll 4
+        for (int64_t i = tid; i < n; i += kCsThreads) {
+            const double dv = (double)__ldg(row + i);
+            const int c = (i < n0) ? 0 : 1;
+            const double d = dv - (c ? K1 : K0);
+            if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
+            atomicAdd(&hist[c][bucket_of(dv)], 1u);
+        }
+        __syncthreads();
+        if (tid < kCsTracks) {   // the bucket that holds rank j of the track, and the rank inside it
+            const int vt = tid >> 1;
+            int64_t r = rank[tid], cum = 0;
+            int b = 0;
+            for (; b < kCsBuckets + 2; ++b) {
+                const int64_t cb = (vt == 0) ? hist[0][b] : (vt == 1) ? hist[1][b] : (int64_t)hist[0][b] + hist[1][b];
+                if (cum + cb > r || b == kCsBuckets + 1) break;
+                cum += cb;
+            }
+            bsel[tid] = b;
+            rank[tid] = r - cum;
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * (kCsBuckets + 2); i += kCsThreads) (&hist[0][0])[i] = 0u;   // for the next gene
+        const int next_pass = 0;   // the lists resolve every digit
         const double sum0 = cs_block_sum(s0, red, tid), sum1 = cs_block_sum(s1, red, tid);
         const double sq0 = cs_block_sum(d0, red, tid), sq1 = cs_block_sum(d1, red, tid);
         const double mean0 = K0 + sum0 / (double)a.n0, mean1 = K1 + sum1 / (double)a.n1;
@@ -200,21 +263,22 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
         if (ss0 < 0.0) ss0 = 0.0;
         if (ss1 < 0.0) ss1 = 0.0;
 
-        // ---- compaction: the elements that share a track's leading 12 bits go to the track's list
+        // ---- pass B, compaction: the cells of a track's bucket go to the track's list
         {
-            constexpr int shiftc = CsKey<T>::bits - 4 * kCsFullPasses;
-            K pf[kCsTracks], nm[kCsTracks];
+            int pf[kCsTracks];
+            K nm[kCsTracks];
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) {
-                pf[t] = prefix[t] >> shiftc;
+                pf[t] = bsel[t];
                 nm[t] = ~K(0);
             }
 #pragma unroll 2
             for (int64_t b = 0; b < n; b += kCsThreads) {   // warp-uniform trip count (ballots inside)
                 const int64_t i = b + tid;
                 const bool valid = i < n;
-                const K key = valid ? CsKey<T>::of(__ldg(row + i)) : K(0);
-                const K kp = key >> shiftc;
+                const T v = valid ? __ldg(row + i) : T(0);
+                const K key = CsKey<T>::of(v);
+                const int kp = bucket_of((double)v);
                 const int c = (i < n0) ? 0 : 1;
 #pragma unroll
                 for (int t = 0; t < kCsTracks; ++t) {
@@ -272,11 +336,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 int64_t r = rank[t];
                 for (int pass = next_pass; pass < NPASS; ++pass) {
                     const int shift = CsKey<T>::bits - 4 * (pass + 1);
-                    const K want = pk >> (shift + 4);
+                    const K fixed = (pass == 0) ? K(0) : (~K(0) << (shift + 4));   // digits already chosen
                     for (int e = lane; e < len; e += 32) {
                         const K key = lt[e];
                         const uint32_t dig = (uint32_t)(key >> shift) & 15u;
-                        if ((key >> (shift + 4)) == want) mine[32 * (dig >> 1)] += (dig & 1u) ? 0x10000u : 1u;
+                        if (((key ^ pk) & fixed) == 0) mine[32 * (dig >> 1)] += (dig & 1u) ? 0x10000u : 1u;
                     }
                     int64_t cum = 0;
                     int d = 0;
@@ -315,8 +379,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 if (lane == 0) prefix[t] = pk;
             }
         } else {
-            // ---- a tie group (or a very dense bucket) larger than the list: keep passing over the whole row
-            for (int pass = next_pass; pass < NPASS; ++pass) full_pass(pass);
+            // ---- a tie group (or a very dense bucket) larger than the list: exact radix select over the whole row,
+            //      4 bits per pass, from the original ranks
+            if (tid < kCsTracks) {
+                prefix[tid] = 0;
+                const phet_quantile_pos &q = a.q[tid >> 1];
+                rank[tid] = (tid & 1) ? q.j_hi : q.j_lo;
+            }
+            __syncthreads();
+            for (int pass = 0; pass < NPASS; ++pass) full_pass(pass);
             K pf[kCsTracks];
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
