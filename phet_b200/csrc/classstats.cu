@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
     __shared__ int llen[kCsTracks];                 // candidates appended (may exceed LCAP: overflow -> full passes)
     __shared__ unsigned int hist[2][kCsBuckets + 2];   // per class: cells per value bucket (below, 0 .. kCsBuckets-1, above)
     __shared__ int bsel[kCsTracks];                 // bucket (index into hist) that holds the track's rank
-    __shared__ double bmap[2];                      // bucket = floor((v - bmap[0]) * bmap[1])
+    __shared__ T bmap[2];                           // bucket = floor((v - bmap[0]) * bmap[1]), in the storage type
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *mine = cnt + (size_t)warp * (kCsTracks * 8 * 32) + lane;   // word w of this thread at mine[32 * w]
     const int64_t n0 = a.n0, n = a.n0 + a.n1;
@@ -162,9 +162,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
         // first cell of each class, fp64: exact zero variance for a constant vector, no cancellation trouble)
         const double K0 = (double)__ldg(row), K1 = (double)__ldg(row + n0);
         double s0 = 0.0, s1 = 0.0, d0 = 0.0, d1 = 0.0;
-        auto bucket_of = [&](double dv) {   // monotone non-decreasing in the value: buckets partition the order statistics
-            double tb = floor((dv - bmap[0]) * bmap[1]);
-            tb = fmin(fmax(tb, -1.0), (double)kCsBuckets);
+        auto bucket_of = [&](T v) {   // monotone non-decreasing in the value: buckets partition the order statistics
+            T tb = floor((v - bmap[0]) * bmap[1]);   // (each rounding step is monotone)
+            tb = tmin(tmax(tb, T(-1)), T(kCsBuckets));
             return (int)tb + 1;
         };
         auto full_pass = [&](int pass) {
@@ -226,32 +226,57 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                     lo = fmin(lo, red[w]);
                     hi = fmax(hi, __hiloint2double((int)wpart[w][0], (int)wpart[w][1]));
                 }
-                bmap[0] = lo;
-                bmap[1] = (hi > lo) ? (double)kCsBuckets / (hi - lo) : 0.0;
-                if (!isfinite(bmap[1])) bmap[1] = 0.0;
+                const T scale = (hi > lo) ? (T)((double)kCsBuckets / (hi - lo)) : T(0);
+                bmap[0] = (T)lo;
+                bmap[1] = isfinite(scale) ? scale : T(0);
             }
             __syncthreads();
         }
 #pragma unroll 4
         for (int64_t i = tid; i < n; i += kCsThreads) {
-            const double dv = (double)__ldg(row + i);
+            const T v = __ldg(row + i);
             const int c = (i < n0) ? 0 : 1;
-            const double d = dv - (c ? K1 : K0);
+            const double d = (double)v - (c ? K1 : K0);
             if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
-            atomicAdd(&hist[c][bucket_of(dv)], 1u);
+            atomicAdd(&hist[c][bucket_of(v)], 1u);
         }
         __syncthreads();
-        if (tid < kCsTracks) {   // the bucket that holds rank j of the track, and the rank inside it
-            const int vt = tid >> 1;
-            int64_t r = rank[tid], cum = 0;
-            int b = 0;
-            for (; b < kCsBuckets + 2; ++b) {
-                const int64_t cb = (vt == 0) ? hist[0][b] : (vt == 1) ? hist[1][b] : (int64_t)hist[0][b] + hist[1][b];
-                if (cum + cb > r || b == kCsBuckets + 1) break;
-                cum += cb;
+        if (warp < kCsTracks) {   // one warp per track: the bucket that holds rank j, and the rank inside it
+            constexpr int PER = (kCsBuckets + 2 + 31) / 32;
+            const int vt = warp >> 1;
+            const int64_t r = rank[warp];
+            unsigned int cb[PER];
+            unsigned int local = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int b = lane * PER + q;
+                unsigned int x = 0;
+                if (b < kCsBuckets + 2) x = (vt == 0) ? hist[0][b] : (vt == 1) ? hist[1][b] : hist[0][b] + hist[1][b];
+                cb[q] = x;
+                local += x;
             }
-            bsel[tid] = b;
-            rank[tid] = r - cum;
+            unsigned int incl = local;   // inclusive scan over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int64_t before = (int64_t)incl - local;
+            const bool mine_has = before <= r && r < (int64_t)incl;
+            const unsigned owner = __ballot_sync(kFull, mine_has);
+            if (owner == 0u) {   // r beyond the vector (cannot happen for validated positions): last bucket
+                if (lane == 0) { bsel[warp] = kCsBuckets + 1; rank[warp] = 0; }
+            } else if (mine_has) {
+                int64_t cum = before;
+                int q = 0;
+#pragma unroll
+                for (; q < PER - 1; ++q) {
+                    if (cum + cb[q] > r) break;
+                    cum += cb[q];
+                }
+                bsel[warp] = lane * PER + q;
+                rank[warp] = r - cum;
+            }
         }
         __syncthreads();
         for (int i = tid; i < 2 * (kCsBuckets + 2); i += kCsThreads) (&hist[0][0])[i] = 0u;   // for the next gene
@@ -278,7 +303,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 const bool valid = i < n;
                 const T v = valid ? __ldg(row + i) : T(0);
                 const K key = CsKey<T>::of(v);
-                const int kp = bucket_of((double)v);
+                const int kp = bucket_of(v);
                 const int c = (i < n0) ? 0 : 1;
 #pragma unroll
                 for (int t = 0; t < kCsTracks; ++t) {
