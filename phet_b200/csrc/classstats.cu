@@ -71,6 +71,20 @@ __device__ __forceinline__ double cs_iqr(double yjl, double ykl, double yjh, dou
     return __dsub_rn(qh, ql);
 }
 
+// 16-byte loads of the row: four times (float) / twice (double) the bytes in flight per thread -- the two reads of
+// the row are bound by L2 / HBM latency at one CTA of 512 threads per SM, not by bandwidth
+template <typename T> struct CsVec;
+template <> struct CsVec<float> {
+    typedef float4 type;
+    static constexpr int width = 4;
+    static __device__ __forceinline__ void get(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct CsVec<double> {
+    typedef double2 type;
+    static constexpr int width = 2;
+    static __device__ __forceinline__ void get(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+};
+
 struct ClassStatsArgs {
     const void *xg;
     int64_t n_pad, xg_g0, g_begin, g_end, n0, n1;
@@ -232,13 +246,24 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
             }
             __syncthreads();
         }
-#pragma unroll 4
-        for (int64_t i = tid; i < n; i += kCsThreads) {
-            const T v = __ldg(row + i);
-            const int c = (i < n0) ? 0 : 1;
-            const double d = (double)v - (c ? K1 : K0);
-            if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
-            atomicAdd(&hist[c][bucket_of(v)], 1u);
+        constexpr int VW = CsVec<T>::width;
+        const typename CsVec<T>::type *rowv = reinterpret_cast<const typename CsVec<T>::type *>(row);   // rows are 16-byte aligned, n_pad covers the tail
+        const int64_t nvec16 = (n + VW - 1) / VW;
+#pragma unroll 2
+        for (int64_t iv = tid; iv < nvec16; iv += kCsThreads) {
+            T e[VW];
+            CsVec<T>::get(__ldg(rowv + iv), e);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) {
+                const int64_t i = iv * VW + k;
+                if (i < n) {
+                    const T v = e[k];
+                    const int c = (i < n0) ? 0 : 1;
+                    const double d = (double)v - (c ? K1 : K0);
+                    if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
+                    atomicAdd(&hist[c][bucket_of(v)], 1u);
+                }
+            }
         }
         __syncthreads();
         if (warp < kCsTracks) {   // one warp per track: the bucket that holds rank j, and the rank inside it
@@ -297,26 +322,33 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 pf[t] = bsel[t];
                 nm[t] = ~K(0);
             }
-#pragma unroll 2
-            for (int64_t b = 0; b < n; b += kCsThreads) {   // warp-uniform trip count (ballots inside)
-                const int64_t i = b + tid;
-                const bool valid = i < n;
-                const T v = valid ? __ldg(row + i) : T(0);
-                const K key = CsKey<T>::of(v);
-                const int kp = bucket_of(v);
-                const int c = (i < n0) ? 0 : 1;
+            for (int64_t bv = 0; bv < nvec16; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
+                const int64_t iv = bv + tid;
+                T e[VW];
 #pragma unroll
-                for (int t = 0; t < kCsTracks; ++t) {
-                    const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
-                    const bool match = member && kp == pf[t];
-                    if (member && kp > pf[t] && key < nm[t]) nm[t] = key;
-                    const unsigned mask = __ballot_sync(kFull, match);
-                    if (mask) {
-                        int base = 0;
-                        if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(&llen[t], __popc(mask));
-                        base = __shfl_sync(kFull, base, __ffs((int)mask) - 1);
-                        const int pos = base + __popc(mask & ((1u << lane) - 1u));
-                        if (match && pos < LCAP) lists[t * LCAP + pos] = key;
+                for (int k = 0; k < VW; ++k) e[k] = T(0);
+                if (iv < nvec16) CsVec<T>::get(__ldg(rowv + iv), e);
+#pragma unroll
+                for (int k = 0; k < VW; ++k) {
+                    const int64_t i = iv * VW + k;
+                    const bool valid = iv < nvec16 && i < n;
+                    const T v = e[k];
+                    const K key = CsKey<T>::of(v);
+                    const int kp = bucket_of(v);
+                    const int c = (i < n0) ? 0 : 1;
+#pragma unroll
+                    for (int t = 0; t < kCsTracks; ++t) {
+                        const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
+                        const bool match = member && kp == pf[t];
+                        if (member && kp > pf[t] && key < nm[t]) nm[t] = key;
+                        const unsigned mask = __ballot_sync(kFull, match);
+                        if (mask) {
+                            int base = 0;
+                            if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(&llen[t], __popc(mask));
+                            base = __shfl_sync(kFull, base, __ffs((int)mask) - 1);
+                            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                            if (match && pos < LCAP) lists[t * LCAP + pos] = key;
+                        }
                     }
                 }
             }
