@@ -187,3 +187,37 @@ def test_cli_native_loader_and_device_ranking_equal_host_path(tmp_path):
     a = open(tmp_path / "a" / "counts_phet_br_features.csv").read()
     b = open(tmp_path / "b" / "counts_phet_br_features.csv").read()
     assert a == b and len(a.splitlines()) > 2
+
+
+def test_new_entry_points_fail_loudly(tmp_path):
+    """Misuse of the 8(f) entry points is an error with a message, never a silent wrong answer."""
+    import ctypes as C
+    from phet_b200 import _capi
+    ctx = _capi.Context(0)
+    try:
+        with pytest.raises(_capi.PhetError, match="no scores"):
+            ctx.rank()                                           # nothing resident yet
+        s = np.arange(10, dtype=np.float64)
+        with pytest.raises(_capi.PhetError, match="k <= G"):
+            ctx.rank(s, k=11)
+        with pytest.raises(_capi.PhetError, match="no staged matrix|buffer has not been produced"):
+            ctx.read(_capi.BUF_STAGED, np.float32, (1,))
+        y = np.repeat(np.arange(3), 20)
+        X = np.random.default_rng(0).normal(size=(60, 5))
+        with pytest.raises(_capi.PhetError, match="load the classes and the matrix"):
+            ctx.anova(np.zeros((4, 3, 6), dtype=np.int32), 0.0)
+        ctx.set_classes(np.where(y == 0)[0], np.where(y != 0)[0])
+        ctx.load_matrix(X)
+        bad = np.zeros((4, 3, 6), dtype=np.int32)
+        bad[1, 2, 3] = 60                                        # row outside [0, N)
+        with pytest.raises(_capi.PhetError, match="outside"):
+            ctx.anova(bad, 0.0)
+        with pytest.raises(_capi.PhetError, match="at most 64 groups"):
+            ctx.kruskal(np.zeros((2, 65, 2), dtype=np.int32))
+        ptr = ctx.stage_matrix(np.ascontiguousarray(X))
+        with pytest.raises(_capi.PhetError, match="gene range"):
+            ctx.load_matrix_genes(ptr, 5, 60, 5, _capi.PHET_F64, 3, 9)
+        with pytest.raises(_capi.PhetError, match="STEP3_MIN_SIZE"):
+            ctx.set_option(_capi.OPT_STEP3_MIN_SIZE, -1)
+    finally:
+        ctx.close()
