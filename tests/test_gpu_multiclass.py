@@ -119,3 +119,37 @@ def test_anova_constant_groups_and_large_statistics():
         t = -2 * np.log(want)
     t[t == np.inf] = 0
     assert np.allclose(fsum, t.sum(1), rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("N", [50000, 120000])   # 200 KB vector staged in shared memory / gathered from L2
+def test_group_tests_on_long_cell_vectors(N):
+    """phet_anova / phet_kruskal at BASELINE-sized cell counts against scipy on every gene (float32 input: rtol 1e-3)."""
+    from scipy import stats
+    import math
+    from phet_b200 import _capi
+    rng = np.random.default_rng(N)
+    K, G, S = 3, 48, 40
+    y = (np.arange(N) * K // N).astype(np.int64)
+    X = rng.gamma(2.0, 1.0, (N, G)).astype(np.float32)
+    X[y == 2, :8] += 0.4
+    m = int(np.sqrt(min(np.bincount(y))))
+    idx = np.empty((S, K, m), dtype=np.int32)
+    for s in range(S):
+        for c in range(K):
+            idx[s, c] = rng.choice(np.where(y == c)[0], m, replace=False)
+    ctx = _capi.Context(0)
+    try:
+        ctx.set_classes(np.where(y == 0)[0], np.where(y != 0)[0])
+        ctx.load_matrix(X, _capi.NORM_ZSCORE)
+        a, b = 0.5 * (K * m - K), 0.5 * (K - 1)
+        ctx.anova(idx, math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b), 2.0 ** -150, capture=True)
+        Pa = ctx.read(_capi.BUF_P, np.float64, (G, S))
+        ctx.kruskal(idx, 2.0 ** -150, capture=True)
+        Pk = ctx.read(_capi.BUF_P, np.float64, (G, S))
+    finally:
+        ctx.close()
+    Xz = stats.zscore(X.astype(np.float64), axis=0)
+    for s in range(S):
+        groups = [Xz[idx[s, c]] for c in range(K)]
+        assert np.allclose(Pa[:, s], stats.f_oneway(*groups)[1], rtol=1e-3, atol=1e-300)
+        assert np.allclose(Pk[:, s], stats.kruskal(*groups)[1], rtol=1e-3, atol=1e-300)
