@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
         constexpr int VW = CsVec<T>::width;
         const typename CsVec<T>::type *rowv = reinterpret_cast<const typename CsVec<T>::type *>(row);   // rows are 16-byte aligned, n_pad covers the tail
         const int64_t nvec16 = (n + VW - 1) / VW;
-#pragma unroll 2
+#pragma unroll 4
         for (int64_t iv = tid; iv < nvec16; iv += kCsThreads) {
             T e[VW];
             CsVec<T>::get(__ldg(rowv + iv), e);
@@ -322,12 +322,13 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 pf[t] = bsel[t];
                 nm[t] = ~K(0);
             }
+            typename CsVec<T>::type nxt = {};   // the next trip's cells are in flight while this trip's are compacted
+            if (tid < nvec16) nxt = __ldg(rowv + tid);
             for (int64_t bv = 0; bv < nvec16; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
                 const int64_t iv = bv + tid;
                 T e[VW];
-#pragma unroll
-                for (int k = 0; k < VW; ++k) e[k] = T(0);
-                if (iv < nvec16) CsVec<T>::get(__ldg(rowv + iv), e);
+                CsVec<T>::get(nxt, e);
+                if (iv + kCsThreads < nvec16) nxt = __ldg(rowv + iv + kCsThreads);
 #pragma unroll
                 for (int k = 0; k < VW; ++k) {
                     const int64_t i = iv * VW + k;
