@@ -290,6 +290,39 @@ int phet_fit_host(phet_ctx *ctx, const void *X, int dtype, int64_t N, int64_t G,
                   const uint32_t *perm_case, const phet_fit_params *prm,
                   double *scores_out, int64_t *bin_counts_out);
 
+/* ---- Replay of NumPy's legacy global RNG (csrc/mt_replay.cpp; host code, no GPU needed) -------------------------
+ * The reference draws from the process-global np.random stream (MT19937, seeded once at src/train.py:26):
+ * np.random.choice(rows, m, replace) twice per subsample (phet.py:401-402), then np.random.permutation of both
+ * class columns per gene (phet.py:486-487).  A phet_mt holds that stream natively: created from
+ * np.random.get_state()[1:3] (key[624], pos), advanced by the calls below exactly as NumPy would advance it, and
+ * read back with phet_mt_state for np.random.set_state.
+ *
+ * np.random.permutation(n) is `x = arange(n); for i = n-1 .. 1: j = rk_interval(i); swap(x[i], x[j])` where
+ * rk_interval(i) is the first stream value, masked to the bits of i, that is <= i.  phet_mt_shuffle_rounds emits the
+ * swap targets only (the sequential part, vectorised); applying them is independent per permutation and is done on
+ * the device (phet_draw_index_sets, PHET_PERM_REPLAY) or by phet_host_fisher_yates. */
+typedef struct phet_mt phet_mt;
+int phet_mt_create(const uint32_t *key624, int32_t pos, phet_mt **out);
+int phet_mt_state(const phet_mt *mt, uint32_t *key624_out, int32_t *pos_out);
+int phet_mt_destroy(phet_mt *mt);
+/* 512 when the AVX-512 scan is in use, 0 for the scalar one (mt may be NULL: what a new generator would use). */
+int phet_mt_simd(const phet_mt *mt);
+/* One job = one np.random.permutation(n) per round: its n - 1 swap targets, in draw order (t = 0 .. n-2 is the
+ * target of position i = n - 1 - t), are written to (char *)out + round * stride_bytes as 2-byte (n <= 65536) or
+ * 4-byte integers; out == NULL consumes the stream without storing (genes another rank owns).  Rounds are the
+ * outer loop, jobs the inner one -- {n0, n1} x S rounds is phet.py:397-402, {n0, n1} x G rounds is phet.py:484-487. */
+typedef struct {
+    int64_t n;
+    void *out;
+    int64_t stride_bytes;
+    int32_t elem_bytes;
+} phet_mt_job;
+int phet_mt_shuffle_rounds(phet_mt *mt, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds);
+/* count draws of rk_interval(max): what np.random.randint(0, max + 1, count) consumes (choice(..., replace=True)). */
+int phet_mt_bounded(phet_mt *mt, uint32_t max, int64_t count, uint32_t *out);
+/* The first `take` entries of the permutation of arange(n) that the draws produce (host; tests, small problems). */
+int phet_host_fisher_yates(const void *draws, int32_t elem_bytes, int64_t n, int64_t take, uint32_t *out);
+
 /* Testing hooks: host evaluations of the exact device routines (same source file) so the
  * CPU test-suite can check them without a GPU. */
 double phet_host_p_two_sided_t(double t, double df, double ln_beta);

@@ -19,7 +19,9 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libphet_b200.so")
 STAMP = LIB + ".stamp"
 SOURCES = ["api.cu", "normalize.cu", "finalize.cu", "classstats.cu", "rank.cu", "mtx.cu", "anova.cu", "step3big.cu", "step1_f32.cu", "step1_f64.cu", "step3_f32.cu", "step3_f64.cu",
-           "step3p_f32.cu", "step3p_f64.cu"]
+           "step3p_f32.cu", "step3p_f64.cu", "mt_replay.cpp"]
+# host-only sources go through g++ directly (AVX-512 intrinsics behind target attributes + a runtime CPU check)
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-fno-math-errno"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", 
               "--expt-relaxed-constexpr"] + os.environ.get("PHET_NVCC_EXTRA", "").split()
@@ -40,7 +42,7 @@ def _source_hash():
         for f in sorted(os.listdir(root)):
             with open(os.path.join(root, f), "rb") as fh:
                 h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    h.update(" ".join(NVCC_FLAGS + CXX_FLAGS + SOURCES).encode())
     return h.hexdigest()
 
 
@@ -67,7 +69,7 @@ def _deps(path, seen=None):
 
 def _object_hash(src):
     import hashlib
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    h = hashlib.sha256(" ".join(CXX_FLAGS if src.endswith(".cpp") else NVCC_FLAGS).encode())
     for f in sorted(_deps(os.path.join(CSRC, src))):
         with open(f, "rb") as fh:
             h.update(os.path.basename(f).encode() + b"\0" + fh.read())
@@ -75,18 +77,21 @@ def _object_hash(src):
 
 
 def _compile(src, verbose):
-    obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+    obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
     stamp = obj + ".stamp"
     want = _object_hash(src)
     if not verbose and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == want:
         return obj, ""   # this object's source and headers are unchanged
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
-    if verbose:
+    if src.endswith(".cpp"):
+        cmd = [shutil.which("g++") or "g++", *CXX_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    else:
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    if verbose and not src.endswith(".cpp"):
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        raise RuntimeError("compile failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
     with open(stamp, "w") as fh:
         fh.write(want)
     return obj, r.stderr

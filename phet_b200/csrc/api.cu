@@ -541,7 +541,9 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
     PHET_CUDA(cudaStreamSynchronize(c->stream));
     PHET_REQUIRE(hbad == 0, "index sets contain a row number outside [0, N)");
     c->idxT_ok = false;
-    if (c->n0 <= 65536 && c->n1 <= 65536 && m <= 255) {  // transposed 16-bit copy for the pair-per-thread Step 1
+    // 16-bit table: class-local positions must stay BELOW 0xFFFF, the "row not served yet" marker of k_build_idxT
+    // (a 65,536-cell class has a legal position 65,535 and goes to the 32-bit table instead)
+    if (c->n0 <= 65535 && c->n1 <= 65535 && m <= 255) {  // transposed 16-bit copy for the pair-per-thread Step 1
         const int64_t nblk = (S + 31) / 32;
         const int64_t mp = (m + 15) / 16 * 16;
         const int64_t nT = 2 * nblk * mp * 32;
@@ -965,7 +967,7 @@ static int buffer_info(phet_ctx *c, int which, void **p, int64_t *bytes) {
         case PHET_BUF_R: *p = c->r.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_BINS: *p = c->bins.p; *bytes = c->G; break;
         case PHET_BUF_SCORES: *p = c->scores.p; *bytes = (int64_t)sizeof(double) * c->G; break;
-        case PHET_BUF_XG: *p = c->xg.p; *bytes = c->G * c->n_pad * (c->storage == PHET_F32 ? 4 : 8); break;
+        case PHET_BUF_XG: *p = c->xg.p; *bytes = c->xg_rows * c->n_pad * (c->storage == PHET_F32 ? 4 : 8); break;  // row 0 = gene xg_g0
         case PHET_BUF_MEAN: *p = c->mean.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_STD: *p = c->sd.p; *bytes = (int64_t)sizeof(double) * c->G; break;
         case PHET_BUF_ROWS: *p = c->rows_grouped.p; *bytes = (int64_t)sizeof(int32_t) * (c->n0 + c->n1); break;

@@ -1,0 +1,430 @@
+// Native replay of NumPy's legacy global RNG (RandomState: MT19937 + masked rejection) for the draws PHet makes:
+//
+//   phet.py:401-402   np.random.choice(rows, m, replace=False)  ==  rows[np.random.permutation(len(rows))[:m]]
+//                     np.random.choice(rows, m, replace=True)   ==  rows[np.random.randint(0, len(rows), m)]
+//   phet.py:486-487   np.random.permutation(column)             ==  column[np.random.permutation(len(column))]
+//
+// (equivalences and identical state advance: SURVEY.md section 8c, tests/test_mt_replay_cpu.py).  The reference
+// replays 2 S + 2 G whole-class shuffles per fit -- 1.5e9 accepted draws at BASELINE config 4 -- and a Python
+// loop over np.random.permutation needs 25.7 s for them.  Here the work is split in two:
+//
+//   (1) the DRAWS: np.random.permutation(n) is `for i = n-1 .. 1: j = rk_interval(i); swap(x[i], x[j])` with
+//       rk_interval(i) = first value of the stream (masked to the bits of i) that is <= i.  Which raw outputs are
+//       accepted depends on the running i, so this part is sequential -- but it is pure streaming: generate
+//       tempered MT19937 outputs, mask, compare, compact the accepted ones.  It is vectorised 64 outputs at a
+//       time (AVX-512): a value <= i - k at lane k is accepted whatever the earlier lanes did, a value > i is
+//       rejected whatever they did, and anything in between (probability ~ 64^2 / 2i) drops to an exact
+//       16-wide / scalar step.  Output: the swap targets j, 16 bits each when n <= 65536.
+//   (2) the SWAPS: random access, but independent across permutations -- applied on the GPU (csrc/fy_apply.cu)
+//       from the uploaded j streams, or by phet_host_fisher_yates for tests and small problems.
+//
+// The state goes in and out in np.random.get_state() / set_state() form (key[624], pos), so the caller's global
+// stream continues exactly where the reference's would.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define PHET_X86 1
+#else
+#define PHET_X86 0
+#endif
+
+#include "../../include/phet_b200.h"
+
+namespace phet {
+void set_error(const std::string &msg);
+}
+
+namespace {
+
+constexpr int kN = 624, kM = 397;
+constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
+constexpr int kCarry = 64;  // outputs of the previous block kept in front of the current one
+
+inline uint32_t temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+inline uint32_t twist1(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & kUpper) | (b & kLower);
+    return (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
+}
+
+void twist_scalar(uint32_t *key) {
+    int i = 0;
+    for (; i < kN - kM; ++i) key[i] = key[i + kM] ^ twist1(key[i], key[i + 1]);
+    for (; i < kN - 1; ++i) key[i] = key[i + (kM - kN)] ^ twist1(key[i], key[i + 1]);
+    key[kN - 1] = key[kM - 1] ^ twist1(key[kN - 1], key[0]);
+}
+
+void temper_scalar(const uint32_t *key, uint32_t *out) {
+    for (int i = 0; i < kN; ++i) out[i] = temper(key[i]);
+}
+
+inline uint32_t bitmask(uint32_t v) {  // smallest 2^k - 1 >= v  (numpy: random_interval / gen_mask)
+    v |= v >> 1;
+    v |= v >> 2;
+    v |= v >> 4;
+    v |= v >> 8;
+    v |= v >> 16;
+    return v;
+}
+
+#if PHET_X86
+__attribute__((target("avx512f,avx512bw,avx512vl"))) inline __m512i twist16(__m512i a, __m512i b) {
+    const __m512i y = _mm512_or_si512(_mm512_and_si512(a, _mm512_set1_epi32((int)kUpper)),
+                                      _mm512_and_si512(b, _mm512_set1_epi32((int)kLower)));
+    const __mmask16 odd = _mm512_test_epi32_mask(y, _mm512_set1_epi32(1));
+    const __m512i sh = _mm512_srli_epi32(y, 1);
+    return _mm512_mask_xor_epi32(sh, odd, sh, _mm512_set1_epi32((int)kMatrixA));
+}
+
+// In-place twist of key[0..624) (the array has >= 32 words of padding behind it).
+__attribute__((target("avx512f,avx512bw,avx512vl"))) void twist_avx512(uint32_t *key) {
+    // new[k] = old[k + 397] ^ tw(old[k], old[k + 1]),  k in [0, 227)
+    int k = 0;
+    for (; k + 16 <= kN - kM - 3; k += 16) {  // k = 0 .. 208: reads up to old[620]
+        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+        const __m512i c = _mm512_loadu_si512(key + k + kM);
+        _mm512_storeu_si512(key + k, _mm512_xor_si512(c, twist16(a, b)));
+    }
+    {   // k = 224, 225, 226 (the other lanes would clobber old words the second region still needs)
+        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+        const __m512i c = _mm512_loadu_si512(key + k + kM);
+        _mm512_mask_storeu_epi32(key + k, (__mmask16)0x7, _mm512_xor_si512(c, twist16(a, b)));
+        k = kN - kM;
+    }
+    key[kN] = key[0];  // old[624] := new[0], what k = 623 pairs with
+    // new[k] = new[k - 227] ^ tw(old[k], old[k + 1]),  k in [227, 624)
+    for (; k + 16 <= kN; k += 16) {
+        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+        const __m512i c = _mm512_loadu_si512(key + k - (kN - kM));
+        _mm512_storeu_si512(key + k, _mm512_xor_si512(c, twist16(a, b)));
+    }
+    if (k < kN) {  // k = 611 .. 623
+        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+        const __m512i c = _mm512_loadu_si512(key + k - (kN - kM));
+        _mm512_mask_storeu_epi32(key + k, (__mmask16)((1u << (kN - k)) - 1u), _mm512_xor_si512(c, twist16(a, b)));
+    }
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl"))) void temper_avx512(const uint32_t *key, uint32_t *out) {
+    for (int k = 0; k < kN; k += 16) {  // 624 = 39 * 16
+        __m512i y = _mm512_loadu_si512(key + k);
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
+        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), _mm512_set1_epi32((int)0x9d2c5680u)));
+        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), _mm512_set1_epi32((int)0xefc60000u)));
+        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
+        _mm512_storeu_si512(out + k, y);
+    }
+}
+#endif
+
+bool cpu_has_avx512() {
+#if PHET_X86
+    static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                           __builtin_cpu_supports("avx512vl") && getenv("PHET_MT_SCALAR") == nullptr;
+    return ok;
+#else
+    return false;
+#endif
+}
+
+}  // namespace
+
+// The generator: NumPy's (key, pos) plus a window of tempered outputs.  buf = [kCarry carried outputs of the
+// previous block | 624 outputs of the current block]; [pos, end) are the unconsumed ones.
+struct phet_mt {
+    alignas(64) uint32_t key[kN + 32];
+    alignas(64) uint32_t prev_key[kN + 32];
+    alignas(64) uint32_t buf[kCarry + kN + 32];
+    int pos = kCarry + kN, end = kCarry + kN;
+    bool avx512 = false;
+
+    void load(const uint32_t *k, int p) {
+        memcpy(key, k, sizeof(uint32_t) * kN);
+        memset(key + kN, 0, sizeof(uint32_t) * 32);
+        memcpy(prev_key, key, sizeof(key));
+        fill_outputs();
+        pos = kCarry + p;
+        end = kCarry + kN;
+    }
+    void fill_outputs() {
+#if PHET_X86
+        if (avx512) {
+            temper_avx512(key, buf + kCarry);
+            return;
+        }
+#endif
+        temper_scalar(key, buf + kCarry);
+    }
+    // fewer than kCarry outputs left: move them in front of a fresh block
+    void refill() {
+        const int rem = end - pos;
+        if (rem > 0) memmove(buf + kCarry - rem, buf + pos, sizeof(uint32_t) * (size_t)rem);
+        memcpy(prev_key, key, sizeof(uint32_t) * kN);
+#if PHET_X86
+        if (avx512) twist_avx512(key);
+        else
+#endif
+            twist_scalar(key);
+        fill_outputs();
+        pos = kCarry - rem;
+        end = kCarry + kN;
+    }
+    inline void ensure(int k) {  // k <= kCarry
+        if (end - pos < k) refill();
+    }
+    inline uint32_t next32() {
+        if (pos == end) refill();
+        return buf[pos++];
+    }
+    void state(uint32_t *k, int *p) const {
+        if (pos >= kCarry) {
+            memcpy(k, key, sizeof(uint32_t) * kN);
+            *p = pos - kCarry;  // 624: regenerate on the next draw (NumPy's convention)
+        } else {  // still inside the carried tail of the previous block
+            memcpy(k, prev_key, sizeof(uint32_t) * kN);
+            *p = kN - (kCarry - pos);
+        }
+    }
+};
+
+namespace {
+
+// ---- the draws of one np.random.permutation(n): dst[t] = rk_interval(n - 1 - t), t = 0 .. n - 2
+template <typename J, bool STORE>
+void shuffle_draws_scalar(phet_mt &e, uint32_t n, J *dst) {
+    size_t t = 0;
+    for (uint32_t i = n - 1; i >= 1; --i) {
+        const uint32_t mask = bitmask(i);
+        uint32_t v;
+        while ((v = (e.next32() & mask)) > i) {
+        }
+        if (STORE) dst[t] = (J)v;
+        ++t;
+    }
+}
+
+#if PHET_X86
+template <typename J>
+__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed(J *dst, __m512i v, __mmask16 keep, int cnt);
+
+template <>
+__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed<uint32_t>(uint32_t *dst, __m512i v,
+                                                                                           __mmask16 keep, int cnt) {
+    const __m512i c = _mm512_maskz_compress_epi32(keep, v);
+    _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << cnt) - 1u), c);
+}
+
+template <>
+__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed<uint16_t>(uint16_t *dst, __m512i v,
+                                                                                           __mmask16 keep, int cnt) {
+    const __m512i c = _mm512_maskz_compress_epi32(keep, v);
+    _mm256_mask_storeu_epi16(dst, (__mmask16)((1u << cnt) - 1u), _mm512_cvtepi32_epi16(c));
+}
+
+// 64 outputs per trip.  With i the running position at the start of the trip, lane k (k-th output of the trip)
+// sees i_k = i - #{accepted among lanes < k} in [i - k, i]:  v > i is rejected and v <= i - k is accepted whatever
+// the earlier lanes did.  The few lanes in between (probability ~ k / 2^bits(i) each) are settled one by one, in
+// order, with the exact i_k -- the lanes before them are all decided by then.  A trip stops where i would leave
+// the octave [lo, mask] that fixes the bit mask.
+constexpr uint32_t kScalarBelow = 96;  // the last draws of a permutation go one output at a time
+
+template <typename J, bool STORE>
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi,bmi2,popcnt"))) void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
+    const __m512i lane = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m512i lanek[4] = {lane, _mm512_add_epi32(lane, _mm512_set1_epi32(16)), _mm512_add_epi32(lane, _mm512_set1_epi32(32)),
+                              _mm512_add_epi32(lane, _mm512_set1_epi32(48))};
+    size_t t = 0;
+    uint32_t i = n - 1;
+    while (i >= kScalarBelow) {
+        const uint32_t mask = bitmask(i), lo = (mask >> 1) + 1;  // every i in [lo, mask] shares this mask
+        const uint32_t floor_i = lo > kScalarBelow ? lo : kScalarBelow;
+        const __m512i vm = _mm512_set1_epi32((int)mask);
+        while (i >= floor_i) {
+            e.ensure(64);
+            const uint32_t *src = e.buf + e.pos;
+            const __m512i vi = _mm512_set1_epi32((int)i);
+            __m512i v[4];
+            uint64_t sure = 0, amb = 0;
+#pragma GCC unroll 4
+            for (int q = 0; q < 4; ++q) {
+                v[q] = _mm512_and_si512(_mm512_loadu_si512(src + 16 * q), vm);
+                // v > i: rejected; v + k <= i: accepted (both against the same broadcast of i; v + k cannot wrap: v < 2^31)
+                const __mmask16 nrej = _mm512_cmple_epu32_mask(v[q], vi);
+                const __mmask16 sq = _mm512_cmple_epu32_mask(_mm512_add_epi32(v[q], lanek[q]), vi);
+                sure |= (uint64_t)sq << (16 * q);
+                amb |= (uint64_t)(__mmask16)(nrej & ~sq) << (16 * q);
+            }
+            while (__builtin_expect(amb != 0, 0)) {  // in lane order: everything before lane k is decided
+                const int k = __builtin_ctzll(amb);
+                const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure & ((1ull << k) - 1ull));
+                if ((src[k] & mask) <= ik) sure |= 1ull << k;
+                amb &= amb - 1;
+            }
+            uint32_t total = (uint32_t)__builtin_popcountll(sure);
+            const uint32_t room = i - lo + 1;  // accepts left in this octave
+            int used = 64;
+            if (__builtin_expect(total >= room, 0)) {  // stop right after the room-th accepted lane: the outputs
+                                                       // behind it meet a narrower mask (even the rejected ones)
+                used = __builtin_ctzll(_pdep_u64(1ull << (room - 1), sure)) + 1;
+                sure &= (used == 64) ? ~0ull : ((1ull << used) - 1ull);
+                total = room;
+            }
+            if (STORE) {
+                size_t tt = t;
+#pragma GCC unroll 4
+                for (int q = 0; q < 4; ++q) {
+                    const __mmask16 sq = (__mmask16)(sure >> (16 * q));
+                    const int cnt = __builtin_popcount((unsigned)sq);
+                    store_compressed<J>(dst + tt, v[q], sq, cnt);
+                    tt += (size_t)cnt;
+                }
+            }
+            t += total;
+            i -= total;
+            e.pos += used;
+        }
+    }
+    for (; i >= 1; --i) {  // the tail, one output at a time
+        const uint32_t mask = bitmask(i);
+        uint32_t r;
+        while ((r = (e.next32() & mask)) > i) {
+        }
+        if (STORE) dst[t] = (J)r;
+        ++t;
+    }
+}
+#endif
+
+template <typename J>
+void shuffle_draws(phet_mt &e, uint32_t n, J *dst) {
+    if (n < 2) return;
+#if PHET_X86
+    if (e.avx512) {
+        if (dst) shuffle_draws_avx512<J, true>(e, n, dst);
+        else shuffle_draws_avx512<J, false>(e, n, dst);
+        return;
+    }
+#endif
+    if (dst) shuffle_draws_scalar<J, true>(e, n, dst);
+    else shuffle_draws_scalar<J, false>(e, n, dst);
+}
+
+#define MT_REQUIRE(cond, msg)                                    \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::phet::set_error(std::string("invalid: ") + (msg)); \
+            return PHET_ERR_INVALID;                             \
+        }                                                        \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int phet_mt_create(const uint32_t *key, int32_t pos, phet_mt **out) {
+    MT_REQUIRE(key != nullptr && out != nullptr, "NULL argument");
+    MT_REQUIRE(pos >= 0 && pos <= kN, "MT19937 position must be in [0, 624]");
+    void *mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(phet_mt)) != 0 || !mem) {
+        phet::set_error("out of host memory");
+        return PHET_ERR_NOMEM;
+    }
+    phet_mt *e = new (mem) phet_mt();
+    e->avx512 = cpu_has_avx512();
+    e->load(key, pos);
+    *out = e;
+    return PHET_OK;
+}
+
+int phet_mt_state(const phet_mt *e, uint32_t *key_out, int32_t *pos_out) {
+    MT_REQUIRE(e != nullptr && key_out != nullptr && pos_out != nullptr, "NULL argument");
+    int p = 0;
+    e->state(key_out, &p);
+    *pos_out = p;
+    return PHET_OK;
+}
+
+int phet_mt_destroy(phet_mt *e) {
+    if (e) {
+        e->~phet_mt();
+        free(e);
+    }
+    return PHET_OK;
+}
+
+int phet_mt_simd(const phet_mt *e) { return e ? (e->avx512 ? 512 : 0) : (cpu_has_avx512() ? 512 : 0); }
+
+int phet_mt_shuffle_rounds(phet_mt *e, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds) {
+    MT_REQUIRE(e != nullptr && jobs != nullptr && n_jobs >= 1 && rounds >= 0, "bad arguments");
+    for (int k = 0; k < n_jobs; ++k) {
+        MT_REQUIRE(jobs[k].n >= 1 && jobs[k].n <= (int64_t)0xFFFFFFFFll, "permutation length must be in [1, 2^32)");
+        MT_REQUIRE(jobs[k].elem_bytes == 2 || jobs[k].elem_bytes == 4, "elem_bytes must be 2 or 4");
+        MT_REQUIRE(jobs[k].elem_bytes == 4 || jobs[k].n <= 65536, "16-bit draws need n <= 65536");
+        MT_REQUIRE(jobs[k].out == nullptr || jobs[k].stride_bytes >= (jobs[k].n - 1) * jobs[k].elem_bytes,
+                   "stride shorter than one permutation's draws");
+    }
+    for (int64_t r = 0; r < rounds; ++r) {
+        for (int k = 0; k < n_jobs; ++k) {
+            const phet_mt_job &j = jobs[k];
+            unsigned char *dst = j.out ? static_cast<unsigned char *>(j.out) + (size_t)r * (size_t)j.stride_bytes : nullptr;
+            if (j.elem_bytes == 2) shuffle_draws<uint16_t>(*e, (uint32_t)j.n, reinterpret_cast<uint16_t *>(dst));
+            else shuffle_draws<uint32_t>(*e, (uint32_t)j.n, reinterpret_cast<uint32_t *>(dst));
+        }
+    }
+    return PHET_OK;
+}
+
+int phet_mt_bounded(phet_mt *e, uint32_t max, int64_t count, uint32_t *out) {
+    MT_REQUIRE(e != nullptr && out != nullptr && count >= 0, "bad arguments");
+    if (max == 0) {  // random_interval(0) returns 0 without touching the stream
+        for (int64_t k = 0; k < count; ++k) out[k] = 0;
+        return PHET_OK;
+    }
+    const uint32_t mask = bitmask(max);
+    for (int64_t k = 0; k < count; ++k) {
+        uint32_t v;
+        while ((v = (e->next32() & mask)) > max) {
+        }
+        out[k] = v;
+    }
+    return PHET_OK;
+}
+
+int phet_host_fisher_yates(const void *draws, int32_t elem_bytes, int64_t n, int64_t take, uint32_t *out) {
+    MT_REQUIRE(out != nullptr && n >= 1 && take >= 0 && take <= n, "bad arguments");
+    MT_REQUIRE(n == 1 || draws != nullptr, "draws are NULL");
+    MT_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "elem_bytes must be 2 or 4");
+    uint32_t *x = static_cast<uint32_t *>(malloc(sizeof(uint32_t) * (size_t)n));
+    if (!x) {
+        phet::set_error("out of host memory");
+        return PHET_ERR_NOMEM;
+    }
+    for (int64_t q = 0; q < n; ++q) x[q] = (uint32_t)q;
+    for (int64_t t = 0; t + 1 < n; ++t) {
+        const int64_t i = n - 1 - t;
+        const uint32_t j = elem_bytes == 2 ? static_cast<const uint16_t *>(draws)[t] : static_cast<const uint32_t *>(draws)[t];
+        if ((int64_t)j > i) {
+            free(x);
+            phet::set_error("invalid: a draw exceeds its position (not a rk_interval stream)");
+            return PHET_ERR_INVALID;
+        }
+        std::swap(x[i], x[j]);
+    }
+    memcpy(out, x, sizeof(uint32_t) * (size_t)take);
+    free(x);
+    return PHET_OK;
+}
+
+}  // extern "C"

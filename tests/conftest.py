@@ -20,7 +20,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
-                              for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("cli_", "siblings_", "multi_")))
+                              for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if not n.startswith(("cli_", "siblings_", "multi_", "big_")))
 
 
 def load_golden(name):
