@@ -40,7 +40,8 @@ typedef enum {
 typedef enum { PHET_F32 = 0, PHET_F64 = 1 } phet_dtype;
 typedef enum { PHET_NORM_NONE = 0, PHET_NORM_ZSCORE = 1 } phet_normalize;
 typedef enum { PHET_TEST_T = 0, PHET_TEST_Z = 1 } phet_test;          /* phet.py:425-428 */
-typedef enum { PHET_PERM_HOST = 0, PHET_PERM_DEVICE = 1 } phet_perm_mode;
+typedef enum { PHET_PERM_HOST = 0, PHET_PERM_DEVICE = 1, PHET_PERM_REPLAY = 2 } phet_perm_mode;
+typedef struct phet_mt phet_mt;  /* NumPy's legacy global stream, held natively (see below) */
 
 /* Device buffers a caller may want to wrap (e.g. for an NCCL all-reduce).  phet_device_ptr. */
 typedef enum {
@@ -161,6 +162,17 @@ typedef struct {
     const double *table_full, *table_last;
     int64_t n_last;
     int64_t block_genes;                   /* genes per H2D block; 0 = auto */
+    /* PHET_PERM_REPLAY: the Step-3 permutations are the ones the reference would draw from `mt` (phet.py:486-487),
+     * for ALL G genes in gene order (a rank that owns a gene range consumes the other genes' draws without
+     * storing them, so every rank leaves `mt` in the reference's final state).  The draws are made on a host
+     * thread while the device works on earlier blocks; the swaps run on the device.
+     * draw_index_sets != 0: the S x 2 index sets are drawn from `mt` first (phet.py:397-402, replace = False;
+     * requires m <= min(n0, n1)) instead of coming from phet_set_index_sets; S_draw / m give their shape and
+     * idx_out (host int32[S][2][m], may be NULL) receives them as ORIGINAL row numbers. */
+    phet_mt *mt;
+    int32_t draw_index_sets;
+    int64_t S_draw;
+    int32_t *idx_out;
 } phet_pipeline_params;
 
 int phet_run_pipeline(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G, int dtype,
@@ -301,7 +313,6 @@ int phet_fit_host(phet_ctx *ctx, const void *X, int dtype, int64_t N, int64_t G,
  * rk_interval(i) is the first stream value, masked to the bits of i, that is <= i.  phet_mt_shuffle_rounds emits the
  * swap targets only (the sequential part, vectorised); applying them is independent per permutation and is done on
  * the device (phet_draw_index_sets, PHET_PERM_REPLAY) or by phet_host_fisher_yates. */
-typedef struct phet_mt phet_mt;
 int phet_mt_create(const uint32_t *key624, int32_t pos, phet_mt **out);
 int phet_mt_state(const phet_mt *mt, uint32_t *key624_out, int32_t *pos_out);
 int phet_mt_destroy(phet_mt *mt);
@@ -322,6 +333,19 @@ int phet_mt_shuffle_rounds(phet_mt *mt, const phet_mt_job *jobs, int32_t n_jobs,
 int phet_mt_bounded(phet_mt *mt, uint32_t max, int64_t count, uint32_t *out);
 /* The first `take` entries of the permutation of arange(n) that the draws produce (host; tests, small problems). */
 int phet_host_fisher_yates(const void *draws, int32_t elem_bytes, int64_t n, int64_t take, uint32_t *out);
+
+/* Permutations from swap targets on the device (csrc/fy_apply.cu; what PHET_PERM_REPLAY runs per block): draws is
+ * host memory, [count][ld] targets of elem_bytes (2 or 4) as phet_mt_shuffle_rounds writes them; out: host
+ * uint32[count][take], the first `take` entries of each permutation of arange(n). */
+int phet_fy_apply(phet_ctx *ctx, const void *draws, int32_t elem_bytes, int64_t ld, int64_t n, int64_t count,
+                  int64_t take, uint32_t *out);
+/* The index sets of phet.py:397-402 (replace = False, m <= min(n0, n1)) drawn from `mt`: for each of S subsamples the
+ * first m entries of np.random.permutation over the control rows, then over the case rows -- what
+ * np.random.choice(rows, m, replace=False) returns -- installed like phet_set_index_sets.  idx_out: host
+ * int32[S][2][m] (ORIGINAL row numbers) or NULL.  Requires phet_set_classes. */
+int phet_draw_index_sets(phet_ctx *ctx, phet_mt *mt, int64_t S, int64_t m, int32_t *idx_out);
+/* out[0]: host seconds the draw thread spent in the last replay; out[1]: seconds the issuing thread waited for it. */
+int phet_replay_stats(phet_ctx *ctx, double out[2]);
 
 /* Testing hooks: host evaluations of the exact device routines (same source file) so the
  * CPU test-suite can check them without a GPU. */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libphet_b200.so")
 PHET_F32, PHET_F64 = 0, 1
 NORM_NONE, NORM_ZSCORE = 0, 1
 TEST_T, TEST_Z = 0, 1
-PERM_HOST, PERM_DEVICE = 0, 1
+PERM_HOST, PERM_DEVICE, PERM_REPLAY = 0, 1, 2
 OPT_KEEP_H = 1
 OPT_STEP3_MIN_SIZE = 2
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
@@ -29,6 +29,8 @@ EXPORTS = [
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
     "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix", "phet_load_matrix_genes",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
+    "phet_mt_create", "phet_mt_state", "phet_mt_destroy", "phet_mt_simd", "phet_mt_shuffle_rounds", "phet_mt_bounded",
+    "phet_host_fisher_yates", "phet_fy_apply", "phet_replay_stats", "phet_draw_index_sets",
 ]
 
 
@@ -51,7 +53,12 @@ class PipelineParams(C.Structure):
                 ("s_begin", C.c_int64), ("s_end", C.c_int64), ("g3_begin", C.c_int64), ("g3_end", C.c_int64),
                 ("step1", Step1Params), ("m", C.c_int64), ("perm_mode", C.c_int32), ("seed", C.c_uint64),
                 ("perm_ctrl", C.c_void_p), ("perm_case", C.c_void_p), ("table_full", C.c_void_p),
-                ("table_last", C.c_void_p), ("n_last", C.c_int64), ("block_genes", C.c_int64)]
+                ("table_last", C.c_void_p), ("n_last", C.c_int64), ("block_genes", C.c_int64),
+                ("mt", C.c_void_p), ("draw_index_sets", C.c_int32), ("S_draw", C.c_int64), ("idx_out", C.c_void_p)]
+
+
+class MtJob(C.Structure):
+    _fields_ = [("n", C.c_int64), ("out", C.c_void_p), ("stride_bytes", C.c_int64), ("elem_bytes", C.c_int32)]
 
 
 class FitParams(C.Structure):
@@ -126,6 +133,16 @@ def load_library(build_if_missing: bool = True):
     lib.phet_host_p_two_sided_z.restype = dbl
     lib.phet_host_perm_apply.argtypes = [u64, u64, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.phet_host_perm_apply.restype = C.c_uint32
+    lib.phet_mt_create.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.phet_mt_state.argtypes = [vp, vp, C.POINTER(i32)]
+    lib.phet_mt_destroy.argtypes = [vp]
+    lib.phet_mt_simd.argtypes = [vp]
+    lib.phet_mt_shuffle_rounds.argtypes = [vp, C.POINTER(MtJob), i32, i64]
+    lib.phet_mt_bounded.argtypes = [vp, C.c_uint32, i64, vp]
+    lib.phet_host_fisher_yates.argtypes = [vp, i32, i64, i64, vp]
+    lib.phet_fy_apply.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp]
+    lib.phet_replay_stats.argtypes = [vp, C.POINTER(dbl)]
+    lib.phet_draw_index_sets.argtypes = [vp, vp, i64, i64, vp]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.phet_abi_version() != 1:
@@ -141,6 +158,85 @@ def _check(rc):
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class MtStream:
+    """NumPy's legacy global stream (``np.random``: MT19937) held natively -- include/phet_b200.h ``phet_mt``.
+
+    ``MtStream.from_numpy()`` takes ``np.random.get_state()``; the draws the library makes advance it exactly as
+    the reference's ``np.random.choice`` / ``np.random.permutation`` calls would (phet.py:401-402, 486-487);
+    ``to_numpy()`` puts the advanced state back with ``np.random.set_state`` so the caller's stream goes on where
+    the reference's would.  No GPU involved."""
+
+    def __init__(self, key: np.ndarray, pos: int, gauss=(0, 0.0)):
+        self.lib = load_library()
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        assert key.size == 624
+        h = C.c_void_p()
+        _check(self.lib.phet_mt_create(_ptr(key), int(pos), C.byref(h)))
+        self.h = h
+        self._gauss = gauss
+
+    @classmethod
+    def from_numpy(cls, state=None):
+        st = np.random.get_state() if state is None else state
+        if st[0] != "MT19937":
+            raise PhetError("np.random is not the legacy MT19937 stream")
+        return cls(st[1], st[2], (st[3], st[4]))
+
+    def state(self):
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32()
+        _check(self.lib.phet_mt_state(self.h, _ptr(key), C.byref(pos)))
+        return key, int(pos.value)
+
+    def numpy_state(self):
+        key, pos = self.state()
+        return ("MT19937", key, pos, self._gauss[0], self._gauss[1])
+
+    def to_numpy(self):
+        np.random.set_state(self.numpy_state())
+
+    def simd(self) -> int:
+        return int(self.lib.phet_mt_simd(self.h))
+
+    def shuffle_draws(self, sizes, rounds: int, store: bool = True):
+        """The swap targets of ``rounds`` x [np.random.permutation(n) for n in sizes]: a list of arrays
+        (rounds, n - 1), uint16 when n <= 65536 else uint32 (None when ``store`` is False: stream advanced only)."""
+        outs, jobs = [], (MtJob * len(sizes))()
+        for k, n in enumerate(sizes):
+            eb = 2 if n <= 65536 else 4
+            arr = np.zeros((rounds, max(int(n) - 1, 1)), dtype=np.uint16 if eb == 2 else np.uint32) if store else None
+            outs.append(arr)
+            jobs[k] = MtJob(int(n), arr.ctypes.data if store else None, arr.strides[0] if store else 0, eb)
+        _check(self.lib.phet_mt_shuffle_rounds(self.h, jobs, len(sizes), int(rounds)))
+        return outs
+
+    def permutation(self, n: int, take: int | None = None) -> np.ndarray:
+        """np.random.permutation(n)[:take], swaps applied on the host (tests, small problems)."""
+        n = int(n)
+        take = n if take is None else int(take)
+        draws = self.shuffle_draws([n], 1)[0]
+        out = np.empty(take, dtype=np.uint32)
+        _check(self.lib.phet_host_fisher_yates(_ptr(draws), draws.dtype.itemsize, n, take, _ptr(out)))
+        return out
+
+    def bounded(self, maximum: int, count: int) -> np.ndarray:
+        """``count`` draws of rk_interval(maximum): what np.random.randint(0, maximum + 1, count) returns."""
+        out = np.empty(int(count), dtype=np.uint32)
+        _check(self.lib.phet_mt_bounded(self.h, int(maximum), int(count), _ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phet_mt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class MtxFile:
@@ -313,10 +409,23 @@ class Context:
 
     def run_pipeline(self, X, N, G, dtype, params: Step1Params, m, table_full, table_last, n_last,
                      g_range=None, s_range=None, g3_range=None, normalize=NORM_ZSCORE, storage=None,
-                     perm_ctrl=None, perm_case=None, seed=0, is_device=False, block_genes=0):
+                     perm_ctrl=None, perm_case=None, seed=0, is_device=False, block_genes=0, mt=None,
+                     replay_perms=False, draw_index_sets=None):
         """Stage 0 + Step 1 + Step 3 over gene blocks.  X: C-contiguous host ndarray (N, G) or, with
-        is_device=True, a raw device pointer (int)."""
+        is_device=True, a raw device pointer (int).  ``mt`` (an MtStream) + ``replay_perms=True``: the Step-3
+        permutations are the reference's own draws (PHET_PERM_REPLAY); ``draw_index_sets=(S, keep)``: the index
+        sets are drawn from ``mt`` first and, with keep=True, returned as int32 (S, 2, m) original rows."""
         pp = PipelineParams()
+        idx_out = None
+        if draw_index_sets is not None:
+            S_draw, keep_idx = draw_index_sets
+            pp.draw_index_sets, pp.S_draw = 1, int(S_draw)
+            self.S, self.m = int(S_draw), int(m)
+            if keep_idx:
+                idx_out = np.empty((int(S_draw), 2, int(m)), dtype=np.int32)
+                pp.idx_out = idx_out.ctypes.data
+        if mt is not None:
+            pp.mt = mt.h
         pp.normalize = normalize
         pp.storage = dtype if storage is None else storage
         pp.g_begin, pp.g_end = g_range if g_range is not None else (0, G)
@@ -333,12 +442,36 @@ class Context:
             pk = np.ascontiguousarray(perm_case, dtype=np.uint32)
             keep += [pc, pk]
             pp.perm_mode, pp.perm_ctrl, pp.perm_case = PERM_HOST, pc.ctypes.data, pk.ctypes.data
+        elif replay_perms:
+            pp.perm_mode = PERM_REPLAY
         else:
             pp.perm_mode, pp.seed = PERM_DEVICE, seed
         pp.block_genes = block_genes
         ptr = C.c_void_p(X) if is_device else _ptr(X)
         _check(self.lib.phet_run_pipeline(self.h, ptr, 1 if is_device else 0, N, G, dtype, C.byref(pp)))
         self.N, self.G = N, G
+        return idx_out
+
+    def fy_apply(self, draws: np.ndarray, n: int, take: int | None = None) -> np.ndarray:
+        """Permutations from swap targets on the device: draws (count, >= n - 1) uint16 / uint32 -> uint32 (count, take)."""
+        draws = np.ascontiguousarray(draws)
+        take = int(n) if take is None else int(take)
+        out = np.empty((draws.shape[0], take), dtype=np.uint32)
+        _check(self.lib.phet_fy_apply(self.h, _ptr(draws), draws.dtype.itemsize, draws.shape[1], int(n), draws.shape[0], take, _ptr(out)))
+        return out
+
+    def draw_index_sets(self, mt: "MtStream", S: int, m: int) -> np.ndarray:
+        """Index sets drawn from ``mt`` as the reference draws them (phet.py:397-402, replace=False), installed on
+        the device; returns them as int32 (S, 2, m) original row numbers."""
+        idx = np.empty((int(S), 2, int(m)), dtype=np.int32)
+        _check(self.lib.phet_draw_index_sets(self.h, mt.h, int(S), int(m), _ptr(idx)))
+        self.S, self.m = int(S), int(m)
+        return idx
+
+    def replay_stats(self):
+        out = (C.c_double * 2)()
+        _check(self.lib.phet_replay_stats(self.h, out))
+        return dict(draw_thread_s=float(out[0]), issue_wait_s=float(out[1]))
 
     def fisher(self, S_total):
         _check(self.lib.phet_fisher(self.h, S_total))

@@ -235,6 +235,7 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.perm_mode = perm_mode;
     a.perm0 = c->perm0.p;
     a.perm1 = c->perm1.p;
+    a.perm_g0 = c->perm_g0;
     a.coprime0 = c->coprime.p;
     a.coprime1 = c->coprime.p ? c->coprime.p + kCoprimeCount : nullptr;
     a.seed = seed;
@@ -328,6 +329,10 @@ int phet_ctx_destroy(phet_ctx *c) {
     if (!c) return PHET_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    replay_ring_destroy(c);
+    c->cls_rows.release();
+    c->fy_scratch.release();
+    c->draws_dev.release();
     c->rows_grouped.release();
     c->pos_of_row.release();
     c->xg.release();
@@ -408,7 +413,7 @@ int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const in
     // Layout: the cells of each class are placed in a fixed pseudo-random order (seeded
     // Fisher-Yates), so that cheap per-gene affine walks over positions (Step 3, device mode)
     // visit pseudo-random cells.  order[q] = class-local index held at class-relative position q.
-    std::vector<int32_t> grouped((size_t)N), pos((size_t)N, -1), cls_pos((size_t)N);
+    std::vector<int32_t> grouped((size_t)N), pos((size_t)N, -1), cls_pos((size_t)N), cls_rows((size_t)N);
     for (int cls = 0; cls < 2; ++cls) {
         const int64_t n = cls ? n1 : n0, off = cls ? n0 : 0;
         const int32_t *rows = cls ? case_rows : ctrl_rows;
@@ -430,11 +435,14 @@ int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const in
             grouped[(size_t)(off + q)] = r;
             pos[(size_t)r] = (int32_t)(off + q);
             cls_pos[(size_t)(off + t)] = (int32_t)q;
+            cls_rows[(size_t)(off + t)] = r;
         }
     }
     if (int e = c->rows_grouped.alloc((size_t)N)) return e;
     if (int e = c->pos_of_row.alloc((size_t)N)) return e;
     if (int e = c->cls_pos.alloc((size_t)N)) return e;
+    if (int e = c->cls_rows.alloc((size_t)N)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->cls_rows.p, cls_rows.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
     PHET_CUDA(cudaMemcpyAsync(c->rows_grouped.p, grouped.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
     PHET_CUDA(cudaMemcpyAsync(c->pos_of_row.p, pos.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
     PHET_CUDA(cudaMemcpyAsync(c->cls_pos.p, cls_pos.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice, c->stream));
@@ -447,8 +455,10 @@ int phet_set_classes(phet_ctx *c, const int32_t *ctrl_rows, int64_t n0, const in
     return PHET_OK;
 }
 
+extern "C++" {
+namespace phet {
 // Allocate the per-fit device buffers for genes [g_begin, g_end) of an N x G problem.
-static int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int normalize, int storage, int64_t g_begin,
+int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int normalize, int storage, int64_t g_begin,
                           int64_t g_end) {
     PHET_REQUIRE(c->classes_set, "phet_set_classes must be called before loading the matrix");
     PHET_REQUIRE(N == c->n0 + c->n1, "N does not match the class sizes");
@@ -487,6 +497,8 @@ static int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int norm
     PHET_CUDA(cudaMemsetAsync(c->sd.p, 0, sizeof(double) * G, c->stream));
     return PHET_OK;
 }
+}  // namespace phet
+}  // extern "C++"
 
 int phet_load_matrix(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype, int normalize,
                      int storage) {
@@ -522,15 +534,12 @@ int phet_load_matrix_genes(phet_ctx *c, const void *X_dev, int64_t ldx, int64_t 
     return PHET_OK;
 }
 
-int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
-    PHET_REQUIRE(c != nullptr, "ctx is NULL");
-    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called first");
-    PHET_REQUIRE(idx != nullptr && S >= 1 && m >= 1, "index sets: need S >= 1, m >= 1");
-    PHET_REQUIRE(m <= 512, "subsample size m > 512 is not supported");
-    PHET_CUDA(cudaSetDevice(c->device));
+extern "C++" {
+namespace phet {
+// c->idx holds int32[S][2][m] ORIGINAL row numbers (uploaded by phet_set_index_sets, or written by the replay
+// path): remap to grouped positions, validate, and build the transposed tables of the pair-per-thread kernels.
+int finish_index_sets(phet_ctx *c, int64_t S, int64_t m) {
     const int64_t n = S * 2 * m;
-    if (int e = c->idx.alloc((size_t)n)) return e;
-    PHET_CUDA(cudaMemcpyAsync(c->idx.p, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
     int *bad = reinterpret_cast<int *>(c->scalars.p + 12);
     PHET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
     k_remap_idx<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->idx.p, n, c->pos_of_row.p, c->n0 + c->n1, bad);
@@ -570,6 +579,20 @@ int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
     c->idx_set = true;
     return PHET_OK;
 }
+}  // namespace phet
+}  // extern "C++"
+
+int phet_set_index_sets(phet_ctx *c, const int32_t *idx, int64_t S, int64_t m) {
+    PHET_REQUIRE(c != nullptr, "ctx is NULL");
+    PHET_REQUIRE(c->classes_set, "phet_set_classes must be called first");
+    PHET_REQUIRE(idx != nullptr && S >= 1 && m >= 1, "index sets: need S >= 1, m >= 1");
+    PHET_REQUIRE(m <= 512, "subsample size m > 512 is not supported");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const int64_t n = S * 2 * m;
+    if (int e = c->idx.alloc((size_t)n)) return e;
+    PHET_CUDA(cudaMemcpyAsync(c->idx.p, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    return finish_index_sets(c, S, m);
+}
 
 int phet_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_params *prm, int accumulate) {
     PHET_REQUIRE(c != nullptr && prm != nullptr, "ctx/params NULL");
@@ -583,12 +606,15 @@ int phet_step1(phet_ctx *c, int64_t s_begin, int64_t s_end, const phet_step1_par
     return launch_step1(c, c->xg_g0, c->xg_g0 + c->xg_rows, s_begin, s_end, prm, accumulate);
 }
 
+extern "C++" {
+namespace phet {
 // Allocations, table/permutation uploads and zeroing shared by every Step-3 launch of a fit.
-static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,
+int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,
                          const double *table_full, const double *table_last, int64_t n_last) {
     PHET_REQUIRE(m >= 1 && m <= 512, "slice length m must be in [1, 512]");
-    PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE, "bad perm_mode");
+    PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE || perm_mode == PHET_PERM_REPLAY, "bad perm_mode");
     PHET_REQUIRE(table_full && table_last, "KS tables are NULL");
+    c->perm_g0 = 0;
     int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
     int64_t n_slices = (min_c + m - 1) / m;
     if (c->step3_min_size > 0) {
@@ -647,6 +673,8 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
         PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PHET_CUDA(cudaStreamSynchronize(c->stream));
         PHET_REQUIRE(hbad == 0, "host permutations contain a position outside its class");
+    } else if (perm_mode == PHET_PERM_REPLAY) {
+        // the permutation tables are filled block by block on the device (replay.cu)
     } else {
         if (c->coprime.p == nullptr || c->coprime_n0 != c->n0 || c->coprime_n1 != c->n1) {
             std::vector<uint32_t> cp(2 * kCoprimeCount);
@@ -662,6 +690,8 @@ static int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *
     }
     return PHET_OK;
 }
+}  // namespace phet
+}  // extern "C++"
 
 int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_mode, const uint32_t *perm_ctrl,
                const uint32_t *perm_case, uint64_t seed, const double *table_full, const double *table_last,
@@ -670,6 +700,7 @@ int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_
     PHET_REQUIRE(c->matrix_set, "load the matrix before phet_step3");
     PHET_REQUIRE(c->xg_g0 <= g_begin && g_begin <= g_end && g_end <= c->xg_g0 + c->xg_rows,
                  "gene range outside the resident genes");
+    PHET_REQUIRE(perm_mode != PHET_PERM_REPLAY, "PHET_PERM_REPLAY is a phet_run_pipeline mode");
     PHET_CUDA(cudaSetDevice(c->device));
     if (int e = step3_prepare(c, m, perm_mode, perm_ctrl, perm_case, table_full, table_last, n_last)) return e;
     int rc = launch_step3(c, g_begin, g_end, m, perm_mode, seed, n_last);
@@ -684,6 +715,7 @@ int phet_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int perm_
 int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype,
                       const phet_pipeline_params *p) {
     PHET_REQUIRE(c != nullptr && X != nullptr && p != nullptr, "NULL argument");
+    if (p->perm_mode == PHET_PERM_REPLAY || p->draw_index_sets) return run_pipeline_replay(c, X, is_device, N, G, dtype, p);
     PHET_REQUIRE(c->idx_set, "phet_set_index_sets must precede phet_run_pipeline");
     PHET_REQUIRE(p->m == c->m, "m does not match the uploaded index sets");
     PHET_REQUIRE(0 <= p->s_begin && p->s_begin <= p->s_end && p->s_end <= c->S, "subsample range outside [0, S]");

@@ -66,6 +66,10 @@ struct DevBuf {
 
 }  // namespace phet
 
+namespace phet {
+struct ReplayRing;
+}
+
 // A parsed MatrixMarket file (mtx.cu): zero-based triplets in file order.
 struct phet_mtx {
     int64_t rows = 0, cols = 0, declared = 0;
@@ -130,7 +134,8 @@ struct phet_ctx {
     phet::DevBuf<double> dbgP, dbgD;     // [G][S_local]
     phet::DevBuf<double> o;              // [G]
     phet::DevBuf<int32_t> H;             // [G][n_slices]
-    phet::DevBuf<uint32_t> perm0, perm1; // [G][min_c] (host mode)
+    phet::DevBuf<uint32_t> perm0, perm1; // [genes from perm_g0][min_c] (host mode: all G genes; replay mode: one block)
+    int64_t perm_g0 = 0;
     phet::DevBuf<double> tab_full, tab_last;
     phet::DevBuf<double> f, r, fw, scores;   // [G]
     phet::DevBuf<signed char> bins;      // [G]
@@ -157,6 +162,14 @@ struct phet_ctx {
     phet::DevBuf<double> rank_sorted, rank_in;
 
     int32_t step1_geom[5] = {0, 0, 0, 0, 0};
+
+    // replay of the reference's np.random draws (mt_replay.cpp -> fy_apply.cu, replay.cu)
+    phet::DevBuf<int32_t> cls_rows;        // [N]: original row of class-local index t (controls, then cases)
+    phet::DevBuf<uint32_t> fy_scratch;     // global-memory Fisher-Yates rows (classes longer than 65,536 cells)
+    phet::DevBuf<unsigned char> draws_dev; // one block of swap targets as uploaded
+    phet::ReplayRing *ring = nullptr;     // pinned host slots + producer thread state (replay.cu)
+    double replay_host_s = 0.0;            // host seconds the last replay spent drawing (producer thread)
+    double replay_wait_s = 0.0;            // seconds the issuing thread waited for draws
 };
 
 namespace phet {
@@ -175,6 +188,16 @@ int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
 int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
 int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
+int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
+                    const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, cudaStream_t stream);
+// shared by api.cu and replay.cu
+int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int normalize, int storage, int64_t g_begin, int64_t g_end);
+int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,
+                  const double *table_full, const double *table_last, int64_t n_last);
+int finish_index_sets(phet_ctx *c, int64_t S, int64_t m);   // c->idx holds ORIGINAL rows: remap, build the transposed tables
+int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype,
+                        const phet_pipeline_params *p);
+void replay_ring_destroy(phet_ctx *c);
 int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
                  int capture_debug, int kruskal);
 int mtx_parse(const char *path, int threads, phet_mtx &m);

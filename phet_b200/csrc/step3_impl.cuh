@@ -29,7 +29,8 @@ struct Step3Args {
     int64_t cap;   // max(m, n_last): what a slice sorter must hold (n_last > m only in multi-class fits, phet.py:488-492)
     int64_t g_begin, g_end;
     int perm_mode;
-    const uint32_t *perm0, *perm1;  // [G][min_c] class-relative grouped positions (host mode, remapped at upload)
+    const uint32_t *perm0, *perm1;  // [genes from perm_g0][min_c] class-relative grouped positions (host mode, remapped at upload)
+    int64_t perm_g0;                // gene of row 0 of the permutation tables (0 for uploaded tables, a block's first gene in replay mode)
     const uint32_t *coprime0, *coprime1;  // [kCoprimeCount] multipliers coprime to n0 / n1 (device mode)
     uint64_t seed;
     const double *tab_full, *tab_last;
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3(const Step3Args a) {
                         qa = affine_at(ap0, (uint64_t)(start + p));
                         qb = affine_at(ap1, (uint64_t)(start + p));
                     } else {
-                        qa = __ldg(a.perm0 + g * a.min_c + start + p);
-                        qb = __ldg(a.perm1 + g * a.min_c + start + p);
+                        qa = __ldg(a.perm0 + (g - a.perm_g0) * a.min_c + start + p);
+                        qb = __ldg(a.perm1 + (g - a.perm_g0) * a.min_c + start + p);
                     }
                     va[r] = STAGED ? gene[qa] : __ldg(gene + qa);
                     vb[r] = STAGED ? gene[n0 + qb] : __ldg(gene + n0 + qb);

@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) k_ks_big(const Step3Args a, in
                     qa = affine_at(ap0, (uint64_t)(start + p));
                     qb = affine_at(ap1, (uint64_t)(start + p));
                 } else {
-                    qa = __ldg(a.perm0 + g * a.min_c + start + p);
-                    qb = __ldg(a.perm1 + g * a.min_c + start + p);
+                    qa = __ldg(a.perm0 + (g - a.perm_g0) * a.min_c + start + p);
+                    qb = __ldg(a.perm1 + (g - a.perm_g0) * a.min_c + start + p);
                 }
                 va = __ldg(gene + qa);
                 vb = __ldg(gene + n0 + qb);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
             step_r = (uint32_t)((16ull * ap.a) % ncls);                                  // next register: t += 16
             step_s = (uint32_t)(((uint64_t)ap.a * ((uint64_t)nw * (uint64_t)a.m)) % ncls);  // next slice of this warp
         } else {
-            perm = (grp ? a.perm1 : a.perm0) + g * a.min_c;
+            perm = (grp ? a.perm1 : a.perm0) + (g - a.perm_g0) * a.min_c;
         }
         double omin = CUDART_INF;
         for (int64_t k = warp; k < a.n_slices; k += nw) {

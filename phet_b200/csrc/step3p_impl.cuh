@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
             ap[0] = make_affine(a.seed, (uint64_t)g, 0u, (uint32_t)a.n0, a.coprime0);
             ap[1] = make_affine(a.seed, (uint64_t)g, 1u, (uint32_t)a.n1, a.coprime1);
         } else {
-            permc[0] = a.perm0 + g * a.min_c;
-            permc[1] = a.perm1 + g * a.min_c;
+            permc[0] = a.perm0 + (g - a.perm_g0) * a.min_c;
+            permc[1] = a.perm1 + (g - a.perm_g0) * a.min_c;
         }
         auto stage = [&](int cls) {
             __syncthreads();  // every read of the vector in residence is done

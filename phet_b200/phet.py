@@ -33,7 +33,7 @@ class PHet:
                  adjust_pvalue: bool = False, feature_weight: Optional[list[float]] = None,
                  *, iqr_range: Optional[tuple[int, int]] = None, device: int | None = None,
                  storage: Literal["auto", "f32", "f64"] = "auto",
-                 permutation: Literal["reference", "device"] = "reference",
+                 permutation: Literal["reference", "numpy", "device"] = "reference",
                  distributed: bool | Literal["auto"] = "auto",
                  shard: Literal["subsamples", "genes"] = "genes", capture: bool = False):
         """Same parameters as the reference (phet.py:33-104).  Extra keyword-only arguments:
@@ -41,9 +41,16 @@ class PHet:
         iqr_range    alias of ``percentiles`` -- it is the name ``src/train.py:474`` passes.
         device       CUDA device index (default: LOCAL_RANK if set, else 0).
         storage      element type of the normalised matrix kept in HBM/SMEM ("auto" = X's dtype).
-        permutation  "reference": Step-3 permutations are drawn from ``np.random`` exactly as the
-                     reference does (phet.py:486-487), bit-compatible for a given seed;
-                     "device": a keyed bijection evaluated on the GPU (no G x N host draws).
+        permutation  "reference" (default): every random draw of the fit -- the S x 2 index sets (phet.py:401-402)
+                     and the 2 G Step-3 permutations (phet.py:486-487) -- is the reference's own: the
+                     ``np.random`` state is handed to the library, which replays NumPy's MT19937 +
+                     masked-rejection stream natively (host thread: the sequential scan; device: the swaps)
+                     while the device works, and the advanced state is put back into ``np.random``.
+                     Bit-compatible with the reference for a given seed.
+                     "numpy": the same draws made by calling ``np.random`` in Python loops (slow: 26 s at
+                     50k cells x 30k genes; kept as the cross-check of the native replay).
+                     "device": index sets as the reference draws them, Step-3 permutations from a keyed
+                     bijection evaluated on the GPU (no per-gene draws; NOT the reference's stream).
         distributed  shard subsamples (Step 1) and genes (Step 3) over the ranks of an initialised
                      ``torch.distributed`` group; "auto" = on when world_size > 1.
         shard        with distributed ranks: "genes" (default) = every rank loads only its gene slice
@@ -177,54 +184,85 @@ class PHet:
         S = int(self.num_subsamples)
         rank, world, dist = self._dist()
 
-        # ---- host draws, in the reference's order (all Step-1 draws, then Step-3 permutations)
-        t0 = time.perf_counter()
-        if dist is None or rank == 0:
-            idx = self.draw_index_sets(examples_i, examples_j, m, replace)
-        else:
-            idx = np.empty((S, 2, m), dtype=np.int32)
-        n_slices, n_last = hostmath.step3_slices(min_c, m)
-        perm0 = perm1 = None
-        seed = 0
-        if self.permutation == "reference":
-            if dist is None or rank == 0:
-                perm0, perm1 = self.draw_permutations(n0, n1, num_features, min_c)
-            else:
-                perm0 = np.empty((num_features, min_c), dtype=np.uint32)
-                perm1 = np.empty((num_features, min_c), dtype=np.uint32)
-        elif self.permutation == "device":
-            seed = int(np.random.randint(0, 2 ** 31 - 1)) if (dist is None or rank == 0) else 0
-        else:
-            raise ValueError("permutation must be 'reference' or 'device'")
-        if dist is not None:
-            from .distributed import broadcast_numpy
-            idx = broadcast_numpy(idx, dist)
-            if perm0 is not None:
-                perm0 = broadcast_numpy(perm0.view(np.int32), dist).view(np.uint32)
-                perm1 = broadcast_numpy(perm1.view(np.int32), dist).view(np.uint32)
-            seed = int(broadcast_numpy(np.array([seed], dtype=np.int64), dist)[0])
-        self.timings_["host_draws_s"] = time.perf_counter() - t0
-
-        # ---- device
+        if self.permutation not in ("reference", "numpy", "device"):
+            raise ValueError("permutation must be 'reference', 'numpy' or 'device'")
+        # ---- device and streams first: every collective below runs on this rank's own GPU
         dev = self._resolve_device()
-        stream = None
         if staged is not None and dist is not None:
             raise NotImplementedError("a StagedMatrix is fitted by the process that staged it (single device)")
-        if dist is not None:
+        n_slices, n_last = hostmath.step3_slices(min_c, m)
+        if dist is None:
+            ctx = staged.ctx if staged is not None else _capi.Context(dev, None)
+            try:
+                scores = self._fit_on(ctx, X, examples_i, examples_j, m, replace, S, n_slices, n_last, 0, 1, None)
+            finally:
+                if staged is None:
+                    ctx.close()
+        else:
             import torch
-            torch.cuda.set_device(dev)
+            use_cuda = dist.get_backend() == "nccl"
+            if use_cuda:
+                torch.cuda.set_device(dev)
             self._torch_stream = torch.cuda.Stream(dev)   # non-default: handle 0 would mean "own stream"
-            torch.cuda.set_stream(self._torch_stream)
-            stream = self._torch_stream.cuda_stream
-        ctx = staged.ctx if staged is not None else _capi.Context(dev, stream)
-        try:
-            scores = self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices,
-                                      n_last, rank, world, dist)
-        finally:
-            if staged is None:
-                ctx.close()
+            with torch.cuda.stream(self._torch_stream):   # the caller's current stream is restored on exit
+                ctx = _capi.Context(dev, self._torch_stream.cuda_stream)
+                try:
+                    scores = self._fit_on(ctx, X, examples_i, examples_j, m, replace, S, n_slices, n_last, rank, world, dist)
+                finally:
+                    ctx.close()
         self.timings_["fit_s"] = time.perf_counter() - t_all
         return scores
+
+    # ------------------------------------------------------------------------------------
+    def _fit_on(self, ctx, X, examples_i, examples_j, m, replace, S, n_slices, n_last, rank, world, dist):
+        """Draws + device work on an open context.  The random draws follow the reference's order: all Step-1
+        index sets, then (reference / numpy modes) the Step-3 permutations gene by gene."""
+        import time
+        n0, n1 = len(examples_i), len(examples_j)
+        min_c = min(n0, n1)
+        num_features = X.shape[1]
+        t0 = time.perf_counter()
+        idx = perm0 = perm1 = mt = None
+        seed = 0
+        draw_on_device = False
+        if self.permutation == "numpy":
+            if dist is None or rank == 0:
+                idx = self.draw_index_sets(examples_i, examples_j, m, replace)
+                perm0, perm1 = self.draw_permutations(n0, n1, num_features, min_c)
+            else:
+                idx = np.empty((S, 2, m), dtype=np.int32)
+                perm0 = np.empty((num_features, min_c), dtype=np.uint32)
+                perm1 = np.empty((num_features, min_c), dtype=np.uint32)
+            if dist is not None:
+                from .distributed import broadcast_numpy
+                idx = broadcast_numpy(idx, dist)
+                perm0 = broadcast_numpy(perm0.view(np.int32), dist).view(np.uint32)
+                perm1 = broadcast_numpy(perm1.view(np.int32), dist).view(np.uint32)
+        else:
+            # the global stream, held natively; every rank replays rank 0's stream (no draws cross the wire)
+            st = np.random.get_state()
+            key, pos = np.ascontiguousarray(st[1], dtype=np.uint32), int(st[2])
+            if dist is not None:
+                from .distributed import broadcast_numpy
+                packed = broadcast_numpy(np.concatenate([key.view(np.int32), np.array([pos], dtype=np.int32)]), dist)
+                key, pos = packed[:624].view(np.uint32).copy(), int(packed[624])
+            mt = _capi.MtStream(key, pos, (st[3], st[4]))
+            if replace:
+                # m exceeds a class (integer subsampling_size only): choice(rows, m, True) == rows[randint(0, n, m)]
+                idx = np.empty((S, 2, m), dtype=np.int32)
+                for s in range(S):
+                    idx[s, 0] = examples_i[mt.bounded(n0 - 1, m)]
+                    idx[s, 1] = examples_j[mt.bounded(n1 - 1, m)]
+            else:
+                draw_on_device = True
+        self.timings_["host_draws_s"] = time.perf_counter() - t0
+        try:
+            return self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
+                                    rank, world, dist, mt=mt, draw_on_device=draw_on_device)
+        finally:
+            if mt is not None:
+                mt.to_numpy()   # np.random continues where the reference's stream would
+                mt.close()
 
     # ------------------------------------------------------------------------------------
     def _step1_params(self, X_dtype, m):
@@ -241,7 +279,7 @@ class PHet:
         return prm
 
     def _run_device(self, ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
-                    rank, world, dist):
+                    rank, world, dist, mt=None, draw_on_device=False):
         N, G = X.shape
         from .ingest import StagedMatrix
         staged = isinstance(X, StagedMatrix)
@@ -259,13 +297,28 @@ class PHet:
             s_range = (0, S)
         ctx.set_option(_capi.OPT_KEEP_H, 1 if self.capture else 0)   # per-slice KS statistics only for capture
         ctx.set_classes(examples_i, examples_j)
-        ctx.set_index_sets(idx)
+        replay = self.permutation == "reference"
+        draw_arg = None
+        if idx is not None:
+            ctx.set_index_sets(idx)
+        elif replay:
+            draw_arg = (S, True)                      # drawn inside the pipeline, ahead of the Step-3 draws
+        else:                                         # "device": index sets from the stream, then the seed, as ever
+            idx = ctx.draw_index_sets(mt, S, m)
+        if self.permutation == "device":
+            seed = int(mt.bounded(2 ** 31 - 2, 1)[0])  # == np.random.randint(0, 2**31 - 1)
         prm = self._step1_params(X.dtype, m)
         # Stage 0 + Step 1 + Step 3, gene-block pipelined with the H2D copy (phet.py:291-299, 397-432, 473-498)
-        ctx.run_pipeline(X.device_ptr if staged else X, N, G, dtype, prm, m, hostmath.ks_exact_table(m),
-                         hostmath.ks_exact_table(n_last), n_last, is_device=staged, g_range=g_range, s_range=s_range, g3_range=g3_range,
-                         normalize=_capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE,
-                         storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed)
+        drawn = ctx.run_pipeline(X.device_ptr if staged else X, N, G, dtype, prm, m, hostmath.ks_exact_table(m),
+                                 hostmath.ks_exact_table(n_last), n_last, is_device=staged, g_range=g_range, s_range=s_range,
+                                 g3_range=g3_range,
+                                 normalize=_capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE,
+                                 storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed, mt=mt if replay else None,
+                                 replay_perms=replay, draw_index_sets=draw_arg)
+        if drawn is not None:
+            idx = drawn
+        if replay:
+            self.timings_.update(ctx.replay_stats())
         if dist is not None:
             from .distributed import allreduce_device_buffer
             # sum_s -2 ln p | sum_s delta | o, contiguous: one all-reduce (genes outside a rank's slice are 0)

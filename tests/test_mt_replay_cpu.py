@@ -1,0 +1,114 @@
+"""CPU: the native replay of NumPy's legacy global stream (csrc/mt_replay.cpp) against ``np.random`` itself --
+permutations, the index-set draws of phet.py:401-402, bounded draws, and the state the stream is left in.
+No GPU: the swaps are applied by the library's host routine here (the device routine is checked in the GPU tests)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mt():
+    from phet_b200._capi import MtStream
+    return MtStream.from_numpy()
+
+
+def _same_state(mt):
+    key, pos = mt.state()
+    st = np.random.get_state()
+    return np.array_equal(key, st[1]) and pos == st[2]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 29, 45, 252, 1000, 25000, 65535, 65536, 65537, 100000])
+@pytest.mark.parametrize("burn", [0, 7, 623])
+def test_permutation_bit_identical_to_numpy(n, burn):
+    np.random.seed(12345 + n)
+    if burn:
+        np.random.randint(0, 2 ** 31 - 1, size=burn)      # start anywhere inside a 624-word block
+    mt = _mt()
+    for _ in range(3):
+        got = mt.permutation(n)
+        ref = np.random.permutation(n)
+        assert np.array_equal(got, ref)
+        assert _same_state(mt), "state advance differs from NumPy's"
+
+
+def test_choice_without_replacement_is_a_permutation_prefix():
+    """phet.py:401-402: np.random.choice(rows, m, replace=False) == rows[np.random.permutation(len(rows))[:m]]."""
+    rows = np.arange(1000, 1252)
+    np.random.seed(5)
+    mt = _mt()
+    for m in (45, 1, 252):
+        ref = np.random.choice(a=rows, size=m, replace=False)
+        got = rows[mt.permutation(len(rows), take=m)]
+        assert np.array_equal(ref, got) and _same_state(mt)
+
+
+def test_choice_with_replacement_and_randint():
+    """replace=True (integer subsampling_size above a class size): rows[randint(0, n, m)]; the device-mode seed draw."""
+    rows = np.arange(7, 22)
+    np.random.seed(11)
+    mt = _mt()
+    for m in (20, 33):
+        ref = np.random.choice(a=rows, size=m, replace=True)
+        got = rows[mt.bounded(len(rows) - 1, m)]
+        assert np.array_equal(ref, got) and _same_state(mt)
+    ref = int(np.random.randint(0, 2 ** 31 - 1))
+    assert int(mt.bounded(2 ** 31 - 2, 1)[0]) == ref and _same_state(mt)
+    assert mt.bounded(0, 3).tolist() == [0, 0, 0] and _same_state(mt)   # rk_interval(0) does not touch the stream
+
+
+def test_rounds_follow_the_reference_order_and_skipping_only_advances():
+    """{n0, n1} x rounds is the order of phet.py:397-402 / 484-487; store=False must leave the same state."""
+    n0, n1, rounds = 300, 45, 17
+    np.random.seed(99)
+    a, b = _mt(), _mt()
+    d0, d1 = a.shuffle_draws([n0, n1], rounds)
+    b.shuffle_draws([n0, n1], rounds, store=False)
+    assert a.state()[1] == b.state()[1] and np.array_equal(a.state()[0], b.state()[0])
+    from phet_b200 import _capi
+    import ctypes as C
+    lib = _capi.load_library()
+    for r in range(rounds):
+        for draws, n in ((d0, n0), (d1, n1)):
+            out = np.empty(n, dtype=np.uint32)
+            assert lib.phet_host_fisher_yates(draws[r].ctypes.data_as(C.c_void_p), draws.dtype.itemsize, n, n,
+                                              out.ctypes.data_as(C.c_void_p)) == 0
+            assert np.array_equal(out, np.random.permutation(n))
+    assert _same_state(a)
+
+
+def test_state_round_trip_into_numpy():
+    np.random.seed(3)
+    np.random.standard_normal(3)                 # leaves a cached gaussian in the legacy state
+    mt = _mt()
+    mt.permutation(5000)
+    st_before = np.random.get_state()
+    np.random.permutation(5000)
+    want_next = np.random.random(4)
+    np.random.set_state(st_before)
+    mt.to_numpy()                                 # native state back into np.random (gaussian cache untouched)
+    np.random.permutation(1)                      # n = 1 consumes nothing
+    # the native stream already made the draw: np.random must now continue exactly behind it
+    assert np.array_equal(np.random.random(4), want_next)
+
+
+def test_scalar_and_avx512_scans_agree():
+    """The vectorised scan (64 outputs per trip) against the one-output-at-a-time scan, in a fresh process
+    (PHET_MT_SCALAR is read once)."""
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from phet_b200._capi import MtStream\n"
+            "np.random.seed(2024); mt = MtStream.from_numpy()\n"
+            "d = mt.shuffle_draws([25000, 70000, 513, 64], 3)\n"
+            "import hashlib; h = hashlib.sha256()\n"
+            "[h.update(x.tobytes()) for x in d]; k, p = mt.state(); h.update(k.tobytes()); print(mt.simd(), p, h.hexdigest())\n" % ROOT)
+    outs = []
+    for env in ({}, {"PHET_MT_SCALAR": "1"}):
+        e = dict(os.environ)
+        e.update(env)
+        outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, check=True).stdout.split())
+    assert outs[1][0] == "0"
+    assert outs[0][1:] == outs[1][1:]
