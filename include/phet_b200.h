@@ -329,6 +329,17 @@ typedef struct {
     int32_t elem_bytes;
 } phet_mt_job;
 int phet_mt_shuffle_rounds(phet_mt *mt, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds);
+/* The same draws with the work spread over threads: a generator thread fills a cache-resident ring with the stream, a
+ * scanner thread (the only sequential job) walks the permutations with a count-only scan and records where each
+ * STARTS, and `workers` threads redo the scan from there, storing the targets.  Submit blocks of rounds in stream
+ * order (returns at once; outputs must stay valid), wait on the ticket of a block before reading its outputs, end
+ * with phet_mt_par_end, which writes the stream's final state back into `mt` (do not touch `mt` in between).
+ * workers <= 0: env PHET_REPLAY_WORKERS or 4.  max_n: longest permutation that will be submitted (sizes the ring). */
+typedef struct phet_mt_par phet_mt_par;
+int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par **out);
+int phet_mt_par_submit(phet_mt_par *par, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds, int64_t *ticket_out);
+int phet_mt_par_wait(phet_mt_par *par, int64_t ticket);
+int phet_mt_par_end(phet_mt_par *par);
 /* count draws of rk_interval(max): what np.random.randint(0, max + 1, count) consumes (choice(..., replace=True)). */
 int phet_mt_bounded(phet_mt *mt, uint32_t max, int64_t count, uint32_t *out);
 /* The first `take` entries of the permutation of arange(n) that the draws produce (host; tests, small problems). */

@@ -30,6 +30,7 @@ EXPORTS = [
     "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix", "phet_load_matrix_genes",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
     "phet_mt_create", "phet_mt_state", "phet_mt_destroy", "phet_mt_simd", "phet_mt_shuffle_rounds", "phet_mt_bounded",
+    "phet_mt_par_begin", "phet_mt_par_submit", "phet_mt_par_wait", "phet_mt_par_end",
     "phet_host_fisher_yates", "phet_fy_apply", "phet_replay_stats", "phet_draw_index_sets",
 ]
 
@@ -139,6 +140,10 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mt_simd.argtypes = [vp]
     lib.phet_mt_shuffle_rounds.argtypes = [vp, C.POINTER(MtJob), i32, i64]
     lib.phet_mt_bounded.argtypes = [vp, C.c_uint32, i64, vp]
+    lib.phet_mt_par_begin.argtypes = [vp, i32, i64, C.POINTER(vp)]
+    lib.phet_mt_par_submit.argtypes = [vp, C.POINTER(MtJob), i32, i64, C.POINTER(i64)]
+    lib.phet_mt_par_wait.argtypes = [vp, i64]
+    lib.phet_mt_par_end.argtypes = [vp]
     lib.phet_host_fisher_yates.argtypes = [vp, i32, i64, i64, vp]
     lib.phet_fy_apply.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp]
     lib.phet_replay_stats.argtypes = [vp, C.POINTER(dbl)]
@@ -200,16 +205,39 @@ class MtStream:
     def simd(self) -> int:
         return int(self.lib.phet_mt_simd(self.h))
 
-    def shuffle_draws(self, sizes, rounds: int, store: bool = True):
+    def shuffle_draws(self, sizes, rounds: int, store: bool = True, workers: int | None = None, chunks: int = 1):
         """The swap targets of ``rounds`` x [np.random.permutation(n) for n in sizes]: a list of arrays
-        (rounds, n - 1), uint16 when n <= 65536 else uint32 (None when ``store`` is False: stream advanced only)."""
+        (rounds, n - 1), uint16 when n <= 65536 else uint32 (None when ``store`` is False: stream advanced only).
+        ``workers`` not None: through the multi-threaded replay (generator / scanner / store workers), the
+        rounds submitted in ``chunks`` blocks."""
         outs, jobs = [], (MtJob * len(sizes))()
         for k, n in enumerate(sizes):
             eb = 2 if n <= 65536 else 4
             arr = np.zeros((rounds, max(int(n) - 1, 1)), dtype=np.uint16 if eb == 2 else np.uint32) if store else None
             outs.append(arr)
             jobs[k] = MtJob(int(n), arr.ctypes.data if store else None, arr.strides[0] if store else 0, eb)
-        _check(self.lib.phet_mt_shuffle_rounds(self.h, jobs, len(sizes), int(rounds)))
+        if workers is None:
+            _check(self.lib.phet_mt_shuffle_rounds(self.h, jobs, len(sizes), int(rounds)))
+            return outs
+        par = C.c_void_p()
+        _check(self.lib.phet_mt_par_begin(self.h, int(workers), int(max(sizes)), C.byref(par)))
+        try:
+            tickets, r0 = [], 0
+            per = max(1, (int(rounds) + chunks - 1) // chunks)
+            while r0 < rounds:
+                rc = min(per, rounds - r0)
+                jj = (MtJob * len(sizes))()
+                for k, n in enumerate(sizes):
+                    jj[k] = MtJob(jobs[k].n, (jobs[k].out + r0 * jobs[k].stride_bytes) if store else None,
+                                  jobs[k].stride_bytes, jobs[k].elem_bytes)
+                t = C.c_int64()
+                _check(self.lib.phet_mt_par_submit(par, jj, len(sizes), rc, C.byref(t)))
+                tickets.append(t.value)
+                r0 += rc
+            for t in tickets:
+                _check(self.lib.phet_mt_par_wait(par, t))
+        finally:
+            _check(self.lib.phet_mt_par_end(par))
         return outs
 
     def permutation(self, n: int, take: int | None = None) -> np.ndarray:

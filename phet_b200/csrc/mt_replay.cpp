@@ -13,19 +13,31 @@
 //       accepted depends on the running i, so this part is sequential -- but it is pure streaming: generate
 //       tempered MT19937 outputs, mask, compare, compact the accepted ones.  It is vectorised 64 outputs at a
 //       time (AVX-512): a value <= i - k at lane k is accepted whatever the earlier lanes did, a value > i is
-//       rejected whatever they did, and anything in between (probability ~ 64^2 / 2i) drops to an exact
-//       16-wide / scalar step.  Output: the swap targets j, 16 bits each when n <= 65536.
+//       rejected whatever they did, and the few in between are settled in lane order with the exact count.
+//       Output: the swap targets j, 16 bits each when n <= 65536.  (The generator's twist can be issued in small
+//       steps between the scan's trips -- env PHET_MT_PUMP -- to fill the slots the scan's dependency chain leaves
+//       idle; measured on the GPU box's Xeon it changes nothing, both halves being bound by the two 512-bit ports.)
 //   (2) the SWAPS: random access, but independent across permutations -- applied on the GPU (csrc/fy_apply.cu)
 //       from the uploaded j streams, or by phet_host_fisher_yates for tests and small problems.
+//
+// Only WHERE each permutation starts in the stream is inherently sequential.  phet_mt_par_* therefore runs one
+// scanner thread with a count-only scan (no compaction, no stores) that records the generator state (2.5 KB) at
+// the start of every permutation, and worker threads that redo the scan from those states, storing the targets.
 //
 // The state goes in and out in np.random.get_state() / set_state() form (key[624], pos), so the caller's global
 // stream continues exactly where the reference's would.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -40,11 +52,22 @@ namespace phet {
 void set_error(const std::string &msg);
 }
 
+#define MT_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi,bmi2,popcnt")))
+
 namespace {
 
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
-constexpr int kCarry = 64;  // outputs of the previous block kept in front of the current one
+constexpr int kCarry = 64;      // outputs of the previous block kept in front of the current one
+constexpr int kGenSteps = 41;   // copy + 40 vector steps make the next block (see phet_mt::gen_step)
+// generator steps per 64-output trip of the scan (5 * 15.6 outputs >= 64); env PHET_MT_PUMP overrides (0: whole blocks)
+static const int kPump = getenv("PHET_MT_PUMP") ? atoi(getenv("PHET_MT_PUMP")) : 0;
+
+inline void cpu_relax() {
+#if PHET_X86
+    __builtin_ia32_pause();
+#endif
+}
 
 inline uint32_t temper(uint32_t y) {
     y ^= y >> 11;
@@ -80,7 +103,7 @@ inline uint32_t bitmask(uint32_t v) {  // smallest 2^k - 1 >= v  (numpy: random_
 }
 
 #if PHET_X86
-__attribute__((target("avx512f,avx512bw,avx512vl"))) inline __m512i twist16(__m512i a, __m512i b) {
+MT_AVX512 inline __m512i twist16(__m512i a, __m512i b) {
     const __m512i y = _mm512_or_si512(_mm512_and_si512(a, _mm512_set1_epi32((int)kUpper)),
                                       _mm512_and_si512(b, _mm512_set1_epi32((int)kLower)));
     const __mmask16 odd = _mm512_test_epi32_mask(y, _mm512_set1_epi32(1));
@@ -88,43 +111,46 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) inline __m512i twist16(__m5
     return _mm512_mask_xor_epi32(sh, odd, sh, _mm512_set1_epi32((int)kMatrixA));
 }
 
-// In-place twist of key[0..624) (the array has >= 32 words of padding behind it).
-__attribute__((target("avx512f,avx512bw,avx512vl"))) void twist_avx512(uint32_t *key) {
-    // new[k] = old[k + 397] ^ tw(old[k], old[k + 1]),  k in [0, 227)
-    int k = 0;
-    for (; k + 16 <= kN - kM - 3; k += 16) {  // k = 0 .. 208: reads up to old[620]
-        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
-        const __m512i c = _mm512_loadu_si512(key + k + kM);
-        _mm512_storeu_si512(key + k, _mm512_xor_si512(c, twist16(a, b)));
-    }
-    {   // k = 224, 225, 226 (the other lanes would clobber old words the second region still needs)
-        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
-        const __m512i c = _mm512_loadu_si512(key + k + kM);
-        _mm512_mask_storeu_epi32(key + k, (__mmask16)0x7, _mm512_xor_si512(c, twist16(a, b)));
-        k = kN - kM;
-    }
-    key[kN] = key[0];  // old[624] := new[0], what k = 623 pairs with
-    // new[k] = new[k - 227] ^ tw(old[k], old[k + 1]),  k in [227, 624)
-    for (; k + 16 <= kN; k += 16) {
-        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
-        const __m512i c = _mm512_loadu_si512(key + k - (kN - kM));
-        _mm512_storeu_si512(key + k, _mm512_xor_si512(c, twist16(a, b)));
-    }
-    if (k < kN) {  // k = 611 .. 623
-        const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
-        const __m512i c = _mm512_loadu_si512(key + k - (kN - kM));
-        _mm512_mask_storeu_epi32(key + k, (__mmask16)((1u << (kN - k)) - 1u), _mm512_xor_si512(c, twist16(a, b)));
-    }
+MT_AVX512 inline __m512i temper16(__m512i y) {
+    y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
+    y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), _mm512_set1_epi32((int)0x9d2c5680u)));
+    y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), _mm512_set1_epi32((int)0xefc60000u)));
+    return _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
 }
 
-__attribute__((target("avx512f,avx512bw,avx512vl"))) void temper_avx512(const uint32_t *key, uint32_t *out) {
-    for (int k = 0; k < kN; k += 16) {  // 624 = 39 * 16
-        __m512i y = _mm512_loadu_si512(key + k);
-        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
-        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), _mm512_set1_epi32((int)0x9d2c5680u)));
-        y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), _mm512_set1_epi32((int)0xefc60000u)));
-        y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
-        _mm512_storeu_si512(out + k, y);
+MT_AVX512 void temper_avx512(const uint32_t *key, uint32_t *out) {
+    for (int k = 0; k < kN; k += 16)  // 624 = 39 * 16
+        _mm512_storeu_si512(out + k, temper16(_mm512_loadu_si512(key + k)));
+}
+
+// One vector of the in-place twist of key[0..624) (the array has >= 32 words of padding behind it), tempered into
+// out.  Steps 1..40 in order make one block:
+//   1..14   k = 0, 16, .., 208     new[k] = old[k + 397] ^ tw(old[k], old[k + 1])        (reads up to old[620])
+//   15      k = 224 (3 lanes: the others would clobber old words the second half still needs); then old[624] := new[0]
+//   16..39  k = 227, 243, .., 595  new[k] = new[k - 227] ^ tw(old[k], old[k + 1])
+//   40      k = 611 (13 lanes; lane 12 pairs old[623] with new[0] through key[624])
+MT_AVX512 inline void twist_step_avx512(uint32_t *key, uint32_t *out, int step) {
+    int k, off;
+    __mmask16 m = 0xFFFF;
+    if (step <= 15) {
+        k = 16 * (step - 1);
+        off = kM;
+        if (step == 15) m = 0x7;
+    } else {
+        k = (kN - kM) + 16 * (step - 16);
+        off = -(kN - kM);
+        if (step == 40) m = (__mmask16)((1u << (kN - k)) - 1u);
+    }
+    const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+    const __m512i c = _mm512_loadu_si512(key + k + off);
+    const __m512i v = _mm512_xor_si512(c, twist16(a, b));
+    if (m == 0xFFFF) {  // (plain stores: a masked store does not forward to the loads of the next step)
+        _mm512_storeu_si512(key + k, v);
+        _mm512_storeu_si512(out + k, temper16(v));
+    } else {
+        _mm512_mask_storeu_epi32(key + k, m, v);
+        _mm512_mask_storeu_epi32(out + k, m, temper16(v));
+        if (step == 15) key[kN] = key[0];
     }
 }
 #endif
@@ -132,7 +158,8 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) void temper_avx512(const ui
 bool cpu_has_avx512() {
 #if PHET_X86
     static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
-                           __builtin_cpu_supports("avx512vl") && getenv("PHET_MT_SCALAR") == nullptr;
+                           __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") &&
+                           __builtin_cpu_supports("bmi2") && getenv("PHET_MT_SCALAR") == nullptr;
     return ok;
 #else
     return false;
@@ -142,44 +169,71 @@ bool cpu_has_avx512() {
 }  // namespace
 
 // The generator: NumPy's (key, pos) plus a window of tempered outputs.  buf = [kCarry carried outputs of the
-// previous block | 624 outputs of the current block]; [pos, end) are the unconsumed ones.
+// previous block | 624 outputs of the current block]; [pos, end) are the unconsumed ones.  The NEXT block is made
+// in small steps (gen_step) into nbuf / work while the current one is consumed.
 struct phet_mt {
-    alignas(64) uint32_t key[kN + 32];
-    alignas(64) uint32_t prev_key[kN + 32];
-    alignas(64) uint32_t buf[kCarry + kN + 32];
+    alignas(64) uint32_t key_a[kN + 32];
+    alignas(64) uint32_t key_b[kN + 32];
+    alignas(64) uint32_t buf_a[kCarry + kN + 32];
+    alignas(64) uint32_t buf_b[kCarry + kN + 32];
+    uint32_t *cur = key_a;    // state of the block being consumed
+    uint32_t *work = key_b;   // gstep == 0: state of the block BEFORE it; otherwise the next block in the making
+    uint32_t *buf = buf_a, *nbuf = buf_b;
     int pos = kCarry + kN, end = kCarry + kN;
+    int gstep = 0;            // 0 .. kGenSteps: progress of the next block
     bool avx512 = false;
 
     void load(const uint32_t *k, int p) {
-        memcpy(key, k, sizeof(uint32_t) * kN);
-        memset(key + kN, 0, sizeof(uint32_t) * 32);
-        memcpy(prev_key, key, sizeof(key));
-        fill_outputs();
-        pos = kCarry + p;
-        end = kCarry + kN;
-    }
-    void fill_outputs() {
+        cur = key_a;
+        work = key_b;
+        buf = buf_a;
+        nbuf = buf_b;
+        memcpy(cur, k, sizeof(uint32_t) * kN);
+        memset(cur + kN, 0, sizeof(uint32_t) * 32);
+        memcpy(work, cur, sizeof(uint32_t) * (kN + 32));
 #if PHET_X86
-        if (avx512) {
-            temper_avx512(key, buf + kCarry);
-            return;
-        }
-#endif
-        temper_scalar(key, buf + kCarry);
-    }
-    // fewer than kCarry outputs left: move them in front of a fresh block
-    void refill() {
-        const int rem = end - pos;
-        if (rem > 0) memmove(buf + kCarry - rem, buf + pos, sizeof(uint32_t) * (size_t)rem);
-        memcpy(prev_key, key, sizeof(uint32_t) * kN);
-#if PHET_X86
-        if (avx512) twist_avx512(key);
+        if (avx512) temper_avx512(cur, buf + kCarry);
         else
 #endif
-            twist_scalar(key);
-        fill_outputs();
+            temper_scalar(cur, buf + kCarry);
+        pos = kCarry + p;
+        end = kCarry + kN;
+        gstep = 0;
+    }
+    // one step of the next block (step 0 copies the state: `work` stops being the previous block's state, so it
+    // must not run while outputs of the previous block are still unread, pos < kCarry -- see state())
+    inline void gen_step() {
+        if (gstep == 0) {
+            memcpy(work, cur, sizeof(uint32_t) * kN);
+            gstep = 1;
+#if PHET_X86
+            if (avx512) return;
+#endif
+            twist_scalar(work);
+            temper_scalar(work, nbuf + kCarry);
+            gstep = kGenSteps;
+            return;
+        }
+#if PHET_X86
+        twist_step_avx512(work, nbuf + kCarry, gstep);
+#endif
+        ++gstep;
+    }
+    // between two trips of a scan: keep the next block ahead of the reader
+    inline void pump() {
+        if (pos < kCarry) return;
+        for (int s = 0; s < kPump && gstep < kGenSteps; ++s) gen_step();
+    }
+    // fewer than kCarry outputs left: finish the next block and put the leftovers in front of it
+    void refill() {
+        const int rem = end - pos;
+        while (gstep < kGenSteps) gen_step();
+        if (rem > 0) memmove(nbuf + kCarry - rem, buf + pos, sizeof(uint32_t) * (size_t)rem);
+        std::swap(buf, nbuf);
+        std::swap(cur, work);  // work now holds the state of the block just left: the "previous" state until step 0
         pos = kCarry - rem;
         end = kCarry + kN;
+        gstep = 0;
     }
     inline void ensure(int k) {  // k <= kCarry
         if (end - pos < k) refill();
@@ -190,10 +244,10 @@ struct phet_mt {
     }
     void state(uint32_t *k, int *p) const {
         if (pos >= kCarry) {
-            memcpy(k, key, sizeof(uint32_t) * kN);
+            memcpy(k, cur, sizeof(uint32_t) * kN);
             *p = pos - kCarry;  // 624: regenerate on the next draw (NumPy's convention)
-        } else {  // still inside the carried tail of the previous block
-            memcpy(k, prev_key, sizeof(uint32_t) * kN);
+        } else {  // still inside the carried tail of the previous block (gstep == 0: `work` is that block's state)
+            memcpy(k, work, sizeof(uint32_t) * kN);
             *p = kN - (kCarry - pos);
         }
     }
@@ -217,18 +271,16 @@ void shuffle_draws_scalar(phet_mt &e, uint32_t n, J *dst) {
 
 #if PHET_X86
 template <typename J>
-__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed(J *dst, __m512i v, __mmask16 keep, int cnt);
+MT_AVX512 inline void store_compressed(J *dst, __m512i v, __mmask16 keep, int cnt);
 
 template <>
-__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed<uint32_t>(uint32_t *dst, __m512i v,
-                                                                                           __mmask16 keep, int cnt) {
+MT_AVX512 inline void store_compressed<uint32_t>(uint32_t *dst, __m512i v, __mmask16 keep, int cnt) {
     const __m512i c = _mm512_maskz_compress_epi32(keep, v);
     _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << cnt) - 1u), c);
 }
 
 template <>
-__attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compressed<uint16_t>(uint16_t *dst, __m512i v,
-                                                                                           __mmask16 keep, int cnt) {
+MT_AVX512 inline void store_compressed<uint16_t>(uint16_t *dst, __m512i v, __mmask16 keep, int cnt) {
     const __m512i c = _mm512_maskz_compress_epi32(keep, v);
     _mm256_mask_storeu_epi16(dst, (__mmask16)((1u << cnt) - 1u), _mm512_cvtepi32_epi16(c));
 }
@@ -241,7 +293,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) inline void store_compresse
 constexpr uint32_t kScalarBelow = 96;  // the last draws of a permutation go one output at a time
 
 template <typename J, bool STORE>
-__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi,bmi2,popcnt"))) void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
+MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
     const __m512i lane = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
     const __m512i lanek[4] = {lane, _mm512_add_epi32(lane, _mm512_set1_epi32(16)), _mm512_add_epi32(lane, _mm512_set1_epi32(32)),
                               _mm512_add_epi32(lane, _mm512_set1_epi32(48))};
@@ -294,6 +346,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi,bmi2,popcnt"))) vo
             t += total;
             i -= total;
             e.pos += used;
+            e.pump();  // a few vectors of the next block: independent work for the slots the chain through i leaves idle
         }
     }
     for (; i >= 1; --i) {  // the tail, one output at a time
@@ -321,6 +374,122 @@ void shuffle_draws(phet_mt &e, uint32_t n, J *dst) {
     else shuffle_draws_scalar<J, false>(e, n, dst);
 }
 
+phet_mt *mt_alloc() {
+    void *mem = nullptr;
+    if (posix_memalign(&mem, 64, sizeof(phet_mt)) != 0 || !mem) return nullptr;
+    phet_mt *e = new (mem) phet_mt();
+    e->avx512 = cpu_has_avx512();
+    return e;
+}
+
+void mt_free(phet_mt *e) {
+    if (e) {
+        e->~phet_mt();
+        free(e);
+    }
+}
+
+inline void backoff(unsigned &spins) {
+    cpu_relax();
+    if ((++spins & 1023u) == 0) std::this_thread::yield();
+}
+
+struct PermDesc {
+    uint32_t n;
+    int32_t eb;
+    void *dst;
+    int64_t ticket;
+    int32_t pos;              // generator position at the start of this permutation ...
+    uint32_t key[kN];         // ... and its state (filled by the scanner)
+};
+
+}  // namespace
+
+// ---- parallel replay: one stream, two kinds of threads ---------------------------------------------------------
+//   scanner   the one sequential job: walks the permutations in order on the caller's generator with the count-only
+//             scan and records the generator state at the START of each one
+//   workers   take permutations in order and redo the scan from the recorded state with a generator of their own,
+//             this time compacting and storing the accepted targets
+struct phet_mt_par {
+    static constexpr size_t kQ = 1024;
+    phet_mt *mt = nullptr;
+    int64_t max_n = 0;
+    std::vector<PermDesc> desc = std::vector<PermDesc>(kQ);
+    std::unique_ptr<std::atomic<uint8_t>[]> done{new std::atomic<uint8_t>[kQ]};
+    alignas(64) std::atomic<uint64_t> submitted{0};
+    alignas(64) std::atomic<uint64_t> started{0};
+    alignas(64) std::atomic<uint64_t> claimed{0};
+    alignas(64) std::atomic<uint64_t> finished_prefix{0};
+    std::atomic<bool> closed{false};
+    std::mutex mu, prefix_mu;
+    std::condition_variable cv;
+    std::vector<int64_t> ticket_left;
+    std::thread tscan;
+    std::vector<std::thread> workers;
+
+    void scanner_main() {
+        unsigned spins = 0;
+        for (uint64_t k = 0;; ++k) {
+            while (k >= submitted.load(std::memory_order_acquire)) {
+                if (closed.load(std::memory_order_acquire) && k >= submitted.load(std::memory_order_acquire)) return;
+                backoff(spins);
+            }
+            PermDesc &d = desc[k & (kQ - 1)];
+            if (d.dst) {
+                int p = 0;
+                mt->state(d.key, &p);
+                d.pos = p;
+            }
+            started.store(k + 1, std::memory_order_release);
+            shuffle_draws<uint16_t>(*mt, d.n, (uint16_t *)nullptr);
+        }
+    }
+
+    void finish(uint64_t k, int64_t ticket) {
+        done[k & (kQ - 1)].store(1, std::memory_order_release);
+        {
+            std::lock_guard<std::mutex> lk(prefix_mu);
+            uint64_t f = finished_prefix.load(std::memory_order_relaxed);
+            while (done[f & (kQ - 1)].load(std::memory_order_acquire)) {
+                done[f & (kQ - 1)].store(0, std::memory_order_relaxed);
+                ++f;
+            }
+            finished_prefix.store(f, std::memory_order_release);
+        }
+        bool last;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            last = --ticket_left[(size_t)ticket] == 0;
+        }
+        if (last) cv.notify_all();
+    }
+
+    void worker_main() {
+        phet_mt *local = mt_alloc();
+        unsigned spins = 0;
+        for (;;) {
+            uint64_t k = claimed.load(std::memory_order_relaxed);
+            if (k >= started.load(std::memory_order_acquire)) {
+                if (closed.load(std::memory_order_acquire) && k >= submitted.load(std::memory_order_acquire)) break;
+                backoff(spins);
+                continue;
+            }
+            if (!claimed.compare_exchange_weak(k, k + 1, std::memory_order_acq_rel)) continue;
+            const PermDesc &d = desc[k & (kQ - 1)];
+            const int64_t ticket = d.ticket;
+            if (d.dst && d.n >= 2 && local) {
+                local->load(d.key, d.pos);
+                if (d.eb == 2) shuffle_draws<uint16_t>(*local, d.n, static_cast<uint16_t *>(d.dst));
+                else shuffle_draws<uint32_t>(*local, d.n, static_cast<uint32_t *>(d.dst));
+            }
+            finish(k, ticket);
+        }
+        mt_free(local);
+    }
+};
+
+namespace {
+
 #define MT_REQUIRE(cond, msg)                                    \
     do {                                                         \
         if (!(cond)) {                                           \
@@ -329,6 +498,17 @@ void shuffle_draws(phet_mt &e, uint32_t n, J *dst) {
         }                                                        \
     } while (0)
 
+int check_jobs(const phet_mt_job *jobs, int32_t n_jobs, int64_t max_n) {
+    for (int k = 0; k < n_jobs; ++k) {
+        MT_REQUIRE(jobs[k].n >= 1 && jobs[k].n <= max_n, "permutation length out of range");
+        MT_REQUIRE(jobs[k].elem_bytes == 2 || jobs[k].elem_bytes == 4, "elem_bytes must be 2 or 4");
+        MT_REQUIRE(jobs[k].elem_bytes == 4 || jobs[k].n <= 65536, "16-bit draws need n <= 65536");
+        MT_REQUIRE(jobs[k].out == nullptr || jobs[k].stride_bytes >= (jobs[k].n - 1) * jobs[k].elem_bytes,
+                   "stride shorter than one permutation's draws");
+    }
+    return PHET_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -336,13 +516,11 @@ extern "C" {
 int phet_mt_create(const uint32_t *key, int32_t pos, phet_mt **out) {
     MT_REQUIRE(key != nullptr && out != nullptr, "NULL argument");
     MT_REQUIRE(pos >= 0 && pos <= kN, "MT19937 position must be in [0, 624]");
-    void *mem = nullptr;
-    if (posix_memalign(&mem, 64, sizeof(phet_mt)) != 0 || !mem) {
+    phet_mt *e = mt_alloc();
+    if (!e) {
         phet::set_error("out of host memory");
         return PHET_ERR_NOMEM;
     }
-    phet_mt *e = new (mem) phet_mt();
-    e->avx512 = cpu_has_avx512();
     e->load(key, pos);
     *out = e;
     return PHET_OK;
@@ -357,10 +535,7 @@ int phet_mt_state(const phet_mt *e, uint32_t *key_out, int32_t *pos_out) {
 }
 
 int phet_mt_destroy(phet_mt *e) {
-    if (e) {
-        e->~phet_mt();
-        free(e);
-    }
+    mt_free(e);
     return PHET_OK;
 }
 
@@ -368,13 +543,7 @@ int phet_mt_simd(const phet_mt *e) { return e ? (e->avx512 ? 512 : 0) : (cpu_has
 
 int phet_mt_shuffle_rounds(phet_mt *e, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds) {
     MT_REQUIRE(e != nullptr && jobs != nullptr && n_jobs >= 1 && rounds >= 0, "bad arguments");
-    for (int k = 0; k < n_jobs; ++k) {
-        MT_REQUIRE(jobs[k].n >= 1 && jobs[k].n <= (int64_t)0xFFFFFFFFll, "permutation length must be in [1, 2^32)");
-        MT_REQUIRE(jobs[k].elem_bytes == 2 || jobs[k].elem_bytes == 4, "elem_bytes must be 2 or 4");
-        MT_REQUIRE(jobs[k].elem_bytes == 4 || jobs[k].n <= 65536, "16-bit draws need n <= 65536");
-        MT_REQUIRE(jobs[k].out == nullptr || jobs[k].stride_bytes >= (jobs[k].n - 1) * jobs[k].elem_bytes,
-                   "stride shorter than one permutation's draws");
-    }
+    if (int rc = check_jobs(jobs, n_jobs, ((int64_t)1 << 31) - 1)) return rc;
     for (int64_t r = 0; r < rounds; ++r) {
         for (int k = 0; k < n_jobs; ++k) {
             const phet_mt_job &j = jobs[k];
@@ -424,6 +593,75 @@ int phet_host_fisher_yates(const void *draws, int32_t elem_bytes, int64_t n, int
     }
     memcpy(out, x, sizeof(uint32_t) * (size_t)take);
     free(x);
+    return PHET_OK;
+}
+
+// ---- parallel replay ------------------------------------------------------------------------------------------
+int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par **out) {
+    MT_REQUIRE(mt != nullptr && out != nullptr, "NULL argument");
+    MT_REQUIRE(max_n >= 1 && max_n < ((int64_t)1 << 31), "max_n must be in [1, 2^31)");
+    *out = nullptr;
+    if (workers <= 0) {
+        workers = 4;
+        if (const char *w = getenv("PHET_REPLAY_WORKERS")) workers = atoi(w) > 0 ? atoi(w) : 4;
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (unsigned)workers + 2 > hw) workers = hw > 2 ? (int)hw - 2 : 1;
+    }
+    phet_mt_par *p = new (std::nothrow) phet_mt_par();
+    if (!p) {
+        phet::set_error("out of host memory");
+        return PHET_ERR_NOMEM;
+    }
+    p->mt = mt;
+    p->max_n = max_n;
+    for (size_t i = 0; i < phet_mt_par::kQ; ++i) p->done[i].store(0, std::memory_order_relaxed);
+    p->tscan = std::thread(&phet_mt_par::scanner_main, p);
+    for (int w = 0; w < workers; ++w) p->workers.emplace_back(&phet_mt_par::worker_main, p);
+    *out = p;
+    return PHET_OK;
+}
+
+int phet_mt_par_submit(phet_mt_par *p, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds, int64_t *ticket_out) {
+    MT_REQUIRE(p != nullptr && jobs != nullptr && n_jobs >= 1 && rounds >= 0 && ticket_out != nullptr, "bad arguments");
+    MT_REQUIRE(!p->closed.load(), "the replay is already closed");
+    if (int rc = check_jobs(jobs, n_jobs, p->max_n)) return rc;
+    int64_t ticket;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        ticket = (int64_t)p->ticket_left.size();
+        p->ticket_left.push_back(rounds * n_jobs);
+    }
+    *ticket_out = ticket;
+    uint64_t k = p->submitted.load(std::memory_order_relaxed);
+    unsigned spins = 0;
+    for (int64_t r = 0; r < rounds; ++r) {
+        for (int j = 0; j < n_jobs; ++j) {
+            while (k - p->finished_prefix.load(std::memory_order_acquire) >= phet_mt_par::kQ - 1) backoff(spins);
+            PermDesc &d = p->desc[k & (phet_mt_par::kQ - 1)];
+            d.n = (uint32_t)jobs[j].n;
+            d.eb = jobs[j].elem_bytes;
+            d.dst = jobs[j].out ? static_cast<unsigned char *>(jobs[j].out) + (size_t)r * (size_t)jobs[j].stride_bytes : nullptr;
+            d.ticket = ticket;
+            p->submitted.store(++k, std::memory_order_release);
+        }
+    }
+    return PHET_OK;
+}
+
+int phet_mt_par_wait(phet_mt_par *p, int64_t ticket) {
+    MT_REQUIRE(p != nullptr, "NULL argument");
+    std::unique_lock<std::mutex> lk(p->mu);
+    MT_REQUIRE(ticket >= 0 && (size_t)ticket < p->ticket_left.size(), "unknown ticket");
+    p->cv.wait(lk, [&] { return p->ticket_left[(size_t)ticket] == 0; });
+    return PHET_OK;
+}
+
+int phet_mt_par_end(phet_mt_par *p) {
+    if (!p) return PHET_OK;
+    p->closed.store(true, std::memory_order_release);
+    p->tscan.join();  // the caller's generator is now where the reference's stream would be
+    for (std::thread &w : p->workers) w.join();
+    delete p;
     return PHET_OK;
 }
 

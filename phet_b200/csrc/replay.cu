@@ -100,42 +100,68 @@ static DrawLayout draw_layout(int64_t n0, int64_t n1) {
     return L;
 }
 
+// Draw thread: feeds the blocks, in stream order, to the parallel replay (csrc/mt_replay.cpp: generator / scanner /
+// store workers) as ring slots become free, and publishes each storing block once its targets are complete.
 static void producer_main(ReplayRing *r, phet_mt *mt, std::vector<ReplayBlock> blocks, DrawLayout L, int64_t n0, int64_t n1) {
-    int64_t stored = 0;
-    for (size_t b = 0; b < blocks.size(); ++b) {
-        const ReplayBlock &blk = blocks[b];
-        unsigned char *dst = nullptr;
-        if (blk.store) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    phet_mt_par *par = nullptr;
+    int rc = phet_mt_par_begin(mt, 0, n0 > n1 ? n0 : n1, &par);
+    std::vector<int64_t> tickets(blocks.size(), -1);
+    size_t ns = 0, nw = 0;       // blocks submitted / completed
+    int64_t stored_sub = 0, stored_done = 0;
+    bool aborted = false;
+    while (rc == 0 && nw < blocks.size() && !aborted) {
+        // submit whatever has a slot to land in
+        while (ns < blocks.size()) {
+            const ReplayBlock &blk = blocks[ns];
+            unsigned char *dst = nullptr;
+            if (blk.store) {
+                std::lock_guard<std::mutex> lk(r->mu);
+                if (r->abort) {
+                    aborted = true;
+                    break;
+                }
+                if (stored_sub - r->released >= ReplayRing::kSlots) break;
+                dst = r->slot[stored_sub % ReplayRing::kSlots];
+                ++stored_sub;
+            }
+            phet_mt_job jobs[2];
+            jobs[0].n = n0;
+            jobs[0].out = dst;
+            jobs[0].stride_bytes = L.ld0 * L.eb0;
+            jobs[0].elem_bytes = L.eb0;
+            jobs[1].n = n1;
+            jobs[1].out = dst ? dst + L.off1(blk.count) : nullptr;
+            jobs[1].stride_bytes = L.ld1 * L.eb1;
+            jobs[1].elem_bytes = L.eb1;
+            rc = phet_mt_par_submit(par, jobs, 2, blk.count, &tickets[ns]);
+            if (rc != 0) break;
+            ++ns;
+        }
+        if (rc != 0 || aborted) break;
+        if (nw < ns) {
+            rc = phet_mt_par_wait(par, tickets[nw]);
+            if (rc != 0) break;
+            {
+                std::lock_guard<std::mutex> lk(r->mu);
+                if (blocks[nw].store) r->produced = ++stored_done;
+                r->blocks_done = (int64_t)nw + 1;
+            }
+            r->cv.notify_all();
+            ++nw;
+        } else {  // nothing in flight and no free slot: wait for the consumer to hand one back
             std::unique_lock<std::mutex> lk(r->mu);
-            r->cv.wait(lk, [&] { return r->abort || stored - r->released < ReplayRing::kSlots; });
-            if (r->abort) return;
-            dst = r->slot[stored % ReplayRing::kSlots];
-        } else {
-            std::lock_guard<std::mutex> lk(r->mu);
-            if (r->abort) return;
+            r->cv.wait(lk, [&] { return r->abort || stored_sub - r->released < ReplayRing::kSlots; });
+            if (r->abort) aborted = true;
         }
-        const auto t0 = std::chrono::steady_clock::now();
-        phet_mt_job jobs[2];
-        jobs[0].n = n0;
-        jobs[0].out = dst;
-        jobs[0].stride_bytes = L.ld0 * L.eb0;
-        jobs[0].elem_bytes = L.eb0;
-        jobs[1].n = n1;
-        jobs[1].out = dst ? dst + L.off1(blk.count) : nullptr;
-        jobs[1].stride_bytes = L.ld1 * L.eb1;
-        jobs[1].elem_bytes = L.eb1;
-        const int rc = phet_mt_shuffle_rounds(mt, jobs, 2, blk.count);
-        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        {
-            std::lock_guard<std::mutex> lk(r->mu);
-            r->host_seconds += dt;
-            if (rc != 0) r->error = rc;
-            if (blk.store) r->produced = ++stored;
-            r->blocks_done = (int64_t)b + 1;
-        }
-        r->cv.notify_all();
-        if (rc != 0) return;
     }
+    if (par) phet_mt_par_end(par);  // joins its threads; the stream's final state goes back into mt
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        r->host_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        if (rc != 0) r->error = rc;
+    }
+    r->cv.notify_all();
 }
 
 // Wait for the next storing block, upload it, and return the device pointers of its two halves.

@@ -25,3 +25,9 @@ for _ in range(100):
     np.random.permutation(n)
 dt = time.perf_counter() - t
 print("np.random.permutation(25000): %.1f us" % (dt / 100 * 1e6))
+for workers in (1, 2, 4, 6):
+    out = None
+    t = time.perf_counter()
+    mt.shuffle_draws([n, n], rounds, workers=workers, chunks=8)
+    dt = time.perf_counter() - t
+    print("parallel replay, %d store workers: %.2f us/permutation -> config 4: %.3f s" % (workers, dt / (2 * rounds) * 1e6, dt / (2 * rounds) * 62000))

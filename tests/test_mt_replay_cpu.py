@@ -112,3 +112,32 @@ def test_scalar_and_avx512_scans_agree():
         outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, check=True).stdout.split())
     assert outs[1][0] == "0"
     assert outs[0][1:] == outs[1][1:]
+
+
+@pytest.mark.parametrize("sizes,rounds,chunks", [([25000, 25000], 40, 5), ([300, 45], 500, 7), ([100000, 70000], 6, 2),
+                                                 ([1, 2, 3], 50, 3), ([65536, 65537], 4, 1)])
+def test_parallel_replay_equals_sequential(sizes, rounds, chunks):
+    """Generator / scanner / store-worker threads against the one-thread scan: same targets, same final state --
+    which the tests above tie to np.random itself."""
+    for burn in (0, 311):
+        np.random.seed(4242)
+        if burn:
+            np.random.randint(0, 2 ** 31 - 1, size=burn)
+        a, b = _mt(), _mt()
+        da = a.shuffle_draws(sizes, rounds)
+        db = b.shuffle_draws(sizes, rounds, workers=3, chunks=chunks)
+        for x, y in zip(da, db):
+            assert np.array_equal(x, y)
+        ka, pa = a.state()
+        kb, pb = b.state()
+        assert np.array_equal(ka, kb) and pa == pb
+        # and the stream goes on identically
+        assert np.array_equal(a.permutation(1000), b.permutation(1000))
+
+
+def test_parallel_replay_skip_blocks_only_advance():
+    np.random.seed(8)
+    a, b = _mt(), _mt()
+    a.shuffle_draws([5000, 4000], 30, store=False)
+    b.shuffle_draws([5000, 4000], 30, store=False, workers=2, chunks=3)
+    assert np.array_equal(a.state()[0], b.state()[0]) and a.state()[1] == b.state()[1]
