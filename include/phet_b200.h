@@ -40,7 +40,9 @@ typedef enum {
 typedef enum { PHET_F32 = 0, PHET_F64 = 1 } phet_dtype;
 typedef enum { PHET_NORM_NONE = 0, PHET_NORM_ZSCORE = 1 } phet_normalize;
 typedef enum { PHET_TEST_T = 0, PHET_TEST_Z = 1 } phet_test;          /* phet.py:425-428 */
-typedef enum { PHET_PERM_HOST = 0, PHET_PERM_DEVICE = 1, PHET_PERM_REPLAY = 2 } phet_perm_mode;
+/* PHET_PERM_RESIDENT: reuse the permutation tables a previous call left in HBM (a PHET_PERM_HOST upload, or a
+ * PHET_PERM_REPLAY pipeline run with keep_perm_tables) -- the "inputs already resident" case of a benchmark. */
+typedef enum { PHET_PERM_HOST = 0, PHET_PERM_DEVICE = 1, PHET_PERM_REPLAY = 2, PHET_PERM_RESIDENT = 3 } phet_perm_mode;
 typedef struct phet_mt phet_mt;  /* NumPy's legacy global stream, held natively (see below) */
 
 /* Device buffers a caller may want to wrap (e.g. for an NCCL all-reduce).  phet_device_ptr. */
@@ -173,6 +175,7 @@ typedef struct {
     int32_t draw_index_sets;
     int64_t S_draw;
     int32_t *idx_out;
+    int32_t keep_perm_tables;              /* PHET_PERM_REPLAY: keep the tables of genes [g3_begin, g3_end) for PHET_PERM_RESIDENT */
 } phet_pipeline_params;
 
 int phet_run_pipeline(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G, int dtype,
@@ -355,6 +358,10 @@ int phet_fy_apply(phet_ctx *ctx, const void *draws, int32_t elem_bytes, int64_t 
  * np.random.choice(rows, m, replace=False) returns -- installed like phet_set_index_sets.  idx_out: host
  * int32[S][2][m] (ORIGINAL row numbers) or NULL.  Requires phet_set_classes. */
 int phet_draw_index_sets(phet_ctx *ctx, phet_mt *mt, int64_t S, int64_t m, int32_t *idx_out);
+/* Device milliseconds of the last phet_run_pipeline call on a DEVICE matrix (one gene block): out[0] normalise +
+ * transpose, out[1] Step 1, out[2] Step 3 (incl. the device Fisher-Yates in replay mode), from CUDA events recorded
+ * on the context's stream between the phases (synchronises).  Host matrices interleave the phases per block: -1. */
+int phet_phase_ms(phet_ctx *ctx, float out[3]);
 /* out[0]: host seconds the draw thread spent in the last replay; out[1]: seconds the issuing thread waited for it. */
 int phet_replay_stats(phet_ctx *ctx, double out[2]);
 

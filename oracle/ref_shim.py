@@ -24,7 +24,10 @@ import types
 import numpy as np
 from scipy import stats as _stats
 
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.sh (git-ignored copy)
 REFERENCE_SRC = os.environ.get("PHET_REFERENCE_SRC", "/root/reference/src")
+if not os.path.isfile(os.path.join(REFERENCE_SRC, "model", "phet.py")) and os.path.isfile(os.path.join(_VENDORED, "model", "phet.py")):
+    REFERENCE_SRC = _VENDORED   # the GPU box: the unmodified file as vendored by the build step
 
 
 def ztest_restated(x1, x2=None, value=0, alternative="two-sided", usevar="pooled", ddof=1.0):

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libphet_b200.so")
 PHET_F32, PHET_F64 = 0, 1
 NORM_NONE, NORM_ZSCORE = 0, 1
 TEST_T, TEST_Z = 0, 1
-PERM_HOST, PERM_DEVICE, PERM_REPLAY = 0, 1, 2
+PERM_HOST, PERM_DEVICE, PERM_REPLAY, PERM_RESIDENT = 0, 1, 2, 3
 OPT_KEEP_H = 1
 OPT_STEP3_MIN_SIZE = 2
 (BUF_ACC, BUF_O, BUF_H, BUF_P, BUF_DELTA, BUF_F, BUF_R, BUF_BINS, BUF_SCORES, BUF_XG, BUF_MEAN,
@@ -31,7 +31,7 @@ EXPORTS = [
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
     "phet_mt_create", "phet_mt_state", "phet_mt_destroy", "phet_mt_simd", "phet_mt_shuffle_rounds", "phet_mt_bounded",
     "phet_mt_par_begin", "phet_mt_par_submit", "phet_mt_par_wait", "phet_mt_par_end",
-    "phet_host_fisher_yates", "phet_fy_apply", "phet_replay_stats", "phet_draw_index_sets",
+    "phet_host_fisher_yates", "phet_fy_apply", "phet_replay_stats", "phet_draw_index_sets", "phet_phase_ms",
 ]
 
 
@@ -55,7 +55,8 @@ class PipelineParams(C.Structure):
                 ("step1", Step1Params), ("m", C.c_int64), ("perm_mode", C.c_int32), ("seed", C.c_uint64),
                 ("perm_ctrl", C.c_void_p), ("perm_case", C.c_void_p), ("table_full", C.c_void_p),
                 ("table_last", C.c_void_p), ("n_last", C.c_int64), ("block_genes", C.c_int64),
-                ("mt", C.c_void_p), ("draw_index_sets", C.c_int32), ("S_draw", C.c_int64), ("idx_out", C.c_void_p)]
+                ("mt", C.c_void_p), ("draw_index_sets", C.c_int32), ("S_draw", C.c_int64), ("idx_out", C.c_void_p),
+                ("keep_perm_tables", C.c_int32)]
 
 
 class MtJob(C.Structure):
@@ -148,6 +149,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_fy_apply.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp]
     lib.phet_replay_stats.argtypes = [vp, C.POINTER(dbl)]
     lib.phet_draw_index_sets.argtypes = [vp, vp, i64, i64, vp]
+    lib.phet_phase_ms.argtypes = [vp, C.POINTER(C.c_float)]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.phet_abi_version() != 1:
@@ -423,7 +425,7 @@ class Context:
         _check(self.lib.phet_step1(self.h, s_begin, s_end, C.byref(params), 1 if accumulate else 0))
 
     def step3(self, g_begin, g_end, m, table_full, table_last, n_last, perm_ctrl=None, perm_case=None,
-              seed=0):
+              seed=0, resident_perms=False):
         tf = np.ascontiguousarray(table_full, dtype=np.float64)
         tl = np.ascontiguousarray(table_last, dtype=np.float64)
         if perm_ctrl is not None:
@@ -431,6 +433,8 @@ class Context:
             pk = np.ascontiguousarray(perm_case, dtype=np.uint32)
             _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_HOST, _ptr(pc), _ptr(pk), 0, _ptr(tf),
                                        _ptr(tl), n_last))
+        elif resident_perms:
+            _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_RESIDENT, None, None, 0, _ptr(tf), _ptr(tl), n_last))
         else:
             _check(self.lib.phet_step3(self.h, g_begin, g_end, m, PERM_DEVICE, None, None, seed, _ptr(tf),
                                        _ptr(tl), n_last))
@@ -438,7 +442,7 @@ class Context:
     def run_pipeline(self, X, N, G, dtype, params: Step1Params, m, table_full, table_last, n_last,
                      g_range=None, s_range=None, g3_range=None, normalize=NORM_ZSCORE, storage=None,
                      perm_ctrl=None, perm_case=None, seed=0, is_device=False, block_genes=0, mt=None,
-                     replay_perms=False, draw_index_sets=None):
+                     replay_perms=False, draw_index_sets=None, keep_perm_tables=False, resident_perms=False):
         """Stage 0 + Step 1 + Step 3 over gene blocks.  X: C-contiguous host ndarray (N, G) or, with
         is_device=True, a raw device pointer (int).  ``mt`` (an MtStream) + ``replay_perms=True``: the Step-3
         permutations are the reference's own draws (PHET_PERM_REPLAY); ``draw_index_sets=(S, keep)``: the index
@@ -472,6 +476,9 @@ class Context:
             pp.perm_mode, pp.perm_ctrl, pp.perm_case = PERM_HOST, pc.ctypes.data, pk.ctypes.data
         elif replay_perms:
             pp.perm_mode = PERM_REPLAY
+            pp.keep_perm_tables = 1 if keep_perm_tables else 0
+        elif resident_perms:
+            pp.perm_mode = PERM_RESIDENT
         else:
             pp.perm_mode, pp.seed = PERM_DEVICE, seed
         pp.block_genes = block_genes
@@ -495,6 +502,12 @@ class Context:
         _check(self.lib.phet_draw_index_sets(self.h, mt.h, int(S), int(m), _ptr(idx)))
         self.S, self.m = int(S), int(m)
         return idx
+
+    def phase_ms(self):
+        """(normalise, Step 1, Step 3) device milliseconds of the last device-matrix pipeline call (-1: not available)."""
+        out = (C.c_float * 3)()
+        _check(self.lib.phet_phase_ms(self.h, out))
+        return float(out[0]), float(out[1]), float(out[2])
 
     def replay_stats(self):
         out = (C.c_double * 2)()

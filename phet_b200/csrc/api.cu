@@ -232,6 +232,10 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.h_ld = c->n_slices;
     a.g_begin = g_begin;
     a.g_end = g_end;
+    if (perm_mode == PHET_PERM_RESIDENT) {
+        PHET_REQUIRE(g_begin >= c->perm_g0 && g_end <= c->perm_g0 + c->perm_rows, "PHET_PERM_RESIDENT: genes outside the resident tables");
+        perm_mode = PHET_PERM_HOST;
+    }
     a.perm_mode = perm_mode;
     a.perm0 = c->perm0.p;
     a.perm1 = c->perm1.p;
@@ -255,6 +259,12 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
         return launch_ks_big(c, a, c->n_slices > 1 ? 1 : 0);
     }
     return c->storage == PHET_F32 ? run_step3_f32(c, a) : run_step3_f64(c, a);
+}
+
+int phase_mark(phet_ctx *c, int k) {
+    if (!c->ev_phase[k]) PHET_CUDA(cudaEventCreate(&c->ev_phase[k]));
+    PHET_CUDA(cudaEventRecord(c->ev_phase[k], c->stream));
+    return PHET_OK;
 }
 
 }  // namespace phet
@@ -387,6 +397,8 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->rank_in.release();
     c->stage[0].release();
     c->stage[1].release();
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_phase[i]) cudaEventDestroy(c->ev_phase[i]);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
@@ -612,9 +624,13 @@ namespace phet {
 int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,
                          const double *table_full, const double *table_last, int64_t n_last) {
     PHET_REQUIRE(m >= 1 && m <= 512, "slice length m must be in [1, 512]");
-    PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE || perm_mode == PHET_PERM_REPLAY, "bad perm_mode");
+    PHET_REQUIRE(perm_mode == PHET_PERM_HOST || perm_mode == PHET_PERM_DEVICE || perm_mode == PHET_PERM_REPLAY ||
+                     perm_mode == PHET_PERM_RESIDENT, "bad perm_mode");
     PHET_REQUIRE(table_full && table_last, "KS tables are NULL");
-    c->perm_g0 = 0;
+    if (perm_mode != PHET_PERM_RESIDENT) {
+        c->perm_g0 = 0;
+        c->perm_rows = 0;
+    }
     int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
     int64_t n_slices = (min_c + m - 1) / m;
     if (c->step3_min_size > 0) {
@@ -673,6 +689,11 @@ int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ct
         PHET_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PHET_CUDA(cudaStreamSynchronize(c->stream));
         PHET_REQUIRE(hbad == 0, "host permutations contain a position outside its class");
+        c->perm_rows = c->G;
+        c->perm_cols = min_c;
+    } else if (perm_mode == PHET_PERM_RESIDENT) {
+        PHET_REQUIRE(c->perm_rows > 0 && c->perm_cols == min_c && c->perm0.p && c->perm1.p,
+                     "PHET_PERM_RESIDENT: no permutation tables of this shape are resident");
     } else if (perm_mode == PHET_PERM_REPLAY) {
         // the permutation tables are filled block by block on the device (replay.cu)
     } else {
@@ -722,6 +743,7 @@ int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int6
     PHET_REQUIRE(p->g_begin <= p->g3_begin && p->g3_begin <= p->g3_end && p->g3_end <= p->g_end,
                  "Step-3 gene range must lie inside the loaded gene range");
     if (int e = prepare_matrix(c, N, G, dtype, p->normalize, p->storage, p->g_begin, p->g_end)) return e;
+    c->phases_valid = false;
     const phet_quantile_pos &q = p->step1.q;
     PHET_REQUIRE(q.j_lo >= 0 && q.k_lo < c->m && q.j_hi >= 0 && q.k_hi < c->m && q.j_lo <= q.k_lo && q.j_hi <= q.k_hi,
                  "quantile positions outside [0, m)");
@@ -745,8 +767,15 @@ int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int6
     if (gcount > 0) {
         if (is_device) {
             const unsigned char *Xb = static_cast<const unsigned char *>(X) + (size_t)p->g_begin * e_in;
+            if (int e = phase_mark(c, 0)) return e;
             if (int e = compute_block(Xb, G, p->g_begin, gcount)) return e;
-            if (int e = steps_block(p->g_begin, gcount)) return e;
+            if (int e = phase_mark(c, 1)) return e;
+            if (int e = launch_step1(c, p->g_begin, p->g_end, p->s_begin, p->s_end, &p->step1, 0)) return e;
+            if (int e = phase_mark(c, 2)) return e;
+            if (p->g3_end > p->g3_begin)
+                if (int e = launch_step3(c, p->g3_begin, p->g3_end, p->m, p->perm_mode, p->seed, p->n_last)) return e;
+            if (int e = phase_mark(c, 3)) return e;
+            c->phases_valid = true;
         } else {
             if (!c->copy_stream) PHET_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
             for (int i = 0; i < 2; ++i) {
@@ -786,6 +815,16 @@ int phet_run_pipeline(phet_ctx *c, const void *X, int is_device, int64_t N, int6
     // permutations leaves nothing of the caller's in flight, so the call returns with the work queued
     if (!is_device || p->perm_mode == PHET_PERM_HOST) PHET_CUDA(cudaStreamSynchronize(c->stream));
     c->matrix_set = true;
+    return PHET_OK;
+}
+
+int phet_phase_ms(phet_ctx *c, float out[3]) {
+    PHET_REQUIRE(c != nullptr && out != nullptr, "NULL argument");
+    out[0] = out[1] = out[2] = -1.0f;
+    if (!c->phases_valid) return PHET_OK;
+    PHET_CUDA(cudaSetDevice(c->device));
+    PHET_CUDA(cudaEventSynchronize(c->ev_phase[3]));
+    for (int k = 0; k < 3; ++k) PHET_CUDA(cudaEventElapsedTime(&out[k], c->ev_phase[k], c->ev_phase[k + 1]));
     return PHET_OK;
 }
 

@@ -136,6 +136,9 @@ struct phet_ctx {
     phet::DevBuf<int32_t> H;             // [G][n_slices]
     phet::DevBuf<uint32_t> perm0, perm1; // [genes from perm_g0][min_c] (host mode: all G genes; replay mode: one block)
     int64_t perm_g0 = 0;
+    int64_t perm_rows = 0, perm_cols = 0;  // resident tables: genes [perm_g0, perm_g0 + perm_rows) x perm_cols positions (0: none)
+    cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool phases_valid = false;
     phet::DevBuf<double> tab_full, tab_last;
     phet::DevBuf<double> f, r, fw, scores;   // [G]
     phet::DevBuf<signed char> bins;      // [G]
@@ -198,6 +201,7 @@ int finish_index_sets(phet_ctx *c, int64_t S, int64_t m);   // c->idx holds ORIG
 int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, int64_t G, int dtype,
                         const phet_pipeline_params *p);
 void replay_ring_destroy(phet_ctx *c);
+int phase_mark(phet_ctx *c, int k);   // record phase event k on the stream (creates the events on first use)
 int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
                  int capture_debug, int kruskal);
 int mtx_parse(const char *path, int threads, phet_mtx &m);

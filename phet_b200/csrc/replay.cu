@@ -226,6 +226,7 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
     PHET_REQUIRE(0 <= p->s_begin && p->s_begin <= p->s_end && p->s_end <= S, "subsample range outside [0, S]");
     PHET_REQUIRE(c->step3_min_size == 0, "replay mode serves the two-class fit (PHET_OPT_STEP3_MIN_SIZE must be 0)");
     if (int e = prepare_matrix(c, N, G, dtype, p->normalize, p->storage, p->g_begin, p->g_end)) return e;
+    c->phases_valid = false;
     const phet_quantile_pos &q = p->step1.q;
     PHET_REQUIRE(q.j_lo >= 0 && q.k_lo < m && q.j_hi >= 0 && q.k_hi < m && q.j_lo <= q.k_lo && q.j_hi <= q.k_hi,
                  "quantile positions outside [0, m)");
@@ -337,10 +338,11 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
     }
 
     // ---- matrix blocks: normalise + Step 1, then the Step-3 blocks of those genes as their draws arrive
+    const bool keep = replay3 && p->keep_perm_tables != 0;
     if (replay3) {
-        const int64_t rows = rounds_per_block < max_count ? rounds_per_block : max_count;
-        if (int e = c->perm0.alloc((size_t)rows * (size_t)min_c)) return fail(e);
-        if (int e = c->perm1.alloc((size_t)rows * (size_t)min_c)) return fail(e);
+        const int64_t rows = keep ? (p->g3_end - p->g3_begin) : (rounds_per_block < max_count ? rounds_per_block : max_count);
+        if (int e = c->perm0.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
+        if (int e = c->perm1.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
     }
     auto step3_blocks = [&](int64_t x0, int64_t x1) -> int {
         if (!replay3) {
@@ -354,9 +356,10 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
             if (blk.first >= x1) break;        // belongs to a later matrix block
             const unsigned char *d0, *d1;
             if (int e = cons.take(blk.count, &d0, &d1)) return e;
-            if (int e = launch_fy_apply(c, d0, L.eb0, L.ld0, n0, blk.count, min_c, c->cls_pos.p, c->perm0.p, min_c, c->stream)) return e;
-            if (int e = launch_fy_apply(c, d1, L.eb1, L.ld1, n1, blk.count, min_c, c->cls_pos.p + n0, c->perm1.p, min_c, c->stream)) return e;
-            c->perm_g0 = blk.first;
+            const size_t row0 = keep ? (size_t)(blk.first - p->g3_begin) * (size_t)min_c : 0;  // kept tables: one row per gene of the range
+            if (int e = launch_fy_apply(c, d0, L.eb0, L.ld0, n0, blk.count, min_c, c->cls_pos.p, c->perm0.p + row0, min_c, c->stream)) return e;
+            if (int e = launch_fy_apply(c, d1, L.eb1, L.ld1, n1, blk.count, min_c, c->cls_pos.p + n0, c->perm1.p + row0, min_c, c->stream)) return e;
+            c->perm_g0 = keep ? p->g3_begin : blk.first;
             if (int e = launch_step3(c, blk.first, blk.first + blk.count, m, PHET_PERM_HOST, 0, p->n_last)) return e;
         }
         return 0;
@@ -364,9 +367,14 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
     if (gcount > 0) {
         if (is_device) {
             const unsigned char *Xb = static_cast<const unsigned char *>(X) + (size_t)p->g_begin * e_in;
+            if (int e = phase_mark(c, 0)) return fail(e);
             if (int e = launch_normalize(c, Xb, G, p->g_begin, gcount, dtype, p->normalize)) return fail(e);
+            if (int e = phase_mark(c, 1)) return fail(e);
             if (int e = launch_step1(c, p->g_begin, p->g_end, p->s_begin, p->s_end, &p->step1, 0)) return fail(e);
+            if (int e = phase_mark(c, 2)) return fail(e);
             if (int e = step3_blocks(p->g_begin, p->g_end)) return fail(e);
+            if (int e = phase_mark(c, 3)) return fail(e);
+            c->phases_valid = true;
         } else {
             int b = 0;
             for (int64_t g0 = p->g_begin; g0 < p->g_end; g0 += gb, ++b) {
@@ -390,7 +398,14 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
         set_error("invalid: the draw thread failed");
         return r->error;
     }
-    c->perm_g0 = 0;
+    if (keep) {
+        c->perm_g0 = p->g3_begin;
+        c->perm_rows = p->g3_end - p->g3_begin;
+        c->perm_cols = min_c;
+    } else {
+        c->perm_g0 = 0;
+        c->perm_rows = 0;
+    }
     c->replay_host_s = r->host_seconds;
     c->replay_wait_s = cons.wait_s;
     PHET_CUDA(cudaStreamSynchronize(c->stream));  // pinned slots and the caller's matrix are no longer read

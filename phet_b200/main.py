@@ -26,16 +26,15 @@ import pandas as pd
 SEED = 12345  # train.py:26
 
 
-def load_dataset(dspath: str, file_name: str):
-    """train.py:47-84 for the files PHet needs.  MatrixMarket coordinate file, cells x genes,
-    densified as float32 (scanpy's read_mtx default dtype)."""
-    from scipy.io import mmread
-    X = mmread(os.path.join(dspath, file_name + "_matrix.mtx"))
-    X = np.asarray(X.toarray() if hasattr(X, "toarray") else X, dtype=np.float32)
-    np.nan_to_num(X, copy=False, nan=0.0, posinf=0.0, neginf=0.0)
-    y = pd.read_csv(os.path.join(dspath, file_name + "_classes.csv"), sep=",").iloc[:, 0].to_numpy().astype(np.int64)
-    names = pd.read_csv(os.path.join(dspath, file_name + "_feature_names.csv"), sep=",").iloc[:, 0].to_list()
-    return X, y, names
+def _read_labels(dspath: str, file_name: str):
+    """train.py:77-81: the ``classes`` column of <file-name>_classes.csv and the ``features`` column of
+    <file-name>_feature_names.csv (named columns, as the reference reads them)."""
+    yf = pd.read_csv(os.path.join(dspath, file_name + "_classes.csv"), sep=",")
+    nf = pd.read_csv(os.path.join(dspath, file_name + "_feature_names.csv"), sep=",")
+    if "classes" not in yf.columns or "features" not in nf.columns:
+        raise KeyError("expected a 'classes' column in %s_classes.csv and a 'features' column in %s_feature_names.csv "
+                       "(train.py:79,81)" % (file_name, file_name))
+    return yf["classes"].to_numpy().astype(np.int64), nf["features"].to_list()
 
 
 def load_dataset_device(dspath: str, file_name: str, do_filter: bool = True, device=None, minimum_samples: int = 5):
@@ -44,28 +43,8 @@ def load_dataset_device(dspath: str, file_name: str, do_filter: bool = True, dev
     from .ingest import load_mtx
     X = load_mtx(os.path.join(dspath, file_name + "_matrix.mtx"), do_filter=do_filter, minimum_samples=minimum_samples,
                  device=device)
-    y = pd.read_csv(os.path.join(dspath, file_name + "_classes.csv"), sep=",").iloc[:, 0].to_numpy().astype(np.int64)
-    names = pd.read_csv(os.path.join(dspath, file_name + "_feature_names.csv"), sep=",").iloc[:, 0].to_list()
+    y, names = _read_labels(dspath, file_name)
     return X, y[X.kept_rows], np.array(names)[X.kept_cols].tolist()
-
-
-def filter_data(X, y, features_name, minimum_samples: int = 5):
-    """train.py:88-118: cells with sum |x| >= 5; genes with CPM > 1 in >= minimum_samples cells."""
-    example_sums = np.absolute(X).sum(1)
-    examples_ids = np.where(example_sums >= 5)[0]
-    X = X[examples_ids]
-    y = y[examples_ids]
-    num_examples, _ = X.shape
-    temp = np.absolute(X)
-    temp = (temp * 1e6) / temp.sum(axis=1).reshape((num_examples, 1))
-    temp[temp > 1] = 1
-    temp[temp != 1] = 0
-    feature_sums = temp.sum(0)
-    if num_examples <= minimum_samples or minimum_samples > num_examples // 2:
-        minimum_samples = num_examples // 2
-    feature_ids = np.where(feature_sums >= minimum_samples)[0]
-    features_name = np.array(features_name)[feature_ids].tolist()
-    return X[:, feature_ids], y, features_name
 
 
 def build_parser():
@@ -86,12 +65,11 @@ def build_parser():
     p.add_argument("--no-sort-by-pvalue", action="store_true", default=False)
     p.add_argument("--top-k-features", type=int, default=100)
     p.add_argument("--device", type=int, default=None)
-    p.add_argument("--permutation", type=str, default="reference", choices=["reference", "device"])
-    p.add_argument("--loader", type=str, default="native", choices=["native", "scipy"],
-                   help="native: multi-threaded C++ MatrixMarket reader + filter on the B200 (the matrix never "
-                        "exists on the host); scipy: mmread + NumPy filter on the host (train.py:82-118 as written)")
-    p.add_argument("--ranking", type=str, default="device", choices=["device", "pandas"],
-                   help="device: order of the scores from phet_rank; pandas: DataFrame.sort_values (utils.py:107-136)")
+    p.add_argument("--permutation", type=str, default="reference", choices=["reference", "numpy", "device"])
+    p.add_argument("--ranking", type=str, default="pandas", choices=["device", "pandas"],
+                   help="pandas (default): DataFrame.sort_values exactly as utils.py:107-136 (its quicksort decides the "
+                        "order inside a group of EQUAL scores, as in the reference); device: order from phet_rank "
+                        "(equal scores keep ascending gene order)")
     return p
 
 
@@ -99,14 +77,15 @@ def run(args) -> pd.DataFrame:
     from . import PHet
     from .select import significant_features, sort_features
     np.random.seed(seed=SEED)
+    if args.normalize != "zscore":
+        # the reference's PHet call hard-codes normalize="zscore" (train.py:474); --normalize only reaches HIQR / DeltaIQRMean
+        print("## --normalize %s is not forwarded to PHet (train.py:474 passes normalize='zscore'); ignored as in the reference" % args.normalize)
+    if args.top_k_features != 100:
+        print("## --top-k-features only feeds the reference's plots and benchmarks (train.py:136-157, 509-591): out of scope here")
     t0 = time.perf_counter()
-    if args.loader == "native":
-        X, y, names = load_dataset_device(args.dspath, args.file_name, not args.no_filtering, args.device)
-    else:
-        X, y, names = load_dataset(args.dspath, args.file_name)
-        if not args.no_filtering:
-            X, y, names = filter_data(X, y, names)
-    print("## loader %s: %.3f s" % (args.loader, time.perf_counter() - t0))
+    # MatrixMarket file -> filtered float32 matrix in HBM (C++ reader + device filter; replaces train.py:82-118)
+    X, y, names = load_dataset_device(args.dspath, args.file_name, not args.no_filtering, args.device)
+    print("## loader: %.3f s" % (time.perf_counter() - t0))
     print("## %s: %d examples x %d features; classes %s" % (args.file_name, X.shape[0], X.shape[1],
                                                             np.bincount(y).tolist()))
     t0 = time.perf_counter()

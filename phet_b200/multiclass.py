@@ -114,6 +114,9 @@ def fit_multiclass(est, X, y, K, staged):
     agg = est.multiconditions_aggregation
     N, G = X.shape
     S = int(est.num_subsamples)
+    if dist is not None and dist.get_backend() == "nccl":
+        import torch
+        torch.cuda.set_device(est._resolve_device())   # before the first collective: broadcast_numpy allocates on the current device
     t0 = time.perf_counter()
     if dist is None or rank == 0:
         plan = plan_and_draw(est, y, K, G)

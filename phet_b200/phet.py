@@ -21,6 +21,37 @@ from . import _capi, hostmath
 
 SEED_VALUE = 0.001  # phet.py:29 (applied on the device, csrc/finalize.cu)
 
+# One library context per device, kept between fits: its device buffers, streams and pinned slots are reused instead
+# of being allocated and freed (cudaMalloc / cudaFree / cudaHostAlloc of ~12 GB cost ~0.1 s per fit at 50k x 30k).
+_CTX_CACHE: dict = {}
+
+
+def release_device_contexts():
+    """Free the cached per-device contexts (device memory goes back to the driver)."""
+    for ctx in list(_CTX_CACHE.values()):
+        ctx.close()
+    _CTX_CACHE.clear()
+
+
+def _cached_context(dev: int, torch_stream: bool = False):
+    """The context of device ``dev``; with ``torch_stream`` the one that launches on a (cached, non-default) torch
+    stream, so that torch.distributed collectives can be ordered with the library's kernels."""
+    key = (dev, bool(torch_stream))
+    ctx = _CTX_CACHE.get(key)
+    if ctx is None or getattr(ctx, "h", None) is None:
+        if torch_stream:
+            import torch
+            ts = torch.cuda.Stream(dev)            # non-default: handle 0 would mean "own stream"
+            ctx = _capi.Context(dev, ts.cuda_stream)
+            ctx.torch_stream = ts
+        else:
+            ctx = _capi.Context(dev, None)
+        if not _CTX_CACHE:
+            import atexit
+            atexit.register(release_device_contexts)
+        _CTX_CACHE[key] = ctx
+    return ctx
+
 
 class PHet:
     def __init__(self, normalize: Literal["robust", "zscore", "log"] | None = "zscore",
@@ -87,6 +118,20 @@ class PHet:
         self.shard = shard
         self.capture = capture
         self.timings_ = {}
+
+    @property
+    def ranking_(self):
+        """Gene index at each rank, descending score, equal scores in ascending gene order (phet_rank)."""
+        if getattr(self, "_ranking", None) is None:
+            if getattr(self, "_rank_scores", None) is None:
+                raise AttributeError("ranking_ is available after fit_predict")
+            ctx = _cached_context(self._rank_device)
+            self._ranking, _ = ctx.rank(self._rank_scores)
+        return self._ranking
+
+    @ranking_.setter
+    def ranking_(self, value):
+        self._ranking = value
 
     # ------------------------------------------------------------------------------------
     def _check_scope(self, num_classes, sample_ids):
@@ -192,24 +237,26 @@ class PHet:
             raise NotImplementedError("a StagedMatrix is fitted by the process that staged it (single device)")
         n_slices, n_last = hostmath.step3_slices(min_c, m)
         if dist is None:
-            ctx = staged.ctx if staged is not None else _capi.Context(dev, None)
+            ctx = staged.ctx if staged is not None else _cached_context(dev)
             try:
                 scores = self._fit_on(ctx, X, examples_i, examples_j, m, replace, S, n_slices, n_last, 0, 1, None)
-            finally:
-                if staged is None:
+            except BaseException:
+                if staged is None:          # a failed fit may leave the context half-configured: start clean next time
+                    _CTX_CACHE.pop((dev, False), None)
                     ctx.close()
+                raise
         else:
             import torch
-            use_cuda = dist.get_backend() == "nccl"
-            if use_cuda:
-                torch.cuda.set_device(dev)
-            self._torch_stream = torch.cuda.Stream(dev)   # non-default: handle 0 would mean "own stream"
-            with torch.cuda.stream(self._torch_stream):   # the caller's current stream is restored on exit
-                ctx = _capi.Context(dev, self._torch_stream.cuda_stream)
+            if dist.get_backend() == "nccl":
+                torch.cuda.set_device(dev)                # before the first collective of this fit
+            ctx = _cached_context(dev, torch_stream=True)
+            with torch.cuda.stream(ctx.torch_stream):     # the caller's current stream is restored on exit
                 try:
                     scores = self._fit_on(ctx, X, examples_i, examples_j, m, replace, S, n_slices, n_last, rank, world, dist)
-                finally:
+                except BaseException:
+                    _CTX_CACHE.pop((dev, True), None)
                     ctx.close()
+                    raise
         self.timings_["fit_s"] = time.perf_counter() - t_all
         return scores
 
@@ -326,8 +373,11 @@ class PHet:
         # Fisher standardisation, KBinsDiscretizer('uniform') on o, weights and combine (phet.py:435-462, 500-516)
         scores, counts, edges = ctx.finalize(S, self.feature_weight)
         self.bin_counts_ = counts
-        # descending order of the scores, ties in ascending gene order (utils.py:107-136 on the device: phet_rank)
-        self.ranking_, _ = ctx.rank()
+        # descending order of the scores (utils.py:107-136 on the device: phet_rank) is computed on first use of
+        # ``ranking_``: a fit that only wants the scores does not pay for the launch and its synchronisation
+        self._ranking = None
+        self._rank_scores = scores
+        self._rank_device = ctx.device
         self.m_ = m
         self.index_sets_ = idx
         self.launches_ = ctx.launch_count()

@@ -12,7 +12,7 @@ import pandas as pd
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phet_b200 import _capi, load_mtx  # noqa: E402
-from phet_b200.main import filter_data  # noqa: E402
+from oracle.ingest_oracle import filter_data  # noqa: E402
 
 
 def write_mtx(path, N, G, density, rng):

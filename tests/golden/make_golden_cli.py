@@ -44,7 +44,7 @@ def main():
     names = pd.read_csv("/root/reference/samples/srbct_feature_names.csv").iloc[:, 0].to_list()
     # train.py:88-118 filter (drops nothing on SRBCT, kept for fidelity)
     sys.path.insert(0, ROOT)
-    from phet_b200.main import filter_data
+    from oracle.ingest_oracle import filter_data
     Xf, yf, namesf = filter_data(X, y, names)
     assert Xf.shape == X.shape
     S = 200

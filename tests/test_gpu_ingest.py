@@ -1,7 +1,7 @@
 """GPU: the rows of SURVEY.md 8(f) either side of the fit, through the C ABI.
 
-* phet_mtx_stage (input path) against the host restatement of /root/reference/src/train.py:82-118 that
-  phet_b200/main.py keeps (load_dataset + filter_data: scipy mmread, float32, nan_to_num, cell filter, CPM gene
+* phet_mtx_stage (input path) against the host restatement of /root/reference/src/train.py:77-118 in
+  oracle/ingest_oracle.py (load_dataset + filter_data: scipy mmread, float32, nan_to_num, cell filter, CPM gene
   filter) -- the staged matrix and both index lists must be identical, bit for bit;
 * phet_rank (ordering of utils.py:107-136) against pandas' descending sort: identical where scores are distinct,
   ascending gene order inside tie groups (pandas kind="stable").
@@ -54,7 +54,7 @@ def _write_case(tmp_path, name, rng):
 @pytest.mark.parametrize("name", ["counts", "wide", "border", "tiny"])
 def test_stage_matches_host_filter(tmp_path, name, do_filter):
     from phet_b200 import load_mtx
-    from phet_b200.main import filter_data, load_dataset
+    from oracle.ingest_oracle import filter_data, load_dataset
     rng = np.random.default_rng(11)
     path = _write_case(tmp_path, name, rng)
     X, y, names = load_dataset(str(tmp_path), name)
@@ -92,7 +92,7 @@ def test_stage_cleans_nonfinite_and_mirrors_symmetric(tmp_path):
 def test_fit_from_staged_matrix_equals_fit_from_numpy(tmp_path):
     """The fit that starts from HBM (StagedMatrix) returns the scores of the fit that starts from the host array."""
     from phet_b200 import PHet, load_mtx
-    from phet_b200.main import filter_data, load_dataset
+    from oracle.ingest_oracle import filter_data, load_dataset
     rng = np.random.default_rng(5)
     N, G = 300, 500
     X = rng.poisson(1.5, (N, G)).astype(np.float64)
@@ -177,16 +177,29 @@ def test_rank_of_golden_scores_matches_reference_ranking():
 
 
 def test_cli_native_loader_and_device_ranking_equal_host_path(tmp_path):
-    """main.py with the native loader + device ranking (defaults) writes the file the scipy loader + pandas sort write."""
-    from phet_b200.main import main
+    """main.py (C++ reader + device filter, pandas or device ranking) writes the file that the host restatement of
+    train.py:77-118 (oracle/ingest_oracle.py) + the class + the pandas sort write."""
+    from oracle.ingest_oracle import filter_data, load_dataset
+    from phet_b200 import PHet
+    from phet_b200.main import SEED, main
+    from phet_b200.select import significant_features
     rng = np.random.default_rng(2)
     _write_case(tmp_path, "counts", rng)
     common = ["--file-name", "counts", "--dspath", str(tmp_path), "--methods", "phet", "--num-subsamples", "30"]
     main(common + ["--rspath", str(tmp_path / "a")])
-    main(common + ["--rspath", str(tmp_path / "b"), "--loader", "scipy", "--ranking", "pandas"])
+    main(common + ["--rspath", str(tmp_path / "b"), "--ranking", "device"])
+    X, y, names = load_dataset(str(tmp_path), "counts")
+    X, y, names = filter_data(X, y, names)
+    np.random.seed(SEED)
+    scores = PHet(normalize="zscore", iqr_range=(25, 75), num_subsamples=30, feature_weight=[0.4, 0.3, 0.2, 0.1]).fit_predict(X, y)
+    df = significant_features(X=scores, features_name=names, alpha=0.05, fit_type="gamma", per=95)
+    os.makedirs(tmp_path / "c", exist_ok=True)
+    df.to_csv(tmp_path / "c" / "counts_phet_br_features.csv", sep=",", index=False)
     a = open(tmp_path / "a" / "counts_phet_br_features.csv").read()
     b = open(tmp_path / "b" / "counts_phet_br_features.csv").read()
-    assert a == b and len(a.splitlines()) > 2
+    c = open(tmp_path / "c" / "counts_phet_br_features.csv").read()
+    assert a == c and len(a.splitlines()) > 2
+    assert sorted(a.splitlines()) == sorted(b.splitlines())   # device ranking: same rows, order free inside tie groups
 
 
 def test_new_entry_points_fail_loudly(tmp_path):

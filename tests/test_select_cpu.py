@@ -21,7 +21,8 @@ def test_selection_and_ranking_match_reference():
 
 
 def test_cli_filter_and_parser():
-    from phet_b200.main import build_parser, filter_data
+    from oracle.ingest_oracle import filter_data
+    from phet_b200.main import build_parser
     args = build_parser().parse_args(["--file-name", "srbct", "--methods", "phet", "--iqr-range", "10", "90"])
     assert args.methods == ["phet"] and tuple(args.iqr_range) == (10.0, 90.0) and args.num_subsamples == 1000
     rng = np.random.default_rng(0)
