@@ -297,7 +297,8 @@ def cpu_reference_class_sample(wl, X_cols, y):
     for g, s_ in pts:
         np.random.seed(SEED)
         t0 = time.perf_counter()
-        PHet(normalize="zscore", iqr_range=PERCENTILES, num_subsamples=s_, subsampling_size="sqrt",
+        # (the class's own keyword is `percentiles`, phet.py:33-40; train.py:474 passes iqr_range= and fails on it)
+        PHet(normalize="zscore", percentiles=PERCENTILES, num_subsamples=s_, subsampling_size="sqrt",
              feature_weight=FEATURE_WEIGHT).fit_predict(np.array(X_cols[:, :g], copy=True), y)
         T.append(time.perf_counter() - t0)
     A = np.array([[1.0, g, s_, g * s_] for g, s_ in pts])

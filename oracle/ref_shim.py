@@ -62,6 +62,7 @@ def load_reference_phet():
     """Return the reference's own ``PHet`` class, imported from ``/root/reference/src``."""
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_SRC)
+    os.environ.setdefault("TQDM_DISABLE", "1")   # the class drives a tqdm bar per step: megabytes of progress text otherwise
     for name in ("anndata", "scanpy", "decoupler"):
         sys.modules.setdefault(name, types.ModuleType(name))
     if "statsmodels.stats.weightstats" not in sys.modules:

@@ -35,7 +35,7 @@ def _run(monkeypatch, X, N, G, S, ctrl, case, idx, env=None, keep_h=False, g_ran
         monkeypatch.setenv(k, v)
     ctx = _capi.Context(0)
     try:
-        fit = bench.Fit(ctx, dict(N=N, G=G, S=S), ctrl, case, idx, 0, 1, None)
+        fit = bench.Fit(ctx, dict(N=N, G=G, S=S), ctrl, case, idx, 0, 1, None, perms="device")
         ctx.set_option(_capi.OPT_KEEP_H, 1 if keep_h else 0)
         ctx.set_classes(ctrl, case)
         ctx.set_index_sets(idx)
@@ -64,7 +64,7 @@ def test_full_size_properties(name, monkeypatch):
     N, G, S = CONFIGS[name]
     m = hostmath.subsample_size(N // 2, N - N // 2, "sqrt")
     X = bench.synth_matrix_device(N, G, torch.device("cuda", 0))
-    ctrl, case, idx = bench.draw_index_sets(N, S, m)
+    ctrl, case, idx, _ = bench.draw_index_sets(N, S, m)
 
     scores, acc, o, counts, order, path = _run(monkeypatch, X, N, G, S, ctrl, case, idx)
     assert path == "bound-and-prune"
