@@ -54,6 +54,37 @@ def ztest_restated(x1, x2=None, value=0, alternative="two-sided", usevar="pooled
     return zstat, pvalue
 
 
+class _QuietBar:
+    """Stand-in for tqdm inside the reference module: same calls, no output."""
+
+    def __init__(self, iterable=None, *args, **kwargs):
+        self._it = iterable
+
+    def __iter__(self):
+        return iter(self._it if self._it is not None else ())
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def update(self, n=1):
+        pass
+
+    def set_description(self, *a, **k):
+        pass
+
+    def set_postfix(self, *a, **k):
+        pass
+
+    def refresh(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
+
+
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_SRC, "model", "phet.py"))
 
@@ -81,6 +112,9 @@ def load_reference_phet():
     import warnings
     saved_filters = list(warnings.filters)
     from model.phet import PHet  # noqa: E402  (phet.py:7-9 disables logging/warnings globally)
+    import model.phet as _mod
+    if not os.environ.get("PHET_REFERENCE_PROGRESS"):
+        _mod.tqdm = _QuietBar   # the module's progress bar only (its source is untouched): megabytes of text otherwise
     logging.disable(logging.NOTSET)
     warnings.filters[:] = saved_filters
     return PHet

@@ -36,8 +36,15 @@ def release_device_contexts():
 def _cached_context(dev: int, torch_stream: bool = False):
     """The context of device ``dev``; with ``torch_stream`` the one that launches on a (cached, non-default) torch
     stream, so that torch.distributed collectives can be ordered with the library's kernels."""
+    import os
     key = (dev, bool(torch_stream))
+    # the library reads its tuning / testing knobs when a context is created: a context made under other knobs is stale
+    knobs = tuple(os.environ.get(k) for k in ("PHET_STEP1_IMPL", "PHET_STEP3_IMPL", "PHET_STEP1_FORCE_BIG",
+                                              "PHET_STEP1_BIG_THREADS", "PHET_STEP1_NBW", "PHET_PROFILE", "PHET_EXACT_MOMENTS"))
     ctx = _CTX_CACHE.get(key)
+    if ctx is not None and getattr(ctx, "knobs", None) != knobs:
+        ctx.close()
+        ctx = None
     if ctx is None or getattr(ctx, "h", None) is None:
         if torch_stream:
             import torch
@@ -46,6 +53,7 @@ def _cached_context(dev: int, torch_stream: bool = False):
             ctx.torch_stream = ts
         else:
             ctx = _capi.Context(dev, None)
+        ctx.knobs = knobs
         if not _CTX_CACHE:
             import atexit
             atexit.register(release_device_contexts)
