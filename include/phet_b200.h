@@ -332,14 +332,18 @@ typedef struct {
     int32_t elem_bytes;
 } phet_mt_job;
 int phet_mt_shuffle_rounds(phet_mt *mt, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds);
-/* The same draws with the work spread over threads: a generator thread fills a cache-resident ring with the stream, a
- * scanner thread (the only sequential job) walks the permutations with a count-only scan and records where each
- * STARTS, and `workers` threads redo the scan from there, storing the targets.  Submit blocks of rounds in stream
- * order (returns at once; outputs must stay valid), wait on the ticket of a block before reading its outputs, end
- * with phet_mt_par_end, which writes the stream's final state back into `mt` (do not touch `mt` in between).
- * workers <= 0: env PHET_REPLAY_WORKERS or 4.  max_n: longest permutation that will be submitted (sizes the ring). */
+/* The same draws with the work spread over threads.  Only WHERE each permutation starts in the stream is sequential
+ * by nature, so: generator threads (env PHET_REPLAY_GENERATORS, default 4) each walk the whole stream with the twist
+ * alone and temper + store every G-th region into a cache-resident ring (16 bits per output when max_n <= 65536); ONE
+ * scanner thread walks the permutations with a count-only scan of the ring and records where each starts; `workers`
+ * threads (<= 0: env PHET_REPLAY_WORKERS or 4) redo the scan from there, storing the targets.  With too few cores, or
+ * max_n < 2048, the scanner generates for itself and the workers regenerate from recorded generator states.
+ * Submit blocks of rounds in stream order (returns at once; outputs must stay valid), wait on the ticket of a block
+ * before reading its outputs, end with phet_mt_par_end, which writes the stream's final state back into `mt` (do not
+ * touch `mt` in between).  max_n: longest permutation that will be submitted. */
 typedef struct phet_mt_par phet_mt_par;
 int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par **out);
+int phet_mt_par_threads(const phet_mt_par *par, int32_t out[3]);   /* generator, scanner, worker threads in use */
 int phet_mt_par_submit(phet_mt_par *par, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds, int64_t *ticket_out);
 int phet_mt_par_wait(phet_mt_par *par, int64_t ticket);
 int phet_mt_par_end(phet_mt_par *par);

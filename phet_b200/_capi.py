@@ -30,7 +30,7 @@ EXPORTS = [
     "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix", "phet_load_matrix_genes",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
     "phet_mt_create", "phet_mt_state", "phet_mt_destroy", "phet_mt_simd", "phet_mt_shuffle_rounds", "phet_mt_bounded",
-    "phet_mt_par_begin", "phet_mt_par_submit", "phet_mt_par_wait", "phet_mt_par_end",
+    "phet_mt_par_begin", "phet_mt_par_threads", "phet_mt_par_submit", "phet_mt_par_wait", "phet_mt_par_end",
     "phet_host_fisher_yates", "phet_fy_apply", "phet_replay_stats", "phet_draw_index_sets", "phet_phase_ms",
 ]
 
@@ -142,6 +142,7 @@ def load_library(build_if_missing: bool = True):
     lib.phet_mt_shuffle_rounds.argtypes = [vp, C.POINTER(MtJob), i32, i64]
     lib.phet_mt_bounded.argtypes = [vp, C.c_uint32, i64, vp]
     lib.phet_mt_par_begin.argtypes = [vp, i32, i64, C.POINTER(vp)]
+    lib.phet_mt_par_threads.argtypes = [vp, C.POINTER(i32)]
     lib.phet_mt_par_submit.argtypes = [vp, C.POINTER(MtJob), i32, i64, C.POINTER(i64)]
     lib.phet_mt_par_wait.argtypes = [vp, i64]
     lib.phet_mt_par_end.argtypes = [vp]
@@ -211,7 +212,7 @@ class MtStream:
         """The swap targets of ``rounds`` x [np.random.permutation(n) for n in sizes]: a list of arrays
         (rounds, n - 1), uint16 when n <= 65536 else uint32 (None when ``store`` is False: stream advanced only).
         ``workers`` not None: through the multi-threaded replay (generator / scanner / store workers), the
-        rounds submitted in ``chunks`` blocks."""
+        rounds submitted in ``chunks`` blocks (``self.par_threads``: generator, scanner, worker threads used)."""
         outs, jobs = [], (MtJob * len(sizes))()
         for k, n in enumerate(sizes):
             eb = 2 if n <= 65536 else 4
@@ -238,6 +239,9 @@ class MtStream:
                 r0 += rc
             for t in tickets:
                 _check(self.lib.phet_mt_par_wait(par, t))
+            st = (C.c_int32 * 3)()
+            _check(self.lib.phet_mt_par_threads(par, st))
+            self.par_threads = [int(v) for v in st]
         finally:
             _check(self.lib.phet_mt_par_end(par))
         return outs

@@ -58,7 +58,7 @@ namespace {
 
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
-constexpr int kCarry = 64;      // outputs of the previous block kept in front of the current one
+constexpr int kCarry = 128;     // outputs of the previous block kept in front of the current one (>= the widest trip of a scan)
 constexpr int kGenSteps = 41;   // copy + 40 vector steps make the next block (see phet_mt::gen_step)
 // generator steps per 64-output trip of the scan (5 * 15.6 outputs >= 64); env PHET_MT_PUMP overrides (0: whole blocks)
 static const int kPump = getenv("PHET_MT_PUMP") ? atoi(getenv("PHET_MT_PUMP")) : 0;
@@ -123,12 +123,18 @@ MT_AVX512 void temper_avx512(const uint32_t *key, uint32_t *out) {
         _mm512_storeu_si512(out + k, temper16(_mm512_loadu_si512(key + k)));
 }
 
+MT_AVX512 void temper16_avx512(const uint32_t *key, uint16_t *out) {  // low 16 bits of the tempered outputs
+    for (int k = 0; k < kN; k += 16)
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(out + k), _mm512_cvtepi32_epi16(temper16(_mm512_loadu_si512(key + k))));
+}
+
 // One vector of the in-place twist of key[0..624) (the array has >= 32 words of padding behind it), tempered into
 // out.  Steps 1..40 in order make one block:
 //   1..14   k = 0, 16, .., 208     new[k] = old[k + 397] ^ tw(old[k], old[k + 1])        (reads up to old[620])
 //   15      k = 224 (3 lanes: the others would clobber old words the second half still needs); then old[624] := new[0]
 //   16..39  k = 227, 243, .., 595  new[k] = new[k - 227] ^ tw(old[k], old[k + 1])
 //   40      k = 611 (13 lanes; lane 12 pairs old[623] with new[0] through key[624])
+template <bool TEMPER>
 MT_AVX512 inline void twist_step_avx512(uint32_t *key, uint32_t *out, int step) {
     int k, off;
     __mmask16 m = 0xFFFF;
@@ -146,12 +152,16 @@ MT_AVX512 inline void twist_step_avx512(uint32_t *key, uint32_t *out, int step) 
     const __m512i v = _mm512_xor_si512(c, twist16(a, b));
     if (m == 0xFFFF) {  // (plain stores: a masked store does not forward to the loads of the next step)
         _mm512_storeu_si512(key + k, v);
-        _mm512_storeu_si512(out + k, temper16(v));
+        if (TEMPER) _mm512_storeu_si512(out + k, temper16(v));
     } else {
         _mm512_mask_storeu_epi32(key + k, m, v);
-        _mm512_mask_storeu_epi32(out + k, m, temper16(v));
+        if (TEMPER) _mm512_mask_storeu_epi32(out + k, m, temper16(v));
         if (step == 15) key[kN] = key[0];
     }
+}
+
+MT_AVX512 void twist_block_avx512(uint32_t *key) {  // state -> next state, no outputs (a generator that only runs ahead)
+    for (int step = 1; step <= 40; ++step) twist_step_avx512<false>(key, nullptr, step);
 }
 #endif
 
@@ -182,6 +192,7 @@ struct phet_mt {
     int pos = kCarry + kN, end = kCarry + kN;
     int gstep = 0;            // 0 .. kGenSteps: progress of the next block
     bool avx512 = false;
+    int64_t block_no = 0;     // blocks entered since load(): stream position = 624 * block_no + (pos - kCarry)
 
     void load(const uint32_t *k, int p) {
         cur = key_a;
@@ -199,7 +210,9 @@ struct phet_mt {
         pos = kCarry + p;
         end = kCarry + kN;
         gstep = 0;
+        block_no = 0;
     }
+    inline int64_t consumed() const { return block_no * kN + (pos - kCarry); }  // outputs consumed since load(key, 0)
     // one step of the next block (step 0 copies the state: `work` stops being the previous block's state, so it
     // must not run while outputs of the previous block are still unread, pos < kCarry -- see state())
     inline void gen_step() {
@@ -215,7 +228,7 @@ struct phet_mt {
             return;
         }
 #if PHET_X86
-        twist_step_avx512(work, nbuf + kCarry, gstep);
+        twist_step_avx512<true>(work, nbuf + kCarry, gstep);
 #endif
         ++gstep;
     }
@@ -234,6 +247,7 @@ struct phet_mt {
         pos = kCarry - rem;
         end = kCarry + kN;
         gstep = 0;
+        ++block_no;
     }
     inline void ensure(int k) {  // k <= kCarry
         if (end - pos < k) refill();
@@ -255,14 +269,93 @@ struct phet_mt {
 
 namespace {
 
+// ---- where a scan takes the tempered outputs from -----------------------------------------------------------------
+// (a) the generator's own window: one thread generates and scans
+struct SeqSrc {
+    phet_mt &e;
+    const uint32_t *p = nullptr;
+    inline void need(int k) {  // >= k contiguous outputs at the current position (k <= kCarry)
+        e.ensure(k);
+        p = e.buf + e.pos;
+    }
+#if PHET_X86
+    MT_AVX512 inline __m512i vec(int q) const { return _mm512_loadu_si512(p + 16 * q); }
+#endif
+    inline uint32_t at(int k) const { return p[k]; }
+    inline void advance(int used) {
+        e.pos += used;
+        e.pump();
+    }
+    inline uint32_t next() { return e.next32(); }
+};
+
+// (b) a ring that generator threads fill ahead of the readers (parallel replay below).  E = uint16_t when every
+// permutation is of <= 65536 cells (only the low 16 bits of an output can matter): half the bytes between cores.
+struct OutRing {
+    void *w = nullptr;            // [cap + kCarry] elements: the first kCarry are mirrored behind the end
+    int ebytes = 4;
+    size_t cap = 0;               // elements; a multiple of region_elems
+    size_t region_elems = 0;      // 624 * blocks per region
+    size_t nreg = 0;
+    std::unique_ptr<std::atomic<uint64_t>[]> ready;   // per ring slot: 1 + index of the region it holds, once complete
+    alignas(64) std::atomic<uint64_t> low{0};         // outputs below this stream position are no longer read
+    std::atomic<bool> stop{false};
+};
+
+template <typename E>
+struct RingSrc {
+    OutRing *r;
+    uint64_t abs;            // stream position (outputs since the start of block 0)
+    size_t idx;              // abs mod cap
+    uint64_t known;          // outputs in [region start of abs, known) are known to be in the ring
+    const E *p = nullptr;
+    RingSrc(OutRing *ring, uint64_t a)
+        : r(ring), abs(a), idx((size_t)(a % ring->cap)), known(a / ring->region_elems * ring->region_elems) {}  // regions before a's own may be gone
+    inline void need(int k) {
+        if (__builtin_expect(abs + (uint64_t)k > known, 0)) {
+            unsigned spins = 0;
+            for (;;) {
+                const uint64_t reg = known / r->region_elems;   // next region not yet seen complete
+                if (r->ready[reg % r->nreg].load(std::memory_order_acquire) == reg + 1) {
+                    known = (reg + 1) * r->region_elems;
+                    if (abs + (uint64_t)k <= known) break;
+                    continue;
+                }
+                if (r->stop.load(std::memory_order_relaxed)) break;
+                cpu_relax();
+                if ((++spins & 4095u) == 0) std::this_thread::yield();
+            }
+        }
+        p = static_cast<const E *>(r->w) + idx;
+    }
+#if PHET_X86
+    MT_AVX512 inline __m512i vec(int q) const {
+        if (sizeof(E) == 2) return _mm512_cvtepu16_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + 16 * q)));
+        return _mm512_loadu_si512(p + 16 * q);
+    }
+#endif
+    inline uint32_t at(int k) const { return (uint32_t)p[k]; }
+    inline void advance(int used) {
+        abs += (uint64_t)used;
+        idx += (size_t)used;
+        if (idx >= r->cap) idx -= r->cap;
+    }
+    inline uint32_t next() {
+        need(1);
+        const uint32_t v = (uint32_t)p[0];
+        advance(1);
+        return v;
+    }
+};
+
 // ---- the draws of one np.random.permutation(n): dst[t] = rk_interval(n - 1 - t), t = 0 .. n - 2
-template <typename J, bool STORE>
-void shuffle_draws_scalar(phet_mt &e, uint32_t n, J *dst) {
+template <typename J, bool STORE, typename Src>
+void shuffle_draws_scalar(Src &in, uint32_t n, J *dst) {
     size_t t = 0;
     for (uint32_t i = n - 1; i >= 1; --i) {
         const uint32_t mask = bitmask(i);
         uint32_t v;
-        while ((v = (e.next32() & mask)) > i) {
+        while ((v = (in.next() & mask)) > i) {
         }
         if (STORE) dst[t] = (J)v;
         ++t;
@@ -292,8 +385,8 @@ MT_AVX512 inline void store_compressed<uint16_t>(uint16_t *dst, __m512i v, __mma
 // the octave [lo, mask] that fixes the bit mask.
 constexpr uint32_t kScalarBelow = 96;  // the last draws of a permutation go one output at a time
 
-template <typename J, bool STORE>
-MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
+template <typename J, bool STORE, typename Src>
+MT_AVX512 void shuffle_draws_avx512(Src &in, uint32_t n, J *dst) {
     const __m512i lane = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
     const __m512i lanek[4] = {lane, _mm512_add_epi32(lane, _mm512_set1_epi32(16)), _mm512_add_epi32(lane, _mm512_set1_epi32(32)),
                               _mm512_add_epi32(lane, _mm512_set1_epi32(48))};
@@ -303,15 +396,57 @@ MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
         const uint32_t mask = bitmask(i), lo = (mask >> 1) + 1;  // every i in [lo, mask] shares this mask
         const uint32_t floor_i = lo > kScalarBelow ? lo : kScalarBelow;
         const __m512i vm = _mm512_set1_epi32((int)mask);
+        // count-only scans of the wide octaves take 128 outputs per trip: the trip is bound by the dependency chain
+        // i -> compare -> popcount -> i, not by the number of lanes, and with 2^15+ values per octave the lanes left
+        // undecided by the wider uncertainty of i stay rare (~0.25 per trip at mask 32767)
+        if (!STORE && kCarry >= 128 && mask >= 8191u) {
+            while (i >= floor_i) {
+                in.need(128);
+                const __m512i vi = _mm512_set1_epi32((int)i);
+                uint64_t sure[2] = {0, 0}, amb[2] = {0, 0};
+#pragma GCC unroll 8
+                for (int q = 0; q < 8; ++q) {
+                    const __m512i vq = _mm512_and_si512(in.vec(q), vm);
+                    const __mmask16 nrej = _mm512_cmple_epu32_mask(vq, vi);
+                    const __mmask16 sq = _mm512_cmple_epu32_mask(_mm512_add_epi32(vq, _mm512_add_epi32(lanek[q & 3], _mm512_set1_epi32(64 * (q >> 2)))), vi);
+                    sure[q >> 2] |= (uint64_t)sq << (16 * (q & 3));
+                    amb[q >> 2] |= (uint64_t)(__mmask16)(nrej & ~sq) << (16 * (q & 3));
+                }
+                while (__builtin_expect(amb[0] != 0, 0)) {
+                    const int k = __builtin_ctzll(amb[0]);
+                    const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure[0] & ((1ull << k) - 1ull));
+                    if ((in.at(k) & mask) <= ik) sure[0] |= 1ull << k;
+                    amb[0] &= amb[0] - 1;
+                }
+                const uint32_t t0 = (uint32_t)__builtin_popcountll(sure[0]);
+                while (__builtin_expect(amb[1] != 0, 0)) {
+                    const int k = __builtin_ctzll(amb[1]);
+                    const uint32_t ik = i - t0 - (uint32_t)__builtin_popcountll(sure[1] & ((1ull << k) - 1ull));
+                    if ((in.at(64 + k) & mask) <= ik) sure[1] |= 1ull << k;
+                    amb[1] &= amb[1] - 1;
+                }
+                uint32_t total = t0 + (uint32_t)__builtin_popcountll(sure[1]);
+                const uint32_t room = i - lo + 1;
+                int used = 128;
+                if (__builtin_expect(total >= room, 0)) {
+                    if (room <= t0) used = __builtin_ctzll(_pdep_u64(1ull << (room - 1), sure[0])) + 1;
+                    else used = 64 + __builtin_ctzll(_pdep_u64(1ull << (room - t0 - 1), sure[1])) + 1;
+                    total = room;
+                }
+                t += total;
+                i -= total;
+                in.advance(used);
+            }
+            continue;
+        }
         while (i >= floor_i) {
-            e.ensure(64);
-            const uint32_t *src = e.buf + e.pos;
+            in.need(64);
             const __m512i vi = _mm512_set1_epi32((int)i);
             __m512i v[4];
             uint64_t sure = 0, amb = 0;
 #pragma GCC unroll 4
             for (int q = 0; q < 4; ++q) {
-                v[q] = _mm512_and_si512(_mm512_loadu_si512(src + 16 * q), vm);
+                v[q] = _mm512_and_si512(in.vec(q), vm);
                 // v > i: rejected; v + k <= i: accepted (both against the same broadcast of i; v + k cannot wrap: v < 2^31)
                 const __mmask16 nrej = _mm512_cmple_epu32_mask(v[q], vi);
                 const __mmask16 sq = _mm512_cmple_epu32_mask(_mm512_add_epi32(v[q], lanek[q]), vi);
@@ -321,7 +456,7 @@ MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
             while (__builtin_expect(amb != 0, 0)) {  // in lane order: everything before lane k is decided
                 const int k = __builtin_ctzll(amb);
                 const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure & ((1ull << k) - 1ull));
-                if ((src[k] & mask) <= ik) sure |= 1ull << k;
+                if ((in.at(k) & mask) <= ik) sure |= 1ull << k;
                 amb &= amb - 1;
             }
             uint32_t total = (uint32_t)__builtin_popcountll(sure);
@@ -345,14 +480,13 @@ MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
             }
             t += total;
             i -= total;
-            e.pos += used;
-            e.pump();  // a few vectors of the next block: independent work for the slots the chain through i leaves idle
+            in.advance(used);
         }
     }
     for (; i >= 1; --i) {  // the tail, one output at a time
         const uint32_t mask = bitmask(i);
         uint32_t r;
-        while ((r = (e.next32() & mask)) > i) {
+        while ((r = (in.next() & mask)) > i) {
         }
         if (STORE) dst[t] = (J)r;
         ++t;
@@ -360,18 +494,24 @@ MT_AVX512 void shuffle_draws_avx512(phet_mt &e, uint32_t n, J *dst) {
 }
 #endif
 
-template <typename J>
-void shuffle_draws(phet_mt &e, uint32_t n, J *dst) {
+template <typename J, typename Src>
+void shuffle_draws_from(Src &src, bool avx512, uint32_t n, J *dst) {
     if (n < 2) return;
 #if PHET_X86
-    if (e.avx512) {
-        if (dst) shuffle_draws_avx512<J, true>(e, n, dst);
-        else shuffle_draws_avx512<J, false>(e, n, dst);
+    if (avx512) {
+        if (dst) shuffle_draws_avx512<J, true>(src, n, dst);
+        else shuffle_draws_avx512<J, false>(src, n, dst);
         return;
     }
 #endif
-    if (dst) shuffle_draws_scalar<J, true>(e, n, dst);
-    else shuffle_draws_scalar<J, false>(e, n, dst);
+    if (dst) shuffle_draws_scalar<J, true>(src, n, dst);
+    else shuffle_draws_scalar<J, false>(src, n, dst);
+}
+
+template <typename J>
+void shuffle_draws(phet_mt &e, uint32_t n, J *dst) {
+    SeqSrc src{e};
+    shuffle_draws_from<J>(src, e.avx512, n, dst);
 }
 
 phet_mt *mt_alloc() {
@@ -405,29 +545,125 @@ struct PermDesc {
 
 }  // namespace
 
-// ---- parallel replay: one stream, two kinds of threads ---------------------------------------------------------
-//   scanner   the one sequential job: walks the permutations in order on the caller's generator with the count-only
-//             scan and records the generator state at the START of each one
-//   workers   take permutations in order and redo the scan from the recorded state with a generator of their own,
-//             this time compacting and storing the accepted targets
+// ---- parallel replay: one stream, three kinds of threads -------------------------------------------------------
+//   generators  each walks the WHOLE stream with the twist alone (no tempering: ~1/3 of a generator's work) and
+//               tempers + stores every G-th region of 64 blocks into a ring that stays cache-resident (16 bits per
+//               output when every permutation has <= 65536 cells) -- no jump-ahead polynomial needed
+//   scanner     the one job that is sequential by nature: walks the permutations in order with the count-only scan
+//               (no generation, no compaction, no stores) and records where in the stream each one STARTS
+//   workers     take permutations in order and redo the scan from the recorded start, this time compacting and
+//               storing the accepted targets
+// A fit is then bounded by the count-only scan of the stream (measured on the GPU box's Xeon: the ring moves
+// 30 GB/s between two cores, the scan needs ~9 GB/s of 16-bit outputs).
+constexpr int kRegionBlocks = 64;
+constexpr int kSnapEvery = 4096;   // blocks between the generator states kept for the final (key, pos)
+
 struct phet_mt_par {
     static constexpr size_t kQ = 1024;
     phet_mt *mt = nullptr;
     int64_t max_n = 0;
+    bool use_ring = false;
     std::vector<PermDesc> desc = std::vector<PermDesc>(kQ);
+    std::vector<uint64_t> start = std::vector<uint64_t>(kQ);   // ring mode: stream position where permutation k starts
     std::unique_ptr<std::atomic<uint8_t>[]> done{new std::atomic<uint8_t>[kQ]};
     alignas(64) std::atomic<uint64_t> submitted{0};
     alignas(64) std::atomic<uint64_t> started{0};
     alignas(64) std::atomic<uint64_t> claimed{0};
     alignas(64) std::atomic<uint64_t> finished_prefix{0};
+    alignas(64) std::atomic<uint64_t> scan_pos{0};
     std::atomic<bool> closed{false};
     std::mutex mu, prefix_mu;
     std::condition_variable cv;
     std::vector<int64_t> ticket_left;
     std::thread tscan;
-    std::vector<std::thread> workers;
+    std::vector<std::thread> workers, generators;
+    // ring mode
+    OutRing ring;
+    uint32_t key0[kN];
+    uint64_t abs0 = 0, end_pos = 0;
+    std::vector<uint32_t> snaps;   // generator 0: its state at every kSnapEvery-th block (block 0 first)
 
-    void scanner_main() {
+    void publish_low() {  // outputs before the oldest unfinished permutation (or before the scanner) are dead
+        const uint64_t f = finished_prefix.load(std::memory_order_acquire);
+        const uint64_t st = started.load(std::memory_order_acquire);
+        const uint64_t lo = f < st ? start[f & (kQ - 1)] : scan_pos.load(std::memory_order_acquire);
+        uint64_t cur = ring.low.load(std::memory_order_relaxed);
+        while (lo > cur && !ring.low.compare_exchange_weak(cur, lo, std::memory_order_release)) {
+        }
+    }
+
+    template <typename E>
+    void generator_main(int g, int G) {
+        alignas(64) uint32_t key[kN + 32];
+        alignas(64) uint32_t out[kN + 32];
+        memcpy(key, key0, sizeof(key0));
+        memset(key + kN, 0, sizeof(uint32_t) * 32);
+        const bool avx = mt->avx512;
+        uint64_t blk = 0;   // block `key` is the state of
+        unsigned spins = 0;
+        E *w = static_cast<E *>(ring.w);
+        for (uint64_t reg = (uint64_t)g;; reg += (uint64_t)G) {
+            // room: region `reg` overwrites the slot of region reg - nreg
+            while (!ring.stop.load(std::memory_order_relaxed) &&
+                   (reg + 1) * ring.region_elems > ring.low.load(std::memory_order_acquire) + ring.cap)
+                backoff(spins);
+            if (ring.stop.load(std::memory_order_relaxed)) return;
+            for (int b = 0; b < kRegionBlocks; ++b) {
+                const uint64_t want = reg * kRegionBlocks + (uint64_t)b;
+                while (blk < want) {   // run ahead with the twist alone
+#if PHET_X86
+                    if (avx) twist_block_avx512(key);
+                    else
+#endif
+                        twist_scalar(key);
+                    ++blk;
+                    if (g == 0 && blk % kSnapEvery == 0) snaps.insert(snaps.end(), key, key + kN);
+                }
+                E *dst = w + (size_t)((want * kN) % ring.cap);
+                if (sizeof(E) == 4) {
+#if PHET_X86
+                    if (avx) temper_avx512(key, reinterpret_cast<uint32_t *>(dst));
+                    else
+#endif
+                        temper_scalar(key, reinterpret_cast<uint32_t *>(dst));
+                } else {
+#if PHET_X86
+                    if (avx) temper16_avx512(key, reinterpret_cast<uint16_t *>(dst));
+                    else
+#endif
+                    {
+                        temper_scalar(key, out);
+                        for (int i = 0; i < kN; ++i) dst[i] = (E)out[i];
+                    }
+                }
+                if (dst == w) memcpy(w + ring.cap, w, sizeof(E) * kCarry);   // the wrap-around mirror
+            }
+            ring.ready[reg % ring.nreg].store(reg + 1, std::memory_order_release);
+        }
+    }
+
+    template <typename E>
+    void ring_scanner_main() {
+        RingSrc<E> src(&ring, abs0);
+        unsigned spins = 0;
+        for (uint64_t k = 0;; ++k) {
+            while (k >= submitted.load(std::memory_order_acquire)) {
+                if (closed.load(std::memory_order_acquire) && k >= submitted.load(std::memory_order_acquire)) {
+                    end_pos = src.abs;
+                    return;
+                }
+                backoff(spins);
+            }
+            const PermDesc &d = desc[k & (kQ - 1)];
+            start[k & (kQ - 1)] = src.abs;
+            scan_pos.store(src.abs, std::memory_order_release);
+            started.store(k + 1, std::memory_order_release);
+            publish_low();
+            shuffle_draws_from<uint16_t>(src, mt->avx512, d.n, (uint16_t *)nullptr);
+        }
+    }
+
+    void scanner_main() {  // plain mode: scans on the caller's generator, records its state at each start
         unsigned spins = 0;
         for (uint64_t k = 0;; ++k) {
             while (k >= submitted.load(std::memory_order_acquire)) {
@@ -456,6 +692,7 @@ struct phet_mt_par {
             }
             finished_prefix.store(f, std::memory_order_release);
         }
+        if (use_ring) publish_low();
         bool last;
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -464,8 +701,9 @@ struct phet_mt_par {
         if (last) cv.notify_all();
     }
 
+    template <typename E>
     void worker_main() {
-        phet_mt *local = mt_alloc();
+        phet_mt *local = use_ring ? nullptr : mt_alloc();
         unsigned spins = 0;
         for (;;) {
             uint64_t k = claimed.load(std::memory_order_relaxed);
@@ -477,10 +715,16 @@ struct phet_mt_par {
             if (!claimed.compare_exchange_weak(k, k + 1, std::memory_order_acq_rel)) continue;
             const PermDesc &d = desc[k & (kQ - 1)];
             const int64_t ticket = d.ticket;
-            if (d.dst && d.n >= 2 && local) {
-                local->load(d.key, d.pos);
-                if (d.eb == 2) shuffle_draws<uint16_t>(*local, d.n, static_cast<uint16_t *>(d.dst));
-                else shuffle_draws<uint32_t>(*local, d.n, static_cast<uint32_t *>(d.dst));
+            if (d.dst && d.n >= 2) {
+                if (use_ring) {
+                    RingSrc<E> src(&ring, start[k & (kQ - 1)]);
+                    if (d.eb == 2) shuffle_draws_from<uint16_t>(src, mt->avx512, d.n, static_cast<uint16_t *>(d.dst));
+                    else shuffle_draws_from<uint32_t>(src, mt->avx512, d.n, static_cast<uint32_t *>(d.dst));
+                } else if (local) {
+                    local->load(d.key, d.pos);
+                    if (d.eb == 2) shuffle_draws<uint16_t>(*local, d.n, static_cast<uint16_t *>(d.dst));
+                    else shuffle_draws<uint32_t>(*local, d.n, static_cast<uint32_t *>(d.dst));
+                }
             }
             finish(k, ticket);
         }
@@ -601,12 +845,18 @@ int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par *
     MT_REQUIRE(mt != nullptr && out != nullptr, "NULL argument");
     MT_REQUIRE(max_n >= 1 && max_n < ((int64_t)1 << 31), "max_n must be in [1, 2^31)");
     *out = nullptr;
+    const unsigned hw = std::thread::hardware_concurrency();
+    int gens = 4;
+    if (const char *w = getenv("PHET_REPLAY_GENERATORS")) gens = atoi(w) >= 0 ? atoi(w) : 4;
     if (workers <= 0) {
         workers = 4;
         if (const char *w = getenv("PHET_REPLAY_WORKERS")) workers = atoi(w) > 0 ? atoi(w) : 4;
-        const unsigned hw = std::thread::hardware_concurrency();
-        if (hw && (unsigned)workers + 2 > hw) workers = hw > 2 ? (int)hw - 2 : 1;
     }
+    if (hw && (unsigned)(workers + gens + 1) > hw) {   // not enough cores for the ring pipeline: scanner generates for itself
+        gens = 0;
+        if ((unsigned)workers + 1 > hw) workers = hw > 1 ? (int)hw - 1 : 1;
+    }
+    if (max_n < 2048) gens = 0;   // short permutations: the stream is consumed faster than threads can hand it over
     phet_mt_par *p = new (std::nothrow) phet_mt_par();
     if (!p) {
         phet::set_error("out of host memory");
@@ -614,16 +864,64 @@ int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par *
     }
     p->mt = mt;
     p->max_n = max_n;
+    p->use_ring = gens > 0;
     for (size_t i = 0; i < phet_mt_par::kQ; ++i) p->done[i].store(0, std::memory_order_relaxed);
-    p->tscan = std::thread(&phet_mt_par::scanner_main, p);
-    for (int w = 0; w < workers; ++w) p->workers.emplace_back(&phet_mt_par::worker_main, p);
+    const bool narrow = max_n <= 65536;
+    if (p->use_ring) {
+        OutRing &r = p->ring;
+        r.ebytes = narrow ? 2 : 4;
+        r.region_elems = (size_t)kRegionBlocks * kN;
+        size_t ring_mb = 8;
+        if (const char *e = getenv("PHET_REPLAY_RING_MB")) ring_mb = atoi(e) > 0 ? (size_t)atoi(e) : 8;
+        size_t elems = (ring_mb << 20) / (size_t)r.ebytes;
+        const size_t need = (size_t)max_n * 12;   // several permutations' outputs (~1.4 n each) in flight
+        if (elems < need) elems = need;
+        r.nreg = (elems + r.region_elems - 1) / r.region_elems;
+        if (r.nreg < (size_t)(2 * gens + 2)) r.nreg = (size_t)(2 * gens + 2);
+        r.cap = r.nreg * r.region_elems;
+        void *mem = nullptr;
+        if (posix_memalign(&mem, 64, (r.cap + kCarry + 64) * (size_t)r.ebytes) != 0 || !mem) {
+            delete p;
+            phet::set_error("out of host memory");
+            return PHET_ERR_NOMEM;
+        }
+        r.w = mem;
+        r.ready.reset(new std::atomic<uint64_t>[r.nreg]);
+        for (size_t i = 0; i < r.nreg; ++i) r.ready[i].store(0, std::memory_order_relaxed);
+        int pos = 0;
+        mt->state(p->key0, &pos);
+        p->abs0 = (uint64_t)pos;
+        p->snaps.assign(p->key0, p->key0 + kN);
+        p->scan_pos.store(p->abs0, std::memory_order_release);
+        for (int g = 0; g < gens; ++g) {
+            if (narrow) p->generators.emplace_back(&phet_mt_par::generator_main<uint16_t>, p, g, gens);
+            else p->generators.emplace_back(&phet_mt_par::generator_main<uint32_t>, p, g, gens);
+        }
+        if (narrow) p->tscan = std::thread(&phet_mt_par::ring_scanner_main<uint16_t>, p);
+        else p->tscan = std::thread(&phet_mt_par::ring_scanner_main<uint32_t>, p);
+    } else {
+        p->tscan = std::thread(&phet_mt_par::scanner_main, p);
+    }
+    for (int w = 0; w < workers; ++w) {
+        if (narrow) p->workers.emplace_back(&phet_mt_par::worker_main<uint16_t>, p);
+        else p->workers.emplace_back(&phet_mt_par::worker_main<uint32_t>, p);
+    }
     *out = p;
+    return PHET_OK;
+}
+
+int phet_mt_par_threads(const phet_mt_par *p, int32_t out[3]) {
+    MT_REQUIRE(p != nullptr && out != nullptr, "NULL argument");
+    out[0] = (int32_t)p->generators.size();
+    out[1] = 1;
+    out[2] = (int32_t)p->workers.size();
     return PHET_OK;
 }
 
 int phet_mt_par_submit(phet_mt_par *p, const phet_mt_job *jobs, int32_t n_jobs, int64_t rounds, int64_t *ticket_out) {
     MT_REQUIRE(p != nullptr && jobs != nullptr && n_jobs >= 1 && rounds >= 0 && ticket_out != nullptr, "bad arguments");
     MT_REQUIRE(!p->closed.load(), "the replay is already closed");
+
     if (int rc = check_jobs(jobs, n_jobs, p->max_n)) return rc;
     int64_t ticket;
     {
@@ -659,8 +957,36 @@ int phet_mt_par_wait(phet_mt_par *p, int64_t ticket) {
 int phet_mt_par_end(phet_mt_par *p) {
     if (!p) return PHET_OK;
     p->closed.store(true, std::memory_order_release);
-    p->tscan.join();  // the caller's generator is now where the reference's stream would be
+    p->tscan.join();  // plain mode: the caller's generator is now where the reference's stream would be
     for (std::thread &w : p->workers) w.join();
+    if (p->use_ring) {
+        p->ring.stop.store(true, std::memory_order_release);
+        for (std::thread &g : p->generators) g.join();
+        // the stream position the scan ended at -> NumPy's (key, pos), re-twisted from the nearest kept state
+        if (p->end_pos != p->abs0) {
+            uint64_t block = p->end_pos / kN;
+            int off = (int)(p->end_pos % kN);
+            if (off == 0) {  // NumPy regenerates lazily: the last block fully consumed, pos = 624
+                --block;
+                off = kN;
+            }
+            alignas(64) uint32_t key[kN + 32];
+            uint64_t s0 = block / kSnapEvery;
+            const uint64_t have = p->snaps.size() / kN;   // generator 0 may not have reached the last multiple
+            if (s0 >= have) s0 = have - 1;
+            memcpy(key, p->snaps.data() + (size_t)s0 * kN, sizeof(uint32_t) * kN);
+            memset(key + kN, 0, sizeof(uint32_t) * 32);
+            for (uint64_t b2 = s0 * kSnapEvery; b2 < block; ++b2) {
+#if PHET_X86
+                if (p->mt->avx512) twist_block_avx512(key);
+                else
+#endif
+                    twist_scalar(key);
+            }
+            p->mt->load(key, off);
+        }
+        free(p->ring.w);
+    }
     delete p;
     return PHET_OK;
 }

@@ -141,3 +141,33 @@ def test_parallel_replay_skip_blocks_only_advance():
     a.shuffle_draws([5000, 4000], 30, store=False)
     b.shuffle_draws([5000, 4000], 30, store=False, workers=2, chunks=3)
     assert np.array_equal(a.state()[0], b.state()[0]) and a.state()[1] == b.state()[1]
+
+
+@pytest.mark.parametrize("sizes,rounds,env", [
+    ([25000, 25000], 150, {}),                                                   # 16-bit ring, default threads
+    ([25000, 25000], 150, {"PHET_REPLAY_RING_MB": "1", "PHET_REPLAY_GENERATORS": "2"}),   # a ring that wraps every few permutations
+    ([30000, 20000], 120, {"PHET_REPLAY_GENERATORS": "3"}),
+    ([100000, 70000], 24, {"PHET_REPLAY_GENERATORS": "2"}),                      # 32-bit ring
+    ([5000, 300], 900, {"PHET_REPLAY_RING_MB": "1"}),
+    ([25000, 25000], 60, {"PHET_REPLAY_GENERATORS": "0"}),                       # no ring: scanner generates for itself
+    ([25000, 25000], 60, {"PHET_MT_SCALAR": "1", "PHET_REPLAY_GENERATORS": "2"}),         # no AVX-512
+])
+def test_ring_replay_equals_sequential(sizes, rounds, env):
+    """Generator threads -> ring -> scanner -> store workers against the one-thread scan: same targets, same final
+    state, for 16- and 32-bit rings, rings that wrap often, and the fallbacks (fresh process: the knobs are read once)."""
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from phet_b200._capi import MtStream\n"
+            "np.random.seed(777); np.random.randint(0, 2**31 - 1, size=100)\n"
+            "a, b = MtStream.from_numpy(), MtStream.from_numpy()\n"
+            "da = a.shuffle_draws(%r, %d)\n"
+            "db = b.shuffle_draws(%r, %d, workers=3, chunks=6)\n"
+            "ok = all(np.array_equal(x, y) for x, y in zip(da, db))\n"
+            "ka, pa = a.state(); kb, pb = b.state()\n"
+            "ok = ok and np.array_equal(ka, kb) and pa == pb and np.array_equal(a.permutation(999), b.permutation(999))\n"
+            "print(int(ok), *b.par_threads)\n" % (ROOT, sizes, rounds, sizes, rounds))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, check=True, timeout=600).stdout.split()
+    assert out[0] == "1", out
+    if env.get("PHET_REPLAY_GENERATORS") == "0":
+        assert out[1] == "0"
