@@ -30,6 +30,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -300,6 +301,7 @@ struct OutRing {
     std::unique_ptr<std::atomic<uint64_t>[]> ready;   // per ring slot: 1 + index of the region it holds, once complete
     alignas(64) std::atomic<uint64_t> low{0};         // outputs below this stream position are no longer read
     std::atomic<bool> stop{false};
+    std::atomic<uint64_t> reader_spins{0}, writer_spins{0};   // diagnostics: who waits for whom
 };
 
 template <typename E>
@@ -323,7 +325,10 @@ struct RingSrc {
                 }
                 if (r->stop.load(std::memory_order_relaxed)) break;
                 cpu_relax();
-                if ((++spins & 4095u) == 0) std::this_thread::yield();
+                if ((++spins & 4095u) == 0) {
+                    r->reader_spins.fetch_add(4096, std::memory_order_relaxed);
+                    std::this_thread::yield();
+                }
             }
         }
         p = static_cast<const E *>(r->w) + idx;
@@ -494,6 +499,109 @@ MT_AVX512 void shuffle_draws_avx512(Src &in, uint32_t n, J *dst) {
 }
 #endif
 
+#if PHET_X86
+// Count-only scan of 16-bit outputs (the scanner thread of the parallel replay, classes <= 65536 cells): the same
+// trips on 32 lanes per vector -- no widening, 4 compares + 2 mask merges per 64 outputs instead of 8 compares and
+// a dozen mask moves -- 128 outputs per trip where an octave is wide enough for the extra uncertainty of i to cost
+// little.  v + k saturates (vpaddusw), so the trips are only taken while i + 128 < 65535.
+template <typename Src>
+MT_AVX512 void count_draws16_avx512(Src &in, uint32_t n) {
+    const __m512i lane32 = _mm512_set_epi16(31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9,
+                                            8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m512i lanek[4] = {lane32, _mm512_add_epi16(lane32, _mm512_set1_epi16(32)), _mm512_add_epi16(lane32, _mm512_set1_epi16(64)),
+                              _mm512_add_epi16(lane32, _mm512_set1_epi16(96))};
+    uint32_t i = n - 1;
+    while (i >= kScalarBelow) {
+        const uint32_t mask = bitmask(i), lo = (mask >> 1) + 1;
+        const uint32_t floor_i = lo > kScalarBelow ? lo : kScalarBelow;
+        if (i + 160u >= 65535u) {   // (only the first ~160 draws of a 65,536-cell class) one output at a time
+            uint32_t r;
+            while ((r = (in.next() & mask)) > i) {
+            }
+            --i;
+            continue;
+        }
+        const __m512i vm = _mm512_set1_epi16((short)mask);
+        if (mask >= 8191u) {
+            while (i >= floor_i) {
+                in.need(128);
+                const __m512i vi = _mm512_set1_epi16((short)i);
+                const uint16_t *p = reinterpret_cast<const uint16_t *>(in.p);
+                __mmask32 A[4], S[4];
+#pragma GCC unroll 4
+                for (int q = 0; q < 4; ++q) {
+                    const __m512i vq = _mm512_and_si512(_mm512_loadu_si512(p + 32 * q), vm);
+                    A[q] = _mm512_cmple_epu16_mask(vq, vi);                                   // not rejected: v <= i
+                    S[q] = _mm512_cmple_epu16_mask(_mm512_adds_epu16(vq, lanek[q]), vi);      // accepted for sure: v + k <= i
+                }
+                uint64_t sure0 = _cvtmask64_u64(_mm512_kunpackd(S[1], S[0])), sure1 = _cvtmask64_u64(_mm512_kunpackd(S[3], S[2]));
+                uint64_t amb0 = _cvtmask64_u64(_mm512_kunpackd(A[1], A[0])) & ~sure0;
+                uint64_t amb1 = _cvtmask64_u64(_mm512_kunpackd(A[3], A[2])) & ~sure1;
+                while (__builtin_expect(amb0 != 0, 0)) {   // in lane order: everything before lane k is decided
+                    const int k = __builtin_ctzll(amb0);
+                    const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure0 & ((1ull << k) - 1ull));
+                    if (((uint32_t)p[k] & mask) <= ik) sure0 |= 1ull << k;
+                    amb0 &= amb0 - 1;
+                }
+                const uint32_t t0 = (uint32_t)__builtin_popcountll(sure0);
+                while (__builtin_expect(amb1 != 0, 0)) {
+                    const int k = __builtin_ctzll(amb1);
+                    const uint32_t ik = i - t0 - (uint32_t)__builtin_popcountll(sure1 & ((1ull << k) - 1ull));
+                    if (((uint32_t)p[64 + k] & mask) <= ik) sure1 |= 1ull << k;
+                    amb1 &= amb1 - 1;
+                }
+                uint32_t total = t0 + (uint32_t)__builtin_popcountll(sure1);
+                const uint32_t room = i - lo + 1;   // accepts left in this octave
+                int used = 128;
+                if (__builtin_expect(total >= room, 0)) {   // stop right behind the room-th accepted lane
+                    if (room <= t0) used = __builtin_ctzll(_pdep_u64(1ull << (room - 1), sure0)) + 1;
+                    else used = 64 + __builtin_ctzll(_pdep_u64(1ull << (room - t0 - 1), sure1)) + 1;
+                    total = room;
+                }
+                i -= total;
+                in.advance(used);
+            }
+        } else {
+            while (i >= floor_i) {
+                in.need(64);
+                const __m512i vi = _mm512_set1_epi16((short)i);
+                const uint16_t *p = reinterpret_cast<const uint16_t *>(in.p);
+                __mmask32 A[2], S[2];
+#pragma GCC unroll 2
+                for (int q = 0; q < 2; ++q) {
+                    const __m512i vq = _mm512_and_si512(_mm512_loadu_si512(p + 32 * q), vm);
+                    A[q] = _mm512_cmple_epu16_mask(vq, vi);
+                    S[q] = _mm512_cmple_epu16_mask(_mm512_adds_epu16(vq, lanek[q]), vi);
+                }
+                uint64_t sure = _cvtmask64_u64(_mm512_kunpackd(S[1], S[0]));
+                uint64_t amb = _cvtmask64_u64(_mm512_kunpackd(A[1], A[0])) & ~sure;
+                while (__builtin_expect(amb != 0, 0)) {
+                    const int k = __builtin_ctzll(amb);
+                    const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure & ((1ull << k) - 1ull));
+                    if (((uint32_t)p[k] & mask) <= ik) sure |= 1ull << k;
+                    amb &= amb - 1;
+                }
+                uint32_t total = (uint32_t)__builtin_popcountll(sure);
+                const uint32_t room = i - lo + 1;
+                int used = 64;
+                if (__builtin_expect(total >= room, 0)) {
+                    used = __builtin_ctzll(_pdep_u64(1ull << (room - 1), sure)) + 1;
+                    total = room;
+                }
+                i -= total;
+                in.advance(used);
+            }
+        }
+    }
+    for (; i >= 1; --i) {   // the tail, one output at a time
+        const uint32_t mask = bitmask(i);
+        uint32_t r;
+        while ((r = (in.next() & mask)) > i) {
+        }
+    }
+}
+#endif
+
 template <typename J, typename Src>
 void shuffle_draws_from(Src &src, bool avx512, uint32_t n, J *dst) {
     if (n < 2) return;
@@ -605,8 +713,10 @@ struct phet_mt_par {
         for (uint64_t reg = (uint64_t)g;; reg += (uint64_t)G) {
             // room: region `reg` overwrites the slot of region reg - nreg
             while (!ring.stop.load(std::memory_order_relaxed) &&
-                   (reg + 1) * ring.region_elems > ring.low.load(std::memory_order_acquire) + ring.cap)
+                   (reg + 1) * ring.region_elems > ring.low.load(std::memory_order_acquire) + ring.cap) {
                 backoff(spins);
+                if ((spins & 1023u) == 0) ring.writer_spins.fetch_add(1024, std::memory_order_relaxed);
+            }
             if (ring.stop.load(std::memory_order_relaxed)) return;
             for (int b = 0; b < kRegionBlocks; ++b) {
                 const uint64_t want = reg * kRegionBlocks + (uint64_t)b;
@@ -659,9 +769,21 @@ struct phet_mt_par {
             scan_pos.store(src.abs, std::memory_order_release);
             started.store(k + 1, std::memory_order_release);
             publish_low();
-            shuffle_draws_from<uint16_t>(src, mt->avx512, d.n, (uint16_t *)nullptr);
+            count_only(src, d.n);
         }
     }
+
+    void count_only(RingSrc<uint16_t> &src, uint32_t n) {
+        if (n < 2) return;
+#if PHET_X86
+        if (mt->avx512) {
+            count_draws16_avx512(src, n);
+            return;
+        }
+#endif
+        shuffle_draws_from<uint16_t>(src, false, n, (uint16_t *)nullptr);
+    }
+    void count_only(RingSrc<uint32_t> &src, uint32_t n) { shuffle_draws_from<uint16_t>(src, mt->avx512, n, (uint16_t *)nullptr); }
 
     void scanner_main() {  // plain mode: scans on the caller's generator, records its state at each start
         unsigned spins = 0;
@@ -985,6 +1107,9 @@ int phet_mt_par_end(phet_mt_par *p) {
             }
             p->mt->load(key, off);
         }
+        if (getenv("PHET_REPLAY_DEBUG"))
+            fprintf(stderr, "replay: readers spun %llu (starved by the generators), generators spun %llu (ring full)\n",
+                    (unsigned long long)p->ring.reader_spins.load(), (unsigned long long)p->ring.writer_spins.load());
         free(p->ring.w);
     }
     delete p;

@@ -14,8 +14,8 @@ int main(int argc, char** argv){
       std::vector<int64_t> tk(nblk);
       for (int b=0;b<nblk;b++){
           if (b>=slots) phet_mt_par_wait(par, tk[b-slots]);
-          uint16_t* d=buf[b%slots].data();
-          phet_mt_job j[2]={{n,d,(int64_t)n*2,2},{n,d+(size_t)per*n,(int64_t)n*2,2}};
+          uint16_t* d=getenv("SKIP")?nullptr:buf[b%slots].data();
+          phet_mt_job j[2]={{n,d,(int64_t)n*2,2},{n,d?d+(size_t)per*n:nullptr,(int64_t)n*2,2}};
           phet_mt_par_submit(par,j,2,per,&tk[b]);
       }
       for (int b=nblk-slots;b<nblk;b++) phet_mt_par_wait(par, tk[b]);
