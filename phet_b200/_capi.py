@@ -566,7 +566,7 @@ class Context:
         _check(self.lib.phet_write_buffer(self.h, which, _ptr(arr), arr.nbytes))
 
     def step3_path(self):
-        return {0: "none", 1: "full-warp sort", 2: "half-warp sort", 3: "bound-and-prune"}[int(self.lib.phet_step3_path(self.h))]
+        return {0: "none", 1: "full-warp sort", 2: "half-warp sort", 3: "bound-and-prune", 4: "scatter bound-and-prune"}[int(self.lib.phet_step3_path(self.h))]
 
     def launch_count(self):
         return int(self.lib.phet_launch_count(self.h))

@@ -19,7 +19,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libphet_b200.so")
 STAMP = LIB + ".stamp"
 SOURCES = ["api.cu", "normalize.cu", "finalize.cu", "classstats.cu", "rank.cu", "mtx.cu", "anova.cu", "step3big.cu", "step1_f32.cu", "step1_f64.cu", "step3_f32.cu", "step3_f64.cu",
-           "step3p_f32.cu", "step3p_f64.cu", "fy_apply.cu", "replay.cu", "mt_replay.cpp"]
+           "step3p_f32.cu", "step3p_f64.cu", "step3s_f32.cu", "step3s_f64.cu", "fy_apply.cu", "replay.cu", "mt_replay.cpp"]
 # host-only sources go through g++ directly (AVX-512 intrinsics behind target attributes + a runtime CPU check)
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-fno-math-errno"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

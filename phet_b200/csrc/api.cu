@@ -168,6 +168,50 @@ static void coprime_list(uint32_t n, uint32_t *out) {
     }
 }
 
+// a^-1 mod n for gcd(a, n) = 1 (n == 1: 0)
+static uint32_t inverse_mod(uint32_t a, uint32_t n) {
+    int64_t t = 0, nt = 1, r = (int64_t)n, nr = (int64_t)(a % n);
+    while (nr != 0) {
+        const int64_t qq = r / nr;
+        const int64_t t2 = t - qq * nt;
+        t = nt;
+        nt = t2;
+        const int64_t r2 = r - qq * nr;
+        r = nr;
+        nr = r2;
+    }
+    if (t < 0) t += (int64_t)n;
+    return (uint32_t)(t % (int64_t)n);
+}
+
+bool step3_scatter_applies_f32(const phet_ctx *c, const Step3Args &a);   // step3s_f32.cu / step3s_f64.cu
+bool step3_scatter_applies_f64(const phet_ctx *c, const Step3Args &a);
+
+// The scatter kernel (step3s_impl.cuh) will serve Step 3 of a fit with this geometry: table modes then provide the
+// inverse view of the permutations (slice of every cell) instead of, or next to, the forward one.
+bool step3_wants_inverse(phet_ctx *c, int64_t m, int64_t n_last) {
+    Step3Args a{};
+    a.n0 = c->n0;
+    a.n1 = c->n1;
+    a.m = m;
+    a.n_slices = c->n_slices;
+    a.n_last = n_last;
+    a.min_c = (c->n_slices - 1) * m + n_last;
+    a.cap = m > n_last ? m : n_last;
+    a.perm_mode = PHET_PERM_HOST;
+    return c->storage == PHET_F32 ? step3_scatter_applies_f32(c, a) : step3_scatter_applies_f64(c, a);
+}
+
+// Inverse view of uploaded permutation tables: slice_of[g][perm[g][t]] = min(t / m, last slice).
+__global__ void k_slice_of_from_perm(const uint32_t *__restrict__ perm, int64_t n, int64_t min_c, uint16_t *__restrict__ slice_of,
+                                     int64_t ld, uint32_t magic_m, uint32_t last_slice) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t g = i / min_c;
+    const uint32_t t = (uint32_t)(i - g * min_c);
+    slice_of[g * ld + perm[i]] = (uint16_t)min(__umulhi(t, magic_m), last_slice);
+}
+
 int launch_step1(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t s_begin, int64_t s_end,
                  const phet_step1_params *prm, int accumulate) {
     Step1Args a;
@@ -242,6 +286,16 @@ int launch_step3(phet_ctx *c, int64_t g_begin, int64_t g_end, int64_t m, int per
     a.perm_g0 = c->perm_g0;
     a.coprime0 = c->coprime.p;
     a.coprime1 = c->coprime.p ? c->coprime.p + kCoprimeCount : nullptr;
+    a.coprime_inv0 = c->coprime_inv.p;
+    a.coprime_inv1 = c->coprime_inv.p ? c->coprime_inv.p + kCoprimeCount : nullptr;
+    a.slice_of = (perm_mode == PHET_PERM_HOST && c->slice_of_valid) ? c->slice_of.p : nullptr;
+    a.slice_ld = c->n0 + c->n1;
+    if (perm_mode == PHET_PERM_HOST && !c->perm_fwd_valid) {
+        // only the inverse view of the tables was written (replay mode): the scatter kernel has to be the one that runs
+        PHET_REQUIRE(a.slice_of != nullptr && n_last <= 512 && step3_wants_inverse(c, m, n_last),
+                     "resident permutation tables hold the inverse view only, but this launch needs the forward view "
+                     "(PHET_OPT_KEEP_H / PHET_STEP3_IMPL changed since they were drawn?)");
+    }
     a.seed = seed;
     a.tab_full = c->tab_full.p;
     a.tab_last = c->tab_last.p;
@@ -306,7 +360,8 @@ int phet_ctx_create(int device, void *stream, phet_ctx **out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     if (const char *impl = getenv("PHET_STEP1_IMPL")) c->step1_impl = (strcmp(impl, "warp") == 0) ? 1 : 0;
-    if (const char *impl = getenv("PHET_STEP3_IMPL")) c->step3_impl = (strcmp(impl, "sort") == 0) ? 1 : 0;
+    if (const char *impl = getenv("PHET_STEP3_IMPL"))   // sort: exact h of every slice; prune: gather bound-and-prune; scatter: streaming bound-and-prune
+        c->step3_impl = strcmp(impl, "sort") == 0 ? 1 : strcmp(impl, "prune") == 0 ? 2 : strcmp(impl, "scatter") == 0 ? 3 : 0;
     if (const char *fb = getenv("PHET_STEP1_FORCE_BIG")) c->pair_force_big = atoi(fb) != 0;
     if (const char *bt = getenv("PHET_STEP1_BIG_THREADS")) {
         const int t = atoi(bt);
@@ -630,6 +685,8 @@ int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ct
     if (perm_mode != PHET_PERM_RESIDENT) {
         c->perm_g0 = 0;
         c->perm_rows = 0;
+        c->slice_of_valid = false;
+        c->perm_fwd_valid = false;
     }
     int64_t min_c = c->n0 < c->n1 ? c->n0 : c->n1;
     int64_t n_slices = (min_c + m - 1) / m;
@@ -691,20 +748,40 @@ int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ct
         PHET_REQUIRE(hbad == 0, "host permutations contain a position outside its class");
         c->perm_rows = c->G;
         c->perm_cols = min_c;
+        c->perm_fwd_valid = true;
+        if (n_last <= 512 && step3_wants_inverse(c, m, n_last)) {
+            // the scatter kernel reads the INVERSE view: the slice of every cell in storage order
+            const int64_t ld = c->n0 + c->n1;
+            if (int e = c->slice_of.alloc((size_t)c->G * (size_t)ld)) return e;
+            PHET_CUDA(cudaMemsetAsync(c->slice_of.p, 0xFF, sizeof(uint16_t) * (size_t)c->G * (size_t)ld, c->stream));
+            const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint64_t)m) + 1u;
+            k_slice_of_from_perm<<<blocks, 256, 0, c->stream>>>(c->perm0.p, (int64_t)n, min_c, c->slice_of.p, ld, magic,
+                                                                 (uint32_t)(n_slices - 1));
+            k_slice_of_from_perm<<<blocks, 256, 0, c->stream>>>(c->perm1.p, (int64_t)n, min_c, c->slice_of.p + c->n0, ld, magic,
+                                                                 (uint32_t)(n_slices - 1));
+            c->launches += 2;
+            PHET_CUDA(cudaGetLastError());
+            c->slice_of_valid = true;
+        }
     } else if (perm_mode == PHET_PERM_RESIDENT) {
-        PHET_REQUIRE(c->perm_rows > 0 && c->perm_cols == min_c && c->perm0.p && c->perm1.p,
+        PHET_REQUIRE(c->perm_rows > 0 && c->perm_cols == min_c && (c->perm_fwd_valid || c->slice_of_valid),
                      "PHET_PERM_RESIDENT: no permutation tables of this shape are resident");
     } else if (perm_mode == PHET_PERM_REPLAY) {
         // the permutation tables are filled block by block on the device (replay.cu)
     } else {
         if (c->coprime.p == nullptr || c->coprime_n0 != c->n0 || c->coprime_n1 != c->n1) {
-            std::vector<uint32_t> cp(2 * kCoprimeCount);
+            std::vector<uint32_t> cp(2 * kCoprimeCount), cpi(2 * kCoprimeCount);
             coprime_list((uint32_t)c->n0, cp.data());
             coprime_list((uint32_t)c->n1, cp.data() + kCoprimeCount);
+            for (int k = 0; k < 2 * kCoprimeCount; ++k)   // cell -> permuted index needs the inverse multipliers (scatter kernel)
+                cpi[k] = inverse_mod(cp[k], (uint32_t)(k < kCoprimeCount ? c->n0 : c->n1));
             if (int e = c->coprime.alloc(2 * kCoprimeCount)) return e;
+            if (int e = c->coprime_inv.alloc(2 * kCoprimeCount)) return e;
             PHET_CUDA(cudaMemcpyAsync(c->coprime.p, cp.data(), sizeof(uint32_t) * cp.size(), cudaMemcpyHostToDevice,
                                       c->stream));
-            PHET_CUDA(cudaStreamSynchronize(c->stream));  // cp is a stack-lifetime host buffer
+            PHET_CUDA(cudaMemcpyAsync(c->coprime_inv.p, cpi.data(), sizeof(uint32_t) * cpi.size(), cudaMemcpyHostToDevice,
+                                      c->stream));
+            PHET_CUDA(cudaStreamSynchronize(c->stream));  // cp / cpi are stack-lifetime host buffers
             c->coprime_n0 = c->n0;
             c->coprime_n1 = c->n1;
         }

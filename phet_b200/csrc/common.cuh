@@ -136,6 +136,9 @@ struct phet_ctx {
     phet::DevBuf<int32_t> H;             // [G][n_slices]
     phet::DevBuf<uint32_t> perm0, perm1; // [genes from perm_g0][min_c] (host mode: all G genes; replay mode: one block)
     int64_t perm_g0 = 0;
+    phet::DevBuf<uint16_t> slice_of;       // inverse view of the same tables: [perm_rows][n0 + n1] slice of every cell (scatter Step 3)
+    bool slice_of_valid = false, perm_fwd_valid = false;   // which views of the tables are filled
+    phet::DevBuf<uint32_t> coprime_inv;    // [2][kCoprimeCount]: inverses of the affine multipliers mod n0 / n1
     int64_t perm_rows = 0, perm_cols = 0;  // resident tables: genes [perm_g0, perm_g0 + perm_rows) x perm_cols positions (0: none)
     cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};
     bool phases_valid = false;
@@ -193,6 +196,10 @@ int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out,
 int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
 int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
                     const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, cudaStream_t stream);
+// the same shuffles written as the INVERSE view: slice_out[p * out_ld + map[x[q]]] = q < take ? min(q / m, last_slice) : 0xFFFF
+int launch_fy_apply_inverse(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
+                            const int32_t *map_dev, uint16_t *slice_out, int64_t out_ld, int64_t m, int64_t last_slice, cudaStream_t stream);
+bool step3_wants_inverse(phet_ctx *c, int64_t m, int64_t n_last);   // the scatter kernel will serve Step 3 of this fit
 // shared by api.cu and replay.cu
 int prepare_matrix(phet_ctx *c, int64_t N, int64_t G, int dtype, int normalize, int storage, int64_t g_begin, int64_t g_end);
 int step3_prepare(phet_ctx *c, int64_t m, int perm_mode, const uint32_t *perm_ctrl, const uint32_t *perm_case,

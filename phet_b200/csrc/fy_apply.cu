@@ -31,9 +31,15 @@ struct FyGlobal {  // x in a global scratch row (L2): volatile keeps the accesse
     __device__ __forceinline__ void put(uint32_t k, uint32_t v) const { x[k] = v; }
 };
 
+struct FyInv {        // inverse output: slice of every cell instead of the cell at every permuted position
+    uint16_t *out;    // [count][out_ld]; nullptr = forward output
+    uint32_t m, last_slice, magic_m;
+};
+
 template <typename J, typename Store>
 __device__ __forceinline__ void fy_one(const Store &st, const J *__restrict__ draws, uint32_t n, uint32_t take,
-                                       const int32_t *__restrict__ map, uint32_t *__restrict__ out, int lane) {
+                                       const int32_t *__restrict__ map, uint32_t *__restrict__ out, int lane,
+                                       const FyInv &inv, uint16_t *__restrict__ inv_out) {
     for (uint32_t q = lane; q < n; q += 32) st.put(q, q);
     __syncwarp();
     const uint32_t steps = n - 1;
@@ -82,9 +88,17 @@ __device__ __forceinline__ void fy_one(const Store &st, const J *__restrict__ dr
         }
     }
     __syncwarp();
-    for (uint32_t q = lane; q < take; q += 32) {
-        const uint32_t v = st.get(q);
-        out[q] = map ? (uint32_t)__ldg(map + v) : v;
+    if (inv_out != nullptr) {   // every cell of the class is written once: its slice, or 0xFFFF beyond the sliced positions
+        for (uint32_t q = lane; q < n; q += 32) {
+            const uint32_t v = st.get(q);
+            const uint32_t cell = map ? (uint32_t)__ldg(map + v) : v;
+            inv_out[cell] = q < take ? (uint16_t)min(__umulhi(q, inv.magic_m), inv.last_slice) : (uint16_t)0xFFFFu;
+        }
+    } else {
+        for (uint32_t q = lane; q < take; q += 32) {
+            const uint32_t v = st.get(q);
+            out[q] = map ? (uint32_t)__ldg(map + v) : v;
+        }
     }
     __syncwarp();
 }
@@ -99,6 +113,7 @@ struct FyArgs {
     int64_t out_ld;
     uint32_t *scratch;     // global variant: [grid warps][n]
     uint32_t x_bytes;      // shared variant: bytes per warp
+    FyInv inv;
 };
 
 template <typename J>
@@ -107,7 +122,8 @@ __global__ void __launch_bounds__(512) k_fy_apply_smem(const FyArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     FyShared<uint16_t> st{reinterpret_cast<uint16_t *>(fy_smem + (size_t)warp * a.x_bytes)};
     for (int64_t p = (int64_t)blockIdx.x * nw + warp; p < a.count; p += (int64_t)gridDim.x * nw)
-        fy_one<J>(st, static_cast<const J *>(a.draws) + p * a.ld, a.n, a.take, a.map, a.out + p * a.out_ld, lane);
+        fy_one<J>(st, static_cast<const J *>(a.draws) + p * a.ld, a.n, a.take, a.map, a.out ? a.out + p * a.out_ld : nullptr, lane, a.inv,
+                  a.inv.out ? a.inv.out + p * a.out_ld : nullptr);
 }
 
 template <typename J>
@@ -115,12 +131,13 @@ __global__ void __launch_bounds__(256) k_fy_apply_gmem(const FyArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     FyGlobal st{a.scratch + ((size_t)blockIdx.x * nw + warp) * a.n};
     for (int64_t p = (int64_t)blockIdx.x * nw + warp; p < a.count; p += (int64_t)gridDim.x * nw)
-        fy_one<J>(st, static_cast<const J *>(a.draws) + p * a.ld, a.n, a.take, a.map, a.out + p * a.out_ld, lane);
+        fy_one<J>(st, static_cast<const J *>(a.draws) + p * a.ld, a.n, a.take, a.map, a.out ? a.out + p * a.out_ld : nullptr, lane, a.inv,
+                  a.inv.out ? a.inv.out + p * a.out_ld : nullptr);
 }
 
 // draws_dev: device [count][ld] of 2- or 4-byte swap targets; out_dev: device uint32 [count][out_ld].
-int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
-                    const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, cudaStream_t stream) {
+static int launch_fy(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
+                     const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, const FyInv &inv, cudaStream_t stream) {
     if (count <= 0 || take <= 0) return PHET_OK;
     PHET_REQUIRE(n >= 1 && n < ((int64_t)1 << 31) && take <= n, "fy_apply: bad permutation length");
     PHET_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "fy_apply: elem_bytes must be 2 or 4");
@@ -135,6 +152,7 @@ int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t 
     a.out_ld = out_ld;
     a.scratch = nullptr;
     a.x_bytes = 0;
+    a.inv = inv;
     if (n <= 65536) {
         a.x_bytes = (uint32_t)((n * 2 + 15) / 16 * 16);
         int warps = (int)(kMaxSmemOptin / a.x_bytes);
@@ -165,6 +183,21 @@ int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t 
     c->launches++;
     PHET_CUDA(cudaGetLastError());
     return PHET_OK;
+}
+
+int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
+                    const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, cudaStream_t stream) {
+    FyInv inv{nullptr, 1u, 0u, 0u};
+    return launch_fy(c, draws_dev, elem_bytes, ld, n, count, take, map_dev, out_dev, out_ld, inv, stream);
+}
+
+int launch_fy_apply_inverse(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
+                            const int32_t *map_dev, uint16_t *slice_out, int64_t out_ld, int64_t m, int64_t last_slice,
+                            cudaStream_t stream) {
+    PHET_REQUIRE(m >= 1 && last_slice >= 0 && last_slice < 65535 && (uint64_t)take * (uint64_t)m < ((uint64_t)1 << 32),
+                 "fy_apply: slice geometry outside the 16-bit inverse table");
+    FyInv inv{slice_out, (uint32_t)m, (uint32_t)last_slice, (uint32_t)(((uint64_t)1 << 32) / (uint64_t)m) + 1u};
+    return launch_fy(c, draws_dev, elem_bytes, ld, n, count, take, map_dev, nullptr, out_ld, inv, stream);
 }
 
 }  // namespace phet

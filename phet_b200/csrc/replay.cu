@@ -339,10 +339,20 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
 
     // ---- matrix blocks: normalise + Step 1, then the Step-3 blocks of those genes as their draws arrive
     const bool keep = replay3 && p->keep_perm_tables != 0;
+    // which view of the permutations Step 3 reads: the scatter kernel wants the slice of every cell (16 bits per cell
+    // of both classes), the gather kernels the cell at every permuted position (32 bits per sliced position)
+    const bool inverse = replay3 && step3_wants_inverse(c, m, p->n_last);
+    const int64_t n_slices3 = (min_c + m - 1) / m;
     if (replay3) {
         const int64_t rows = keep ? (p->g3_end - p->g3_begin) : (rounds_per_block < max_count ? rounds_per_block : max_count);
-        if (int e = c->perm0.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
-        if (int e = c->perm1.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
+        if (inverse) {
+            if (int e = c->slice_of.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)(n0 + n1))) return fail(e);
+        } else {
+            if (int e = c->perm0.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
+            if (int e = c->perm1.alloc((size_t)(rows > 0 ? rows : 1) * (size_t)min_c)) return fail(e);
+        }
+        c->slice_of_valid = inverse;
+        c->perm_fwd_valid = !inverse;
     }
     auto step3_blocks = [&](int64_t x0, int64_t x1) -> int {
         if (!replay3) {
@@ -356,9 +366,16 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
             if (blk.first >= x1) break;        // belongs to a later matrix block
             const unsigned char *d0, *d1;
             if (int e = cons.take(blk.count, &d0, &d1)) return e;
-            const size_t row0 = keep ? (size_t)(blk.first - p->g3_begin) * (size_t)min_c : 0;  // kept tables: one row per gene of the range
-            if (int e = launch_fy_apply(c, d0, L.eb0, L.ld0, n0, blk.count, min_c, c->cls_pos.p, c->perm0.p + row0, min_c, c->stream)) return e;
-            if (int e = launch_fy_apply(c, d1, L.eb1, L.ld1, n1, blk.count, min_c, c->cls_pos.p + n0, c->perm1.p + row0, min_c, c->stream)) return e;
+            const size_t grow = keep ? (size_t)(blk.first - p->g3_begin) : 0;  // kept tables: one row per gene of the range
+            if (inverse) {
+                uint16_t *so = c->slice_of.p + grow * (size_t)(n0 + n1);
+                if (int e = launch_fy_apply_inverse(c, d0, L.eb0, L.ld0, n0, blk.count, min_c, c->cls_pos.p, so, n0 + n1, m, n_slices3 - 1, c->stream)) return e;
+                if (int e = launch_fy_apply_inverse(c, d1, L.eb1, L.ld1, n1, blk.count, min_c, c->cls_pos.p + n0, so + n0, n0 + n1, m, n_slices3 - 1, c->stream)) return e;
+            } else {
+                const size_t row0 = grow * (size_t)min_c;
+                if (int e = launch_fy_apply(c, d0, L.eb0, L.ld0, n0, blk.count, min_c, c->cls_pos.p, c->perm0.p + row0, min_c, c->stream)) return e;
+                if (int e = launch_fy_apply(c, d1, L.eb1, L.ld1, n1, blk.count, min_c, c->cls_pos.p + n0, c->perm1.p + row0, min_c, c->stream)) return e;
+            }
             c->perm_g0 = keep ? p->g3_begin : blk.first;
             if (int e = launch_step3(c, blk.first, blk.first + blk.count, m, PHET_PERM_HOST, 0, p->n_last)) return e;
         }

@@ -32,6 +32,9 @@ struct Step3Args {
     const uint32_t *perm0, *perm1;  // [genes from perm_g0][min_c] class-relative grouped positions (host mode, remapped at upload)
     int64_t perm_g0;                // gene of row 0 of the permutation tables (0 for uploaded tables, a block's first gene in replay mode)
     const uint32_t *coprime0, *coprime1;  // [kCoprimeCount] multipliers coprime to n0 / n1 (device mode)
+    const uint32_t *coprime_inv0, *coprime_inv1;  // their inverses mod n0 / n1 (scatter kernel: cell -> permuted index)
+    const uint16_t *slice_of;   // [genes from perm_g0][slice_ld]: slice of every cell in storage order, 0xFFFF = in no slice
+    int64_t slice_ld;           // n0 + n1 (table modes; the scatter kernel's view of the permutation)
     uint64_t seed;
     const double *tab_full, *tab_last;
     double *o;

@@ -9,6 +9,8 @@
 
 namespace phet {
 
+template <typename T> int run_step3_scatter(phet_ctx *c, const Step3Args &args);   // step3s_impl.cuh
+
 template <typename T, int E, bool STAGED>
 __global__ void __launch_bounds__(kThreads3, 1) k_step3h(const Step3Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -177,7 +179,11 @@ int run_step3_prune(phet_ctx *c, const Step3Args &args);  // step3p_impl.cuh, in
 template <typename T>
 static int run_step3_any(phet_ctx *c, const Step3Args &args) {
     {
-        const int rc = run_step3_prune<T>(c, args);
+        const int rc = run_step3_prune<T>(c, args);     // step3p_impl.cuh: class vector staged, private counters
+        if (rc != 1) return rc;
+    }
+    {
+        const int rc = run_step3_scatter<T>(c, args);   // step3s_impl.cuh: streams the vectors, any class size (returns 1 when k_step3p applies)
         if (rc != 1) return rc;
     }
     if (args.cap > 256) return run_step3_T<T>(c, args);

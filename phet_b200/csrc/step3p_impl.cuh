@@ -483,9 +483,28 @@ static int launch_step3p_E(phet_ctx *c, const Step3Args &args) {
     return 0;
 }
 
+// The gather formulation serves this launch (its histograms and the class vector fit in shared memory).
+template <typename T>
+inline bool step3_prune_applies(const phet_ctx *c, const Step3Args &args) {
+    if (c->keep_H || c->step3_impl == 1 || c->step3_impl == 3 || c->tab_h0 < 0 || args.n_last > args.m) return false;
+    const int need = (int)((args.m + 15) / 16);
+    if (need <= 1) return s3p_geometry<T, 1>(args).ok;
+    if (need <= 2) return s3p_geometry<T, 2>(args).ok;
+    if (need <= 3) return s3p_geometry<T, 3>(args).ok;
+    if (need <= 4) return s3p_geometry<T, 4>(args).ok;
+    if (need <= 5) return s3p_geometry<T, 5>(args).ok;
+    if (need <= 6) return s3p_geometry<T, 6>(args).ok;
+    if (need <= 7) return s3p_geometry<T, 7>(args).ok;
+    if (need <= 8) return s3p_geometry<T, 8>(args).ok;
+    if (need <= 9) return s3p_geometry<T, 9>(args).ok;
+    if (need <= 10) return s3p_geometry<T, 10>(args).ok;
+    if (need <= 12) return s3p_geometry<T, 12>(args).ok;
+    return s3p_geometry<T, 16>(args).ok;
+}
+
 template <typename T>
 int run_step3_prune(phet_ctx *c, const Step3Args &args) {
-    if (c->keep_H || c->step3_impl == 1 || c->tab_h0 < 0 || args.n_last > args.m) return 1;
+    if (!step3_prune_applies<T>(c, args)) return 1;
     const int need = (int)((args.m + 15) / 16);
     if (need <= 1) return launch_step3p_E<T, 1>(c, args);
     if (need <= 2) return launch_step3p_E<T, 2>(c, args);

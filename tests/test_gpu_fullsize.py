@@ -93,8 +93,10 @@ def test_full_size_properties(name, monkeypatch):
     # ---- two algorithms, one answer
     _, acc_w, o_w, _, _, path_w = _run(monkeypatch, X, N, G, S, ctrl, case, idx, keep_h=True,
                                        env={"PHET_STEP1_IMPL": "warp", "PHET_STEP3_IMPL": "sort"})
-    assert path_w != "bound-and-prune"
+    assert "bound-and-prune" not in path_w
     assert np.array_equal(o_w, o)                                    # KS minimum: identical on all genes
+    _, _, o_p, _, _, path_p = _run(monkeypatch, X, N, G, S, ctrl, case, idx, env={"PHET_STEP3_IMPL": "scatter"})
+    assert path_p == "scatter bound-and-prune" and np.array_equal(o_p, o)    # streaming formulation of bound-and-prune: the same
     assert np.allclose(acc_w[1], acc[1], rtol=1e-9, atol=1e-9)       # sum of delta-IQR: same order statistics
     assert np.allclose(acc_w[0], acc[0], rtol=1e-4, atol=1e-6)       # Fisher sums: fp32 chunk moments vs fp64
     # ---- a few genes against the oracle, every subsample

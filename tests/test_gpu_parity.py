@@ -234,14 +234,18 @@ def test_step1_pair_path_equals_sort_path(name, dt, monkeypatch):
 
 
 @pytest.mark.parametrize("name", NAMES)
-def test_step3_prune_path_matches_reference(name):
-    """Without capture Step 3 runs the bound-and-prune kernel (histogram bounds on h, exact evaluation of
-    the slices that can attain the minimum p only): o must still be bit-exact, bins and counts identical."""
+@pytest.mark.parametrize("impl", ["scatter", "prune"])
+def test_step3_prune_path_matches_reference(name, impl, monkeypatch):
+    """Without capture Step 3 runs a bound-and-prune kernel (histogram bounds on h, exact evaluation of
+    the slices that can attain the minimum p only) -- the staged gather formulation (k_step3p, the default when the
+    class vectors fit in shared memory) or the streaming scatter formulation (k_step3s): o must still be bit-exact, bins and counts identical."""
     g = load_golden(name)
+    monkeypatch.setenv("PHET_STEP3_IMPL", impl)
     for tag in g["dtypes"]:
         est, scores = _run(g, tag, capture=False)
-        # (a class vector that leaves no room for the histograms falls back to the sorting kernels)
-        assert est.step3_path_ == "bound-and-prune" or g["X"].shape[0] > 20000, est.step3_path_
+        # (gather formulation: a class vector that leaves no room for the histograms falls back to the sorting kernels)
+        want = {"scatter": "scatter bound-and-prune", "prune": "bound-and-prune"}[impl]
+        assert est.step3_path_ == want or (impl == "prune" and g["X"].shape[0] > 20000), est.step3_path_
         assert np.array_equal(est.o_, g[f"o_{tag}"]), "o must be bit-exact"
         assert np.array_equal(est.bin_counts_, g[f"bin_counts_{tag}"])
         assert np.allclose(scores, g[f"scores_{tag}"], rtol=RTOL[tag], atol=1e-12)
@@ -249,20 +253,23 @@ def test_step3_prune_path_matches_reference(name):
 
 @pytest.mark.parametrize("name", sorted(_adversarial_cases()))
 @pytest.mark.parametrize("perm", ["device", "reference"])
-def test_step3_prune_path_equals_sort_path(name, perm, monkeypatch):
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_step3_prune_path_equals_sort_path(name, perm, dt, monkeypatch):
     from phet_b200 import PHet
     X, n0, kw = _adversarial_cases()[name]
-    X = np.ascontiguousarray(X.astype(np.float64))
+    X = np.ascontiguousarray(X.astype(dt))
     y = np.r_[np.zeros(n0, dtype=np.int64), np.ones(X.shape[0] - n0, dtype=np.int64)]
     out = {}
-    for impl in ("auto", "sort"):
+    for impl in ("auto", "scatter", "prune", "sort"):
         monkeypatch.setenv("PHET_STEP3_IMPL", impl)
         np.random.seed(5)
         est = PHet(**kw, capture=False, distributed=False, permutation=perm)
         est.fit_predict(X, y)
         out[impl] = (est.o_.copy(), est.step3_path_)
-    assert out["auto"][1] == "bound-and-prune" and out["sort"][1] != "bound-and-prune"
-    assert np.array_equal(out["auto"][0], out["sort"][0])
+    assert out["auto"][1] == "bound-and-prune" and out["scatter"][1] == "scatter bound-and-prune"
+    assert out["prune"][1] == "bound-and-prune" and "bound-and-prune" not in out["sort"][1]
+    for impl in ("auto", "scatter", "prune"):
+        assert np.array_equal(out[impl][0], out["sort"][0]), impl
 
 
 def _global_gather_cases():

@@ -92,10 +92,14 @@ def test_big_geometry_matches_reference(name, force_big, monkeypatch):
     params["percentiles"] = tuple(params["percentiles"])
     for tag in big_cases.BIG[name]["dtypes"]:
         X = X32 if tag == "f32" else np.ascontiguousarray(X32.astype(np.float64))
-        for capture in (True, False):          # capture: sorting kernels (every slice's h); else bound-and-prune
+        # capture: sorting kernels (every slice's h); else bound-and-prune, streaming (scatter) and gather formulation
+        for capture, impl in ((True, "auto"), (False, "scatter"), (False, "prune")):
+            monkeypatch.setenv("PHET_STEP3_IMPL", impl)
             np.random.seed(int(d["seed"]))
             est = PHet(**params, capture=capture, distributed=False)
             scores = est.fit_predict(X, y)
+            if impl == "scatter":
+                assert est.step3_path_ == "scatter bound-and-prune", est.step3_path_
             assert np.array_equal(est.index_sets_[:, 0], d["idx_i"]) and np.array_equal(est.index_sets_[:, 1], d["idx_j"])
             if capture:
                 assert np.array_equal(est.H_, d[f"H_{tag}"]), "KS integer statistics differ"
