@@ -116,6 +116,10 @@ __device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint
         sx[0] += (double)(fs[0] + fs[1]);
         qx[0] += (double)(fq[0] + fq[1]);
     }
+#ifdef PHET_S1P_SERIAL_RMW
+#pragma unroll
+    for (int u = 0; u < 16; ++u) sts_u8(ad[u], lds_u8(ad[u]) + 1u);   // one update at a time (the LSU keeps a thread's accesses in order)
+#else
 #pragma unroll
     for (int u = 0; u < 16; u += 2) {
         // two histogram updates in flight: both counters are read before either is written, and the second
@@ -124,6 +128,7 @@ __device__ __forceinline__ void pair_chunk(const T (&v)[16], int j0, int m, uint
         sts_u8(ad[u], c0 + 1u);
         sts_u8(ad[u + 1], c1 + 1u + (ad[u] == ad[u + 1] ? 1u : 0u));
     }
+#endif
     uint32_t pk[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)  // IMAD chain: ids are < 128, bytes do not overlap
@@ -150,6 +155,31 @@ __device__ __forceinline__ void sort_pow2_asc(T (&x)[N]) {
             }
         }
     }
+}
+
+// Ascending sort of 8 registers with the 19-comparator network (bitonic needs 24).
+template <typename T>
+__device__ __forceinline__ void sort8_asc(T (&x)[8]) {
+#define PHET_CE(i, j) { const T lo_ = tmin(x[i], x[j]), hi_ = tmax(x[i], x[j]); x[i] = lo_; x[j] = hi_; }
+    PHET_CE(0, 2) PHET_CE(1, 3) PHET_CE(4, 6) PHET_CE(5, 7)
+    PHET_CE(0, 4) PHET_CE(1, 5) PHET_CE(2, 6) PHET_CE(3, 7)
+    PHET_CE(0, 1) PHET_CE(2, 3) PHET_CE(4, 5) PHET_CE(6, 7)
+    PHET_CE(2, 4) PHET_CE(3, 5)
+    PHET_CE(1, 4) PHET_CE(3, 6)
+    PHET_CE(1, 2) PHET_CE(3, 4) PHET_CE(5, 6)
+#undef PHET_CE
+}
+
+// Candidate element numbers (one byte each, newest in byte 0) shifted through W 32-bit registers.
+template <int W>
+__device__ __forceinline__ void push_byte(uint32_t (&p)[W], uint32_t j) {
+#pragma unroll
+    for (int i = W - 1; i >= 1; --i) p[i] = __funnelshift_l(p[i - 1], p[i], 8);
+    p[0] = p[0] * 256u + j;
+}
+template <int W>
+__device__ __forceinline__ uint32_t pack_byte(const uint32_t (&p)[W], int k) {  // k: compile-time constant after unrolling
+    return (p[k >> 2] >> (8 * (k & 3))) & 255u;
 }
 
 // x[r] for a runtime r < N without dynamic register indexing
@@ -351,28 +381,63 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     // ---- locate the four sorted positions in the histogram
                     // sum of the four counters of a word: m <= 255 keeps it below 256 (one IMAD); BIG needs the exact sum
                     auto sum4 = [](uint32_t w) -> uint32_t { return BIG ? __dp4a(w, 0x01010101u, 0u) : (w * 0x01010101u) >> 24; };
-                    uint32_t wi = 0, x = lds_u32(hbase), s4 = sum4(x);
-                    int cum = 0;
                     int B[4], E[4], C[4];
                     const int P[4] = {P0, P1, P2, P3};
+                    uint32_t wi = 0, x = 0u, s4 = 0u;
+                    int cum = 0;
+                    if (!BIG) {
+                        // staged instantiation: all words are loaded up front and the four searches are straight-line code
+                        // (the word-by-word walk below is a chain of dependent shared-memory loads)
+                        uint32_t s4v[NBW];
+                        int ps[NBW];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        while (cum + (int)s4 <= P[t] && wi < (uint32_t)(NBW - 1)) {
-                            cum += (int)s4;
-                            ++wi;
-                            x = lds_u32(hbase + 128u * wi);
-                            s4 = sum4(x);
+                        for (int i = 0; i < NBW; ++i) s4v[i] = sum4(lds_u32(hbase + 128u * (uint32_t)i));
+                        int run0 = 0;
+#pragma unroll
+                        for (int i = 0; i < NBW; ++i) {
+                            run0 += (int)s4v[i];
+                            ps[i] = run0;
                         }
-                        int run = cum;
-                        uint32_t q = 0, c = x & 255u;
-                        while (run + (int)c <= P[t] && q < 3u) {
-                            run += (int)c;
-                            ++q;
-                            c = (x >> (8u * q)) & 255u;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            uint32_t wt = 0;
+                            int ct = 0;
+#pragma unroll
+                            for (int i = 0; i < NBW - 1; ++i) {
+                                const bool below = ps[i] <= P[t];
+                                wt += below ? 1u : 0u;
+                                ct += below ? (int)s4v[i] : 0;
+                            }
+                            const uint32_t xw = lds_u32(hbase + 128u * wt);
+                            const int c0 = (int)(xw & 255u), c1 = (int)((xw >> 8) & 255u), c2 = (int)((xw >> 16) & 255u), c3 = (int)(xw >> 24);
+                            const int r0 = ct + c0, r1 = r0 + c1, r2 = r1 + c2;
+                            const int q = (r0 <= P[t] ? 1 : 0) + (r1 <= P[t] ? 1 : 0) + (r2 <= P[t] ? 1 : 0);
+                            B[t] = (int)(wt * 4u) + q;
+                            E[t] = q == 0 ? ct : (q == 1 ? r0 : (q == 2 ? r1 : r2));
+                            C[t] = q == 0 ? c0 : (q == 1 ? c1 : (q == 2 ? c2 : c3));
                         }
-                        B[t] = (int)(wi * 4u + q);
-                        E[t] = run;
-                        C[t] = (int)c;
+                    } else {
+                        x = lds_u32(hbase);
+                        s4 = sum4(x);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            while (cum + (int)s4 <= P[t] && wi < (uint32_t)(NBW - 1)) {
+                                cum += (int)s4;
+                                ++wi;
+                                x = lds_u32(hbase + 128u * wi);
+                                s4 = sum4(x);
+                            }
+                            int run = cum;
+                            uint32_t q = 0, c = x & 255u;
+                            while (run + (int)c <= P[t] && q < 3u) {
+                                run += (int)c;
+                                ++q;
+                                c = (x >> (8u * q)) & 255u;
+                            }
+                            B[t] = (int)(wi * 4u + q);
+                            E[t] = run;
+                            C[t] = (int)c;
+                        }
                     }
                     // BIG (m > 255 possible): a one-byte counter wraps when 256 or more elements share a bucket (a big tie
                     // group); the counters then no longer add up to the number of list entries and the sample goes
@@ -391,127 +456,236 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     if (!smallH) rescue = !pair_big_range<T, IT, BIG>(ip, m, src, blbase, (uint32_t)B[2], (uint32_t)B[3], tieH) || rescue;
                     rescue = rescue || wrapped;
                     mark(9);
-                    // ---- one pass over the bucket list: words holding an element of either bucket range become
-                    //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
-                    //      bits 0-5), compacted in place over the part of the list already consumed
-                    int nrec = 0;
-                    {
-                        // a range that is too big is matched by nothing here (lo > hi) and handled below
-                        const uint32_t lo4L = (smallL ? (uint32_t)B[0] : 1u) * 0x01010101u;
-                        const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
-                        const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
-                        const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
-                        for (int c = 0; c < nchunk; ++c) {
-                            const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t w = (k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
-                                const uint32_t wh = w | 0x80808080u;
-                                const uint32_t fl = (wh - lo4L) & (hi4L - w) & 0x80808080u;
-                                const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
-                                const uint32_t f = fl | (fh >> 1);
-                                if (f) {
-                                    const uint32_t wno = (uint32_t)(4 * c + k);  // < 64 (BIG: < 128, bit 6 goes to byte 1)
-                                    sts_u32(blbase + 4u * (uint32_t)nrec, f | (BIG ? ((wno & 63u) | ((wno >> 6) << 8)) : wno));
-                                    ++nrec;
-                                }
-                            }
-                        }
-                    }
-                    mark(10);
-                    // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
-                    int nL = 0, nH = 0;
-                    for (int i = 0; i < nrec; ++i) {
-                        const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
-                        const int wj = (int)(BIG ? ((rec & 63u) | ((rec >> 2) & 0xFC0u)) : (rec & 63u)) * 4;
-                        uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
-                        while (f) {
-                            const int bit = __ffs((int)f) - 1;
-                            f &= f - 1u;
-                            const bool hi = (bit & 1) == 0;
-                            const int cnt = hi ? nH : nL;
-                            if (cnt < CM) {
-                                const uint32_t jn = (uint32_t)(wj + (bit >> 3));
-                                sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), jn);  // NBW >= 8
-                                if (BIG) sts_u8(hist_addr(hbase, (uint32_t)(32 + cnt + (hi ? 16 : 0))), jn >> 8);  // NBW >= 16
-                            }
-                            nH += hi ? 1 : 0;
-                            nL += hi ? 0 : 1;
-                        }
-                    }
-                    rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
-                    mark(11);
-                    // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
-                    //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
-                    {
-                        const int nLc = nL < CM ? nL : CM, nHc = nH < CM ? nH : CM;
-                        const int nmax = nLc > nHc ? nLc : nHc;
-                        for (int i0 = 0; i0 < nmax; i0 += 4) {
-                            uint32_t pl[4], ph[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
-                                uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
-                                uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
-                                if (BIG) {
-                                    jl |= okl ? lds_u8(hist_addr(hbase, 32u + (uint32_t)(i0 + u))) << 8 : 0u;
-                                    jh |= okh ? lds_u8(hist_addr(hbase, 48u + (uint32_t)(i0 + u))) << 8 : 0u;
-                                }
-                                pl[u] = (uint32_t)__ldg(ip + jl * 32u);
-                                ph[u] = (uint32_t)__ldg(ip + jh * 32u);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const T vl = src.at(pl[u]), vh = src.at(ph[u]);
-                                if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
-                                if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
-                            }
-                        }
-                    }
-                    mark(12);
-                    // ---- sort the candidates of each range and read off the two ranks
                     T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        const int nc = h ? nH : nL;
-                        const bool small = h ? smallH : smallL;
-                        const int ra = h ? P2 - E[2] : P0 - E[0], rb = h ? P3 - E[2] : P1 - E[0];
-                        const uint32_t cb = blbase + (h ? 64u : 0u);
-                        T ya, yb;
-                        if (!small) {
-                            ya = h ? tieH : tieL;
-                            yb = ya;
-                        } else if (nc <= 8 || CM <= 8) {
-                            T c[8];
-                            if (sizeof(T) == 4) {
-                                const uint4 q0 = lds_v4(cb), q1 = lds_v4(cb + 16u);
-                                c[0] = (T)__uint_as_float(q0.x); c[1] = (T)__uint_as_float(q0.y);
-                                c[2] = (T)__uint_as_float(q0.z); c[3] = (T)__uint_as_float(q0.w);
-                                c[4] = (T)__uint_as_float(q1.x); c[5] = (T)__uint_as_float(q1.y);
-                                c[6] = (T)__uint_as_float(q1.z); c[7] = (T)__uint_as_float(q1.w);
-                            } else {
+                    if (!BIG) {
+                        // ---- staged instantiation (m <= 255): one pass over the bucket list shifts the element numbers of the
+                        //      candidates of either bucket range into byte packs held in REGISTERS (newest in byte 0); no
+                        //      records, no element lists in shared memory.  Up to CM candidates per range (16 floats / 8 doubles).
+                        constexpr int PW = CM / 4;
+                        uint32_t pkL[PW], pkH[PW];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) c[i] = lds_val(cb + 8u * (uint32_t)i, T(0));
+                        for (int i = 0; i < PW; ++i) pkL[i] = pkH[i] = 0u;
+                        int nL = 0, nH = 0;
+                        {
+                            // a range that is too big is matched by nothing here (lo > hi) and was handled above
+                            const uint32_t lo4L = (smallL ? (uint32_t)B[0] : 1u) * 0x01010101u;
+                            const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
+                            const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
+                            const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
+                            // words holding a candidate become records (low-range flags in bit 7 of each byte, high-range flags
+                            // in bit 6, word number in bits 0-5), compacted in place over the part of the list already consumed
+                            int nrec = 0;
+                            for (int c = 0; c < nchunk; ++c) {
+                                const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t w = (k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
+                                    const uint32_t wh = w | 0x80808080u;
+                                    const uint32_t fl = (wh - lo4L) & (hi4L - w) & 0x80808080u;
+                                    const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
+                                    const uint32_t f = fl | (fh >> 1);
+                                    if (f) {
+                                        sts_u32(blbase + 4u * (uint32_t)nrec, f | (uint32_t)(4 * c + k));
+                                        ++nrec;
+                                    }
+                                }
+                            }
+                            mark(10);
+                            // records -> element numbers, shifted into the packs of their range
+                            for (int i = 0; i < nrec; ++i) {
+                                const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
+                                const uint32_t jb = (rec & 63u) * 4u;
+                                uint32_t f = rec & 0xC0C0C0C0u;
+                                do {
+                                    const int bit = __ffs((int)f) - 1;
+                                    f &= f - 1u;
+                                    const uint32_t j = jb + (uint32_t)(bit >> 3);
+                                    if (bit & 1) {   // bit 7 of a byte: low range
+                                        push_byte<PW>(pkL, j);
+                                        ++nL;
+                                    } else {
+                                        push_byte<PW>(pkH, j);
+                                        ++nH;
+                                    }
+                                } while (f);
+                            }
+                        }
+                        rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
+                        mark(11);
+                        // ---- the first 8 candidates of each range: index loads, then gathers, all in flight together
+                        T cL[8], cH[8];
+                        {
+                            uint32_t posL[8], posH[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                posL[k] = (k < nL) ? (uint32_t)__ldg(ip + pack_byte<PW>(pkL, k) * 32u) : 0u;
+                                posH[k] = (k < nH) ? (uint32_t)__ldg(ip + pack_byte<PW>(pkH, k) * 32u) : 0u;
                             }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? c[i] : Big<T>::v();
-                            sort_pow2_asc<T, 8>(c);
-                            ya = pick_reg<T, 8>(c, ra);
-                            yb = pick_reg<T, 8>(c, rb);
-                        } else {
-                            T c[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) c[i] = (i < nc) ? lds_val(cb + (uint32_t)(i * (int)sizeof(T)), T(0)) : Big<T>::v();
-                            sort_pow2_asc<T, 16>(c);
-                            ya = pick_reg<T, 16>(c, ra);
-                            yb = pick_reg<T, 16>(c, rb);
+                            for (int k = 0; k < 8; ++k) {
+                                const T vl = src.at(posL[k]), vh = src.at(posH[k]);
+                                cL[k] = (k < nL) ? vl : Big<T>::v();
+                                cH[k] = (k < nH) ? vh : Big<T>::v();
+                            }
                         }
-                        if (h) {
-                            y2 = ya;
-                            y3 = yb;
-                        } else {
-                            y0 = ya;
-                            y1 = yb;
+                        sort8_asc<T>(cL);
+                        sort8_asc<T>(cH);
+                        const int raL = P0 - E[0], rbL = P1 - E[0], raH = P2 - E[2], rbH = P3 - E[2];
+                        y0 = smallL ? pick_reg<T, 8>(cL, raL) : tieL;
+                        y1 = smallL ? pick_reg<T, 8>(cL, rbL) : tieL;
+                        y2 = smallH ? pick_reg<T, 8>(cH, raH) : tieH;
+                        y3 = smallH ? pick_reg<T, 8>(cH, rbH) : tieH;
+                        mark(12);
+                        if (CM > 8 && (nL > 8 || nH > 8)) {   // 9..16 candidates in a range (a few per cent of the samples): all 16 slots
+#pragma unroll 1
+                            for (int h = 0; h < 2; ++h) {
+                                const int nc = h ? nH : nL;
+                                if (nc <= 8 || nc > CM) continue;
+                                uint32_t pk[PW];
+#pragma unroll
+                                for (int i = 0; i < PW; ++i) pk[i] = h ? pkH[i] : pkL[i];
+                                T c16[16];
+                                uint32_t pos16[16];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) pos16[k] = (k < nc) ? (uint32_t)__ldg(ip + pack_byte<PW>(pk, k < CM ? k : 0) * 32u) : 0u;
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    const T v = src.at(pos16[k]);
+                                    c16[k] = (k < nc) ? v : Big<T>::v();
+                                }
+                                sort_pow2_asc<T, 16>(c16);
+                                const T ya = pick_reg<T, 16>(c16, h ? raH : raL), yb = pick_reg<T, 16>(c16, h ? rbH : rbL);
+                                if (h) {
+                                    y2 = ya;
+                                    y3 = yb;
+                                } else {
+                                    y0 = ya;
+                                    y1 = yb;
+                                }
+                            }
+                        }
+                    } else {
+                        // ---- one pass over the bucket list: words holding an element of either bucket range become
+                        //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
+                        //      bits 0-5), compacted in place over the part of the list already consumed
+                        int nrec = 0;
+                        {
+                            // a range that is too big is matched by nothing here (lo > hi) and handled below
+                            const uint32_t lo4L = (smallL ? (uint32_t)B[0] : 1u) * 0x01010101u;
+                            const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
+                            const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
+                            const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
+                            for (int c = 0; c < nchunk; ++c) {
+                                const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
+    #pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t w = (k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
+                                    const uint32_t wh = w | 0x80808080u;
+                                    const uint32_t fl = (wh - lo4L) & (hi4L - w) & 0x80808080u;
+                                    const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
+                                    const uint32_t f = fl | (fh >> 1);
+                                    if (f) {
+                                        const uint32_t wno = (uint32_t)(4 * c + k);  // < 64 (BIG: < 128, bit 6 goes to byte 1)
+                                        sts_u32(blbase + 4u * (uint32_t)nrec, f | (BIG ? ((wno & 63u) | ((wno >> 6) << 8)) : wno));
+                                        ++nrec;
+                                    }
+                                }
+                            }
+                        }
+                        mark(10);
+                        // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
+                        int nL = 0, nH = 0;
+                        for (int i = 0; i < nrec; ++i) {
+                            const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
+                            const int wj = (int)(BIG ? ((rec & 63u) | ((rec >> 2) & 0xFC0u)) : (rec & 63u)) * 4;
+                            uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
+                            while (f) {
+                                const int bit = __ffs((int)f) - 1;
+                                f &= f - 1u;
+                                const bool hi = (bit & 1) == 0;
+                                const int cnt = hi ? nH : nL;
+                                if (cnt < CM) {
+                                    const uint32_t jn = (uint32_t)(wj + (bit >> 3));
+                                    sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), jn);  // NBW >= 8
+                                    if (BIG) sts_u8(hist_addr(hbase, (uint32_t)(32 + cnt + (hi ? 16 : 0))), jn >> 8);  // NBW >= 16
+                                }
+                                nH += hi ? 1 : 0;
+                                nL += hi ? 0 : 1;
+                            }
+                        }
+                        rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
+                        mark(11);
+                        // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
+                        //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
+                        {
+                            const int nLc = nL < CM ? nL : CM, nHc = nH < CM ? nH : CM;
+                            const int nmax = nLc > nHc ? nLc : nHc;
+                            for (int i0 = 0; i0 < nmax; i0 += 4) {
+                                uint32_t pl[4], ph[4];
+    #pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
+                                    uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
+                                    uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
+                                    if (BIG) {
+                                        jl |= okl ? lds_u8(hist_addr(hbase, 32u + (uint32_t)(i0 + u))) << 8 : 0u;
+                                        jh |= okh ? lds_u8(hist_addr(hbase, 48u + (uint32_t)(i0 + u))) << 8 : 0u;
+                                    }
+                                    pl[u] = (uint32_t)__ldg(ip + jl * 32u);
+                                    ph[u] = (uint32_t)__ldg(ip + jh * 32u);
+                                }
+    #pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const T vl = src.at(pl[u]), vh = src.at(ph[u]);
+                                    if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
+                                    if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
+                                }
+                            }
+                        }
+                        mark(12);
+                        // ---- sort the candidates of each range and read off the two ranks
+    #pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+                            const int nc = h ? nH : nL;
+                            const bool small = h ? smallH : smallL;
+                            const int ra = h ? P2 - E[2] : P0 - E[0], rb = h ? P3 - E[2] : P1 - E[0];
+                            const uint32_t cb = blbase + (h ? 64u : 0u);
+                            T ya, yb;
+                            if (!small) {
+                                ya = h ? tieH : tieL;
+                                yb = ya;
+                            } else if (nc <= 8 || CM <= 8) {
+                                T c[8];
+                                if (sizeof(T) == 4) {
+                                    const uint4 q0 = lds_v4(cb), q1 = lds_v4(cb + 16u);
+                                    c[0] = (T)__uint_as_float(q0.x); c[1] = (T)__uint_as_float(q0.y);
+                                    c[2] = (T)__uint_as_float(q0.z); c[3] = (T)__uint_as_float(q0.w);
+                                    c[4] = (T)__uint_as_float(q1.x); c[5] = (T)__uint_as_float(q1.y);
+                                    c[6] = (T)__uint_as_float(q1.z); c[7] = (T)__uint_as_float(q1.w);
+                                } else {
+    #pragma unroll
+                                    for (int i = 0; i < 8; ++i) c[i] = lds_val(cb + 8u * (uint32_t)i, T(0));
+                                }
+    #pragma unroll
+                                for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? c[i] : Big<T>::v();
+                                sort_pow2_asc<T, 8>(c);
+                                ya = pick_reg<T, 8>(c, ra);
+                                yb = pick_reg<T, 8>(c, rb);
+                            } else {
+                                T c[16];
+    #pragma unroll
+                                for (int i = 0; i < 16; ++i) c[i] = (i < nc) ? lds_val(cb + (uint32_t)(i * (int)sizeof(T)), T(0)) : Big<T>::v();
+                                sort_pow2_asc<T, 16>(c);
+                                ya = pick_reg<T, 16>(c, ra);
+                                yb = pick_reg<T, 16>(c, rb);
+                            }
+                            if (h) {
+                                y2 = ya;
+                                y3 = yb;
+                            } else {
+                                y0 = ya;
+                                y1 = yb;
+                            }
                         }
                     }
                     const double q_lo = __dadd_rn(__dmul_rn(w_lo0, (double)y0), __dmul_rn(a.q.g_lo, (double)y1));

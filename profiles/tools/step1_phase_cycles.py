@@ -12,15 +12,15 @@ stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
 ctx = _capi.Context(0, stream.cuda_stream)
 X = bench.synth_matrix_device(N, G, dev)
 m = hostmath.subsample_size(N // 2, N - N // 2, "sqrt")
-ctrl, case, idx = bench.draw_index_sets(N, S, m)
-fit = bench.Fit(ctx, wl, ctrl, case, idx, 0, 1, None)
-fit.setup_resident(); ctx.set_index_sets(idx)
+ctrl, case, idx, _ = bench.draw_index_sets(N, S, m)
+fit = bench.Fit(ctx, wl, ctrl, case, idx, 0, 1, None, perms="device")
+fit.setup_resident(X.data_ptr(), None)
 for _ in range(2): fit.step_resident(X.data_ptr())
 ctx.write(_capi.BUF_PROFILE, np.zeros(16, dtype=np.uint64))
 fit.step_resident(X.data_ptr())
 p = ctx.read(_capi.BUF_PROFILE, np.uint64, (16,)).astype(np.float64)
-names = ["pass A (gather, moments, histogram)", "locate 4 positions", "bucket-list scan -> records", "records -> element numbers",
-         "candidate re-gather", "sort + pick, clear histogram", "rescue + ballot", "scratch / combine / p-value"]
+names = ["pass A (gather, moments, histogram)", "locate 4 positions", "bucket-list scan -> records", "records -> element numbers (packs)",
+         "candidate gather + sort + pick", "9..16-candidate path, clear histogram", "rescue + ballot", "scratch / combine / p-value"]
 passes = p[15]
 tot = p[8:15].sum()
 for n, v in zip(names, p[8:15]): print("%-40s %9.0f cycles/class-pass  %5.1f %%" % (n, v / passes, 100 * v / tot))
