@@ -202,6 +202,14 @@ int phet_combine(phet_ctx *ctx, const double *weights, int32_t B, double *scores
 int phet_finalize(phet_ctx *ctx, int64_t S_total, const double *weights, int32_t B, double *scores_out,
                   int64_t *counts_out, double *edges_out);
 
+/* The same work queued on the context's stream WITHOUT a host synchronisation: scores stay in PHET_BUF_SCORES,
+ * counts and edges on the device (the weights are cached on the device and re-uploaded only when they change).
+ * A caller that runs fit after fit -- or follows the fit with a collective on the same stream -- keeps the GPU
+ * busy back to back; phet_fetch_results copies the last results out and synchronises.  Replaces the same spans
+ * as phet_finalize (phet.py:435-462, 500-516).  Each *_out may be NULL. */
+int phet_finalize_async(phet_ctx *ctx, int64_t S_total, const double *weights, int32_t B);
+int phet_fetch_results(phet_ctx *ctx, double *scores_out, int64_t *counts_out, double *edges_out);
+
 /* Context options.  PHET_OPT_KEEP_H (default 0): 1 = phet_step3 / phet_run_pipeline also fill PHET_BUF_H
  * with the integer KS statistic of EVERY slice (parity / debugging; the sorting kernels run); 0 = only
  * o[g] = min p is produced, which lets Step 3 bound h per slice from bucket histograms and evaluate

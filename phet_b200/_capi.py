@@ -25,7 +25,7 @@ OPT_STEP3_MIN_SIZE = 2
 EXPORTS = [
     "phet_abi_version", "phet_last_error", "phet_device_count", "phet_ctx_create", "phet_ctx_destroy",
     "phet_ctx_sync", "phet_set_classes", "phet_load_matrix", "phet_set_index_sets", "phet_step1",
-    "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_device_ptr",
+    "phet_step3", "phet_run_pipeline", "phet_fisher", "phet_o_minmax", "phet_bin", "phet_combine", "phet_finalize", "phet_finalize_async", "phet_fetch_results", "phet_device_ptr",
     "phet_read_buffer", "phet_write_buffer", "phet_set_option", "phet_step3_path", "phet_launch_count", "phet_step1_geometry", "phet_fit_host", "phet_class_stats",
     "phet_mtx_parse", "phet_mtx_triplets", "phet_mtx_free", "phet_mtx_stage", "phet_mtx_kept", "phet_rank", "phet_anova", "phet_kruskal", "phet_stage_matrix", "phet_load_matrix_genes",
     "phet_host_p_two_sided_t", "phet_host_p_two_sided_z", "phet_host_perm_apply",
@@ -108,6 +108,8 @@ def load_library(build_if_missing: bool = True):
     lib.phet_bin.argtypes = [vp, vp, i32, vp]
     lib.phet_combine.argtypes = [vp, vp, i32, vp]
     lib.phet_finalize.argtypes = [vp, i64, vp, i32, vp, vp, vp]
+    lib.phet_finalize_async.argtypes = [vp, i64, vp, i32]
+    lib.phet_fetch_results.argtypes = [vp, vp, vp, vp]
     lib.phet_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     lib.phet_read_buffer.argtypes = [vp, C.c_int, vp, i64]
     lib.phet_write_buffer.argtypes = [vp, C.c_int, vp, i64]
@@ -549,6 +551,22 @@ class Context:
         _check(self.lib.phet_finalize(self.h, int(S_total), _ptr(w), B, _ptr(scores) if fetch else None, _ptr(counts),
                                       _ptr(edges)))
         return scores, counts, edges
+
+    def finalize_async(self, S_total, weights: np.ndarray):
+        """The work of finalize() queued on the stream without a host synchronisation; results stay on the device
+        until fetch_results()."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        self._n_bins = w.size
+        _check(self.lib.phet_finalize_async(self.h, int(S_total), _ptr(w), w.size))
+
+    def fetch_results(self, scores=True):
+        """(scores or None, bin counts, edges) of the last finalized fit; synchronises."""
+        B = self._n_bins
+        sc = np.empty(self.G, dtype=np.float64) if scores else None
+        counts = np.zeros(B, dtype=np.int64)
+        edges = np.empty(B + 1, dtype=np.float64)
+        _check(self.lib.phet_fetch_results(self.h, _ptr(sc) if scores else None, _ptr(counts), _ptr(edges)))
+        return sc, counts, edges
 
     def device_ptr(self, which):
         p = C.c_void_p()

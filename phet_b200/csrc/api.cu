@@ -970,8 +970,7 @@ int phet_combine(phet_ctx *c, const double *weights, int32_t B, double *scores_o
     return PHET_OK;
 }
 
-int phet_finalize(phet_ctx *c, int64_t S_total, const double *weights, int32_t B, double *scores_out,
-                  int64_t *counts_out, double *edges_out) {
+int phet_finalize_async(phet_ctx *c, int64_t S_total, const double *weights, int32_t B) {
     PHET_REQUIRE(c != nullptr && c->matrix_set, "ctx not ready");
     PHET_REQUIRE(S_total >= 1, "S_total must be >= 1");
     PHET_REQUIRE(weights != nullptr && B >= 1 && B <= 127, "need 1 <= B <= 127 feature weights");
@@ -979,9 +978,33 @@ int phet_finalize(phet_ctx *c, int64_t S_total, const double *weights, int32_t B
     if (int e = c->edges.alloc((size_t)B + 1)) return e;
     if (int e = c->counts.alloc((size_t)B)) return e;
     if (int e = c->weights.alloc((size_t)B)) return e;
-    PHET_CUDA(cudaMemcpyAsync(c->weights.p, weights, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    // the weights only change with the estimator's hyper-parameters: keep a host copy, upload on change (synchronously,
+    // so that no caller-owned host buffer is in flight when the call returns)
+    if (c->weights_host.size() != (size_t)B || memcmp(c->weights_host.data(), weights, sizeof(double) * B) != 0) {
+        c->weights_host.assign(weights, weights + B);
+        PHET_CUDA(cudaMemcpyAsync(c->weights.p, c->weights_host.data(), sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+        PHET_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->n_bins = B;
-    return launch_finalize(c, S_total, B, scores_out, counts_out, edges_out);  // synchronises: weights is a host buffer
+    return launch_finalize(c, S_total, B);
+}
+
+int phet_fetch_results(phet_ctx *c, double *scores_out, int64_t *counts_out, double *edges_out) {
+    PHET_REQUIRE(c != nullptr && c->matrix_set && c->n_bins >= 1, "phet_fetch_results: no finalized fit in this context");
+    PHET_CUDA(cudaSetDevice(c->device));
+    const int32_t B = c->n_bins;
+    if (scores_out) PHET_CUDA(cudaMemcpyAsync(scores_out, c->scores.p, sizeof(double) * c->G, cudaMemcpyDeviceToHost, c->stream));
+    if (counts_out)
+        PHET_CUDA(cudaMemcpyAsync(counts_out, c->counts.p, sizeof(unsigned long long) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (edges_out) PHET_CUDA(cudaMemcpyAsync(edges_out, c->edges.p, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, c->stream));
+    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    return PHET_OK;
+}
+
+int phet_finalize(phet_ctx *c, int64_t S_total, const double *weights, int32_t B, double *scores_out,
+                  int64_t *counts_out, double *edges_out) {
+    if (int e = phet_finalize_async(c, S_total, weights, B)) return e;
+    return phet_fetch_results(c, scores_out, counts_out, edges_out);
 }
 
 int phet_class_stats(phet_ctx *c, const phet_quantile_pos *q3, double *out) {

@@ -131,6 +131,7 @@ struct phet_ctx {
     int tab_h0 = -1;                     // table_full is non-increasing from here on (host-checked); -1: unknown
     phet::DevBuf<double> acc;            // [3][G]: sum -2 ln p, sum delta, and o (aliased below): one all-reduce covers all three
     std::vector<double> tab_full_host, tab_last_host;  // last uploaded KS tables (re-uploaded only when they change)
+    std::vector<double> weights_host;                  // last uploaded feature weights (phet_finalize_async)
     phet::DevBuf<double> dbgP, dbgD;     // [G][S_local]
     phet::DevBuf<double> o;              // [G]
     phet::DevBuf<int32_t> H;             // [G][n_slices]
@@ -192,7 +193,7 @@ int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_q
 int launch_o_minmax(phet_ctx *c, double out[2]);
 int launch_bin(phet_ctx *c, int32_t B, int64_t *counts_out);
 int launch_combine(phet_ctx *c, int32_t B, double *scores_out);
-int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out);
+int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B);
 int launch_rank(phet_ctx *c, const double *scores_dev, int64_t G);
 int launch_fy_apply(phet_ctx *c, const void *draws_dev, int elem_bytes, int64_t ld, int64_t n, int64_t count, int64_t take,
                     const int32_t *map_dev, uint32_t *out_dev, int64_t out_ld, cudaStream_t stream);

@@ -169,21 +169,15 @@ int launch_combine(phet_ctx *c, int32_t B, double *scores_out) {
 }
 
 // Fisher standardisation, edges, binning and combine back to back on the stream; one synchronisation at the end.
-int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B, double *scores_out, int64_t *counts_out, double *edges_out) {
+int launch_finalize(phet_ctx *c, int64_t S_total, int32_t B) {   // queued on the stream, no synchronisation
     if (int e = launch_fisher(c, S_total)) return e;
     k_reduce3<<<1, kRedThreads, 0, c->stream>>>(c->o.p, c->G, c->scalars.p);
     k_edges<<<1, 32, 0, c->stream>>>(c->scalars.p, B, c->edges.p);
     c->launches += 2;
     if (int e = launch_bin(c, B, nullptr)) return e;
     if (int e = launch_combine(c, B, nullptr)) return e;
-    if (scores_out) PHET_CUDA(cudaMemcpyAsync(scores_out, c->scores.p, sizeof(double) * c->G, cudaMemcpyDeviceToHost, c->stream));
-    if (counts_out)
-        PHET_CUDA(cudaMemcpyAsync(counts_out, c->counts.p, sizeof(unsigned long long) * B, cudaMemcpyDeviceToHost, c->stream));
-    if (edges_out) PHET_CUDA(cudaMemcpyAsync(edges_out, c->edges.p, sizeof(double) * (B + 1), cudaMemcpyDeviceToHost, c->stream));
-    PHET_CUDA(cudaStreamSynchronize(c->stream));
+    PHET_CUDA(cudaGetLastError());
     return 0;
 }
-
-
 
 }  // namespace phet
