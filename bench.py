@@ -372,6 +372,7 @@ def main():
                          "on the host); the other mode is reported beside it (value_device_perm / e2e_device_perm)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-at-n", action="store_true", help="N > 1: rank 0 still times the CPU baseline (default: N = 1 only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     N, G, S = wl["N"], wl["G"], wl["S"]
@@ -558,7 +559,8 @@ def main():
                         "(see the ncu summary named in traffic_source)",
                 "grid": geom["grid"], "block": geom["block"], "smem_per_cta": geom["smem"]}
     cpu = None
-    if not args.no_cpu:
+    # the CPU baseline is rank 0's job, at N = 1 (or at N > 1 when asked for: --cpu-at-n, e.g. config 5 on 8 GPUs)
+    if not args.no_cpu and rank == 0 and (world == 1 or args.cpu_at_n):
         g_sub = min(G, 1024)
         cols = X[:, :g_sub].contiguous().cpu().numpy()
         y = np.zeros(N, dtype=np.int64)

@@ -12,6 +12,7 @@
 // fp64 throughout for double storage.  The per-gene Fisher sum is reduced in a fixed order (deterministic).
 #include "common.cuh"
 #include "pvalue.cuh"
+#include "warp_prims.cuh"
 
 namespace phet {
 
@@ -21,6 +22,7 @@ struct AnovaArgs {
     const void *xg;
     int64_t n_pad, xg_g0, g_begin, g_end, N;
     const uint32_t *idxT;   // [K * m][S]: grouped position of element e of group k in subsample s
+    const uint32_t *idxU;   // [S][K * m]: the same positions, one subsample's elements adjacent (warp-per-subsample kernels) or NULL
     int64_t S;
     int K, m;
     double dfn, dfd, ln_beta, p_flush;
@@ -30,17 +32,16 @@ struct AnovaArgs {
 
 // original rows [S][K][m] -> grouped positions, transposed to [K*m][S]
 __global__ void k_anova_index(const int32_t *__restrict__ idx, int64_t S, int64_t KM, const int32_t *__restrict__ pos_of_row,
-                              int64_t N, uint32_t *__restrict__ idxT, int *__restrict__ bad) {
+                              int64_t N, uint32_t *__restrict__ idxT, uint32_t *__restrict__ idxU, int *__restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over [K*m][S]
     if (i >= S * KM) return;
     const int64_t e = i / S, s = i - e * S;
     const int32_t r = idx[s * KM + e];
-    if (r < 0 || r >= N) {
-        *bad = 1;
-        idxT[i] = 0u;
-    } else {
-        idxT[i] = (uint32_t)pos_of_row[r];
-    }
+    uint32_t pos = 0u;
+    if (r < 0 || r >= N) *bad = 1;
+    else pos = (uint32_t)pos_of_row[r];
+    idxT[i] = pos;
+    if (idxU) idxU[s * KM + e] = pos;
 }
 
 // Upper tail of the F distribution, cephes fdtrc(a, b, x) = incbet(b/2, a/2, b / (b + a x)); NaN for x < 0
@@ -274,6 +275,158 @@ __global__ void __launch_bounds__(kKwThreads, 1) k_kruskal(const AnovaArgs a, in
     }
 }
 
+// Kruskal-Wallis by SORTING (n log^2 n instead of n^2): one warp per (gene, subsample) sorts the pooled K * m values with
+// the register network of warp_prims.cuh, parks the sorted strip in shared memory, and every element finds
+// #{x < v} and #{x <= v} by two binary searches -- the same two integers the counting kernel forms, so the doubled
+// ranks, the per-group rank sums and the tie sum are the same exact integers (phet.py:372-377 -> scipy.stats.kruskal).
+// E = registers per lane (32 E >= K m).
+template <typename T, int E, bool STAGED>
+__global__ void __launch_bounds__(kKwThreads, 1) k_kruskal_sort(const AnovaArgs a, int vec_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = kKwThreads / 32;
+    constexpr int NP = 32 * E;
+    // the gene's cell vector is staged once per gene (the K m gathers of the S subsamples then hit shared memory, not L2)
+    T *vec = reinterpret_cast<T *>(smem_raw);                                                      // [N] when STAGED
+    T *pool_all = reinterpret_cast<T *>(smem_raw + vec_bytes);                                     // [NW][NP] sorted strips
+    int *gsum_all = reinterpret_cast<int *>(smem_raw + vec_bytes + (size_t)NW * NP * sizeof(T));   // [NW][K] doubled rank sums
+    __shared__ double red[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.K, m = a.m, n = K * m;
+    T *pool = pool_all + (size_t)warp * NP;
+    int *gsum = gsum_all + warp * K;
+    const double dn = (double)n;
+    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+        const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
+        if (STAGED) {
+            __syncthreads();   // the previous gene's gathers are done
+            for (int64_t i = tid; i < a.N; i += kKwThreads) vec[i] = row[i];
+            __syncthreads();
+        }
+        const T *src = STAGED ? vec : row;
+        double fisher = 0.0, my_ssbn = 0.0, my_tie = 0.0;
+        int64_t my_s = -1;
+        for (int64_t s = warp; s < a.S; s += NW) {
+            const uint32_t *ix = a.idxU + s * (int64_t)n;   // this subsample's positions, adjacent
+            T v[E], orig[E];
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const int e = lane + 32 * r;
+                v[r] = (e < n) ? src[__ldg(ix + e)] : Lim<T>::inf();
+                orig[r] = v[r];
+            }
+            for (int k = lane; k < K; k += 32) gsum[k] = 0;
+            warp_sort_asc<T, E>(v, lane);
+#pragma unroll
+            for (int r = 0; r < E; ++r) pool[lane + 32 * r] = v[r];
+            __syncwarp();
+            long long tie = 0;   // sum over elements of (t^2 - 1), t = size of the element's tie group
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const int e = lane + 32 * r;
+                const bool ok = e < n;
+                const T x = orig[r];
+                // lower / upper bound of x in pool[0, n): branch-free bisection over the padded power-of-two span
+                int lo = 0, hi = 0;
+#pragma unroll
+                for (int step = next_pow2(NP); step >= 1; step >>= 1) {   // (the steps must be able to add up to n = NP)
+                    const int pl = lo + step, ph = hi + step;
+                    if (pl <= n && pool[pl - 1] < x) lo = pl;
+                    if (ph <= n && pool[ph - 1] <= x) hi = ph;
+                }
+                const int dr = ok ? lo + hi + 1 : 0;   // twice the average rank
+                if (ok) {
+                    const long long t = hi - lo;
+                    tie += t * t - 1;
+                }
+                if (m >= 32) {   // the 32 elements of this row belong to at most two groups: two warp reductions
+                    const int gA = (32 * r) / m;
+                    const int bnd = (gA + 1) * m - 32 * r;   // first lane of group gA + 1
+                    const int sA = __reduce_add_sync(0xFFFFFFFFu, lane < bnd ? dr : 0);
+                    const int sB = __reduce_add_sync(0xFFFFFFFFu, lane < bnd ? 0 : dr);
+                    if (lane == 0) {
+                        if (gA < K) gsum[gA] += sA;
+                        if (gA + 1 < K) gsum[gA + 1] += sB;
+                    }
+                } else if (ok) {
+                    atomicAdd(&gsum[e / m], dr);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) tie += __shfl_xor_sync(0xFFFFFFFFu, tie, o);
+            __syncwarp();
+            // the statistic of this unit is parked; every 32 units the warp evaluates 32 tail probabilities at once
+            // (one lane each) instead of one lane evaluating exp / erfc / log while 31 wait
+            const int slot = (int)(((s - warp) / NW) & 31);
+            if (lane == slot) {
+                double ssbn = 0.0;
+                for (int k = 0; k < K; ++k) {   // (same order as the counting kernel: the two stay bit-identical)
+                    const double r = 0.5 * (double)gsum[k];
+                    ssbn += r * r / (double)m;
+                }
+                my_ssbn = ssbn;
+                my_tie = (double)tie;
+                my_s = s;
+            }
+            __syncwarp();
+            if (slot == 31 || s + NW >= a.S) {
+                if (my_s >= 0) {
+                    double h = 12.0 / (dn * (dn + 1.0)) * my_ssbn - 3.0 * (dn + 1.0);
+                    const double ties = 1.0 - my_tie / (dn * dn * dn - dn);
+                    h /= ties;
+                    double p = chi2_sf_int(h, K - 1);
+                    if (p <= a.p_flush) p = 0.0;
+                    if (!(p == p) || isinf(p)) p = 0.0;       // phet.py:378 nan_to_num
+                    if (a.dbgP) a.dbgP[(size_t)g * (size_t)a.S + (size_t)my_s] = p;
+                    fisher += fisher_term(p);
+                    my_s = -1;
+                }
+            }
+        }
+        fisher = warp_sum(fisher);
+        __syncthreads();
+        if (lane == 0) red[warp] = fisher;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NW; ++w) t += red[w];
+            a.acc_f[g] = t;
+        }
+    }
+}
+
+template <typename T, int E>
+static int launch_kruskal_sort_E(phet_ctx *c, const AnovaArgs &a, int64_t grid) {
+    const size_t strips = (size_t)(kKwThreads / 32) * ((size_t)32 * E * sizeof(T) + (size_t)a.K * sizeof(int));
+    if (strips > (size_t)kMaxSmemOptin - 1024) return 1;
+    const size_t vec_bytes = ((size_t)a.N * sizeof(T) + 15) & ~(size_t)15;
+    if (vec_bytes + strips <= (size_t)kMaxSmemOptin - 1024) {
+        PHET_CUDA(cudaFuncSetAttribute(k_kruskal_sort<T, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(vec_bytes + strips)));
+        k_kruskal_sort<T, E, true><<<(unsigned)grid, kKwThreads, vec_bytes + strips, c->stream>>>(a, (int)vec_bytes);
+    } else {   // a cell vector too long to stage: gathers go to L2
+        PHET_CUDA(cudaFuncSetAttribute(k_kruskal_sort<T, E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strips));
+        k_kruskal_sort<T, E, false><<<(unsigned)grid, kKwThreads, strips, c->stream>>>(a, 0);
+    }
+    return 0;
+}
+
+// Returns 1 when the pooled sample does not fit the sort kernel (more than 1024 values): the counting kernel takes it.
+template <typename T>
+static int launch_kruskal_sort(phet_ctx *c, const AnovaArgs &a, int64_t grid) {
+    const int need = (a.K * a.m + 31) / 32;
+    if (sizeof(T) == 8 && need > 12) return 1;   // (two copies of the values per lane: wider double instantiations spill)
+    if (need <= 1) return launch_kruskal_sort_E<T, 1>(c, a, grid);
+    if (need <= 2) return launch_kruskal_sort_E<T, 2>(c, a, grid);
+    if (need <= 3) return launch_kruskal_sort_E<T, 3>(c, a, grid);
+    if (need <= 4) return launch_kruskal_sort_E<T, 4>(c, a, grid);
+    if (need <= 6) return launch_kruskal_sort_E<T, 6>(c, a, grid);
+    if (need <= 8) return launch_kruskal_sort_E<T, 8>(c, a, grid);
+    if (need <= 12) return launch_kruskal_sort_E<T, 12>(c, a, grid);
+    if (need <= 16) return launch_kruskal_sort_E<T, 16>(c, a, grid);
+    if (need <= 24) return launch_kruskal_sort_E<T, 24>(c, a, grid);
+    if (need <= 32) return launch_kruskal_sort_E<T, 32>(c, a, grid);
+    return 1;
+}
+
 int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int64_t m, double ln_beta, double p_flush,
                  int capture_debug, int kruskal) {
     const int64_t KM = K * m, N = c->n0 + c->n1;
@@ -282,8 +435,13 @@ int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int
     PHET_CUDA(cudaMemcpyAsync(c->anova_idx.p, idx_host, sizeof(int32_t) * (size_t)(S * KM), cudaMemcpyHostToDevice, c->stream));
     int *bad = reinterpret_cast<int *>(c->scalars.p + 12);
     PHET_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), c->stream));
+    uint32_t *idxU = nullptr;
+    if (kruskal) {   // warp-per-subsample kernel: one subsample's positions adjacent
+        if (int e = c->anova_idxU.alloc((size_t)(S * KM))) return e;
+        idxU = c->anova_idxU.p;
+    }
     k_anova_index<<<(unsigned)((S * KM + 255) / 256), 256, 0, c->stream>>>(c->anova_idx.p, S, KM, c->pos_of_row.p, N, c->anova_idxT.p,
-                                                                          bad);
+                                                                          idxU, bad);
     c->launches++;
     PHET_CUDA(cudaGetLastError());
     int hbad = 0;
@@ -299,6 +457,7 @@ int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int
     a.g_end = c->xg_g0 + c->xg_rows;
     a.N = N;
     a.idxT = c->anova_idxT.p;
+    a.idxU = idxU;
     a.S = S;
     a.K = (int)K;
     a.m = (int)m;
@@ -324,6 +483,15 @@ int launch_anova(phet_ctx *c, const int32_t *idx_host, int64_t S, int64_t K, int
         const size_t smem_kw = (size_t)(kKwThreads / 32) * ((size_t)n_pad4 * e_st + (size_t)K * sizeof(int));
         PHET_REQUIRE(smem_kw <= (size_t)kMaxSmemOptin - 1024, "phet_group_test: K * m too large for the per-warp rank strips");
         int64_t gridk = c->num_sms < ng ? c->num_sms : ng;
+        if (getenv("PHET_KRUSKAL_IMPL") == nullptr || strcmp(getenv("PHET_KRUSKAL_IMPL"), "count") != 0) {
+            const int rc = c->storage == PHET_F32 ? launch_kruskal_sort<float>(c, a, gridk) : launch_kruskal_sort<double>(c, a, gridk);
+            if (rc != 1) {
+                if (rc) return rc;
+                c->launches++;
+                PHET_CUDA(cudaGetLastError());
+                return PHET_OK;
+            }
+        }
         if (c->storage == PHET_F32) {
             PHET_CUDA(cudaFuncSetAttribute(k_kruskal<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kw));
             k_kruskal<float><<<(unsigned)gridk, kKwThreads, smem_kw, c->stream>>>(a, n_pad4);

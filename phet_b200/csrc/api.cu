@@ -473,6 +473,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->raw_keep.release();
     c->anova_idx.release();
     c->anova_idxT.release();
+    c->anova_idxU.release();
     c->rank_keys.release();
     c->rank_order.release();
     c->rank_sorted.release();

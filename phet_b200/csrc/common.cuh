@@ -161,7 +161,7 @@ struct phet_ctx {
     int raw_dtype = PHET_F32;
     // multi-class Step 1 (anova.cu) and the Step-3 slicing range of a multi-class fit
     phet::DevBuf<int32_t> anova_idx;
-    phet::DevBuf<uint32_t> anova_idxT;
+    phet::DevBuf<uint32_t> anova_idxT, anova_idxU;
     int64_t step3_min_size = 0;          // phet_set_option(PHET_OPT_STEP3_MIN_SIZE): slices cover [0, this) instead of [0, min(n0, n1))
     // ranking (rank.cu)
     phet::DevBuf<unsigned long long> rank_keys;

@@ -153,3 +153,43 @@ def test_group_tests_on_long_cell_vectors(N):
         groups = [Xz[idx[s, c]] for c in range(K)]
         assert np.allclose(Pa[:, s], stats.f_oneway(*groups)[1], rtol=1e-3, atol=1e-300)
         assert np.allclose(Pk[:, s], stats.kruskal(*groups)[1], rtol=1e-3, atol=1e-300)
+
+
+@pytest.mark.parametrize("case", ["continuous_m57", "counts_m40", "ties_m20_k5", "f64_m130", "full_strip_m16_k4", "full_strip_m64_k2"])
+def test_kruskal_sort_kernel_equals_counting_kernel(case, monkeypatch):
+    """k_kruskal_sort (warp sort + two binary searches per element) forms the same exact integers as the counting kernel
+    k_kruskal (#{x < v}, #{x <= v}): the p-values must be bit-identical; and they agree with scipy.stats.kruskal."""
+    from scipy import stats
+    from phet_b200 import _capi
+    rng = np.random.default_rng(11)
+    K, m, dt, gen = {"continuous_m57": (3, 57, np.float32, lambda s: rng.gamma(2.0, 1.0, s)),
+                     "counts_m40": (3, 40, np.float32, lambda s: rng.poisson(0.8, s).astype(np.float64)),
+                     "ties_m20_k5": (5, 20, np.float32, lambda s: rng.integers(0, 4, s).astype(np.float64)),
+                     "f64_m130": (2, 130, np.float64, lambda s: rng.normal(0, 1, s)),
+                     # K m a power of two: the sorted strip has no padding at all
+                     "full_strip_m16_k4": (4, 16, np.float32, lambda s: rng.poisson(1.5, s).astype(np.float64)),
+                     "full_strip_m64_k2": (2, 64, np.float64, lambda s: rng.integers(0, 6, s).astype(np.float64))}[case]
+    N, G, S = 1500, 24, 37
+    y = (np.arange(N) * K // N).astype(np.int64)
+    X = np.ascontiguousarray(gen((N, G)).astype(dt))
+    X[:, 0] = 1.0   # a constant gene: one tie group
+    idx = np.empty((S, K, m), dtype=np.int32)
+    for s in range(S):
+        for c in range(K):
+            idx[s, c] = rng.choice(np.where(y == c)[0], m, replace=False)
+    P = {}
+    for impl in ("sort", "count"):
+        monkeypatch.setenv("PHET_KRUSKAL_IMPL", impl)
+        ctx = _capi.Context(0)
+        try:
+            ctx.set_classes(np.where(y == 0)[0], np.where(y != 0)[0])
+            ctx.load_matrix(X, _capi.NORM_NONE)
+            ctx.kruskal(idx, 0.0, capture=True)
+            P[impl] = ctx.read(_capi.BUF_P, np.float64, (G, S))
+        finally:
+            ctx.close()
+    assert np.array_equal(P["sort"], P["count"])
+    for s in range(0, S, 6):
+        for g in range(1, G, 5):
+            want = stats.kruskal(*[X[idx[s, c], g].astype(np.float64) for c in range(K)])[1]
+            assert np.isclose(P["sort"][g, s], want, rtol=1e-9, atol=1e-300)
