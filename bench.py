@@ -229,7 +229,8 @@ class Fit:
         self.ctx.set_classes(self.ctrl, self.case)
         self.ctx.set_index_sets(self.idx)
         if self.perms == "reference":
-            self._pipeline(X_dev_ptr, mt=mt, replay_perms=True, keep_perm_tables=True)
+            # (N > 1: a rank needs the stream up to its own genes only; the final state of `mt` is not used here)
+            self._pipeline(X_dev_ptr, mt=mt, replay_perms=True, keep_perm_tables=True, stop_after_own_genes=self.world > 1)
             self.ctx.sync()
 
     def finish(self, fetch=True):

@@ -176,6 +176,12 @@ typedef struct {
     int64_t S_draw;
     int32_t *idx_out;
     int32_t keep_perm_tables;              /* PHET_PERM_REPLAY: keep the tables of genes [g3_begin, g3_end) for PHET_PERM_RESIDENT */
+    /* PHET_PERM_REPLAY with several ranks on one host: != 0 stops the replay after the draws of gene g3_end - 1 instead
+     * of running through the remaining genes' draws.  `mt` is then left mid-stream; the rank that owns the LAST genes
+     * (g3_end == G) ends in the reference's final state and hands it to the others (phet_b200/phet.py broadcasts it).
+     * The scan of the stream is sequential, so rank r pays (r + 1) / N of it instead of all of it, and the host's cores
+     * free up as the early ranks finish. */
+    int32_t stop_after_own_genes;
 } phet_pipeline_params;
 
 int phet_run_pipeline(phet_ctx *ctx, const void *X, int is_device, int64_t N, int64_t G, int dtype,

@@ -56,7 +56,7 @@ class PipelineParams(C.Structure):
                 ("perm_ctrl", C.c_void_p), ("perm_case", C.c_void_p), ("table_full", C.c_void_p),
                 ("table_last", C.c_void_p), ("n_last", C.c_int64), ("block_genes", C.c_int64),
                 ("mt", C.c_void_p), ("draw_index_sets", C.c_int32), ("S_draw", C.c_int64), ("idx_out", C.c_void_p),
-                ("keep_perm_tables", C.c_int32)]
+                ("keep_perm_tables", C.c_int32), ("stop_after_own_genes", C.c_int32)]
 
 
 class MtJob(C.Structure):
@@ -448,7 +448,8 @@ class Context:
     def run_pipeline(self, X, N, G, dtype, params: Step1Params, m, table_full, table_last, n_last,
                      g_range=None, s_range=None, g3_range=None, normalize=NORM_ZSCORE, storage=None,
                      perm_ctrl=None, perm_case=None, seed=0, is_device=False, block_genes=0, mt=None,
-                     replay_perms=False, draw_index_sets=None, keep_perm_tables=False, resident_perms=False):
+                     replay_perms=False, draw_index_sets=None, keep_perm_tables=False, resident_perms=False,
+                     stop_after_own_genes=False):
         """Stage 0 + Step 1 + Step 3 over gene blocks.  X: C-contiguous host ndarray (N, G) or, with
         is_device=True, a raw device pointer (int).  ``mt`` (an MtStream) + ``replay_perms=True``: the Step-3
         permutations are the reference's own draws (PHET_PERM_REPLAY); ``draw_index_sets=(S, keep)``: the index
@@ -483,6 +484,7 @@ class Context:
         elif replay_perms:
             pp.perm_mode = PERM_REPLAY
             pp.keep_perm_tables = 1 if keep_perm_tables else 0
+            pp.stop_after_own_genes = 1 if stop_after_own_genes else 0
         elif resident_perms:
             pp.perm_mode = PERM_RESIDENT
         else:

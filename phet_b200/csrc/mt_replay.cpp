@@ -967,13 +967,25 @@ int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par *
     MT_REQUIRE(mt != nullptr && out != nullptr, "NULL argument");
     MT_REQUIRE(max_n >= 1 && max_n < ((int64_t)1 << 31), "max_n must be in [1, 2^31)");
     *out = nullptr;
-    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = std::thread::hardware_concurrency();
+    // several ranks of one job replay the same stream side by side on one host (one process per GPU): each takes its
+    // share of the cores.  All these threads spin, so oversubscription is what hurts: measured on the 8-GPU box (32
+    // cores), 8 replays with 4 + 1 + 4 threads each took 0.5 - 1.3 s instead of 0.45 s.  PHET_REPLAY_PROCS, else
+    // torchrun's LOCAL_WORLD_SIZE, says how many processes share the host.
+    int procs = 1;
+    if (const char *e = getenv("PHET_REPLAY_PROCS")) procs = atoi(e) > 0 ? atoi(e) : 1;
+    else if (const char *e2 = getenv("LOCAL_WORLD_SIZE")) procs = atoi(e2) > 0 ? atoi(e2) : 1;
+    const unsigned budget = hw ? (hw / (unsigned)procs > 0 ? hw / (unsigned)procs : 1u) : 0u;
     int gens = 4;
-    if (const char *w = getenv("PHET_REPLAY_GENERATORS")) gens = atoi(w) >= 0 ? atoi(w) : 4;
+    if (budget && budget < 9) gens = budget >= 3 ? (int)(budget - 2 < 4 ? budget - 2 : 4) : 0;
+    if (const char *w = getenv("PHET_REPLAY_GENERATORS")) gens = atoi(w) >= 0 ? atoi(w) : gens;
     if (workers <= 0) {
         workers = 4;
-        if (const char *w = getenv("PHET_REPLAY_WORKERS")) workers = atoi(w) > 0 ? atoi(w) : 4;
+        if (budget && budget < 9) workers = (int)budget - gens - 1 >= 1 ? (int)budget - gens - 1 : 1;
+        if (workers > 4) workers = 4;
+        if (const char *w = getenv("PHET_REPLAY_WORKERS")) workers = atoi(w) > 0 ? atoi(w) : workers;
     }
+    if (budget) hw = budget;
     if (hw && (unsigned)(workers + gens + 1) > hw) {   // not enough cores for the ring pipeline: scanner generates for itself
         gens = 0;
         if ((unsigned)workers + 1 > hw) workers = hw > 1 ? (int)hw - 1 : 1;

@@ -267,7 +267,7 @@ int run_pipeline_replay(phet_ctx *c, const void *X, int is_device, int64_t N, in
             for (int64_t g0 = a; g0 < b; g0 += rounds_per_block)
                 blocks.push_back({1, g0, (g0 + rounds_per_block <= b) ? rounds_per_block : b - g0, true});
         }
-        if (p->g3_end < G) blocks.push_back({1, p->g3_end, G - p->g3_end, false});
+        if (p->g3_end < G && !p->stop_after_own_genes) blocks.push_back({1, p->g3_end, G - p->g3_end, false});
     }
     int64_t max_count = 1;
     for (const ReplayBlock &b : blocks)

@@ -311,12 +311,26 @@ class PHet:
             else:
                 draw_on_device = True
         self.timings_["host_draws_s"] = time.perf_counter() - t0
+        final_state = None
         try:
-            return self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
-                                    rank, world, dist, mt=mt, draw_on_device=draw_on_device)
+            scores = self._run_device(ctx, X, examples_i, examples_j, idx, perm0, perm1, seed, m, S, n_slices, n_last,
+                                      rank, world, dist, mt=mt, draw_on_device=draw_on_device)
+            if dist is not None and world > 1 and draw_on_device and self.permutation == "reference":
+                # every rank stopped replaying after its own genes' draws (the scan of the stream is sequential: rank r
+                # pays (r + 1) / N of it); the last rank ran to the end of the stream and hands its final state over
+                from .distributed import broadcast_numpy
+                key, pos = mt.state()
+                packed = broadcast_numpy(np.concatenate([key.view(np.int32), np.array([pos], dtype=np.int32)]), dist,
+                                         src=world - 1)
+                final_state = ("MT19937", packed[:624].view(np.uint32).copy(), int(packed[624]), st[3], st[4])
+            return scores
         finally:
             if mt is not None:
-                mt.to_numpy()   # np.random continues where the reference's stream would
+                # np.random continues where the reference's stream would
+                if final_state is not None:
+                    np.random.set_state(final_state)
+                else:
+                    mt.to_numpy()
                 mt.close()
 
     # ------------------------------------------------------------------------------------
@@ -369,7 +383,8 @@ class PHet:
                                  g3_range=g3_range,
                                  normalize=_capi.NORM_ZSCORE if self.normalize == "zscore" else _capi.NORM_NONE,
                                  storage=storage, perm_ctrl=perm0, perm_case=perm1, seed=seed, mt=mt if replay else None,
-                                 replay_perms=replay, draw_index_sets=draw_arg)
+                                 replay_perms=replay, draw_index_sets=draw_arg,
+                                 stop_after_own_genes=replay and dist is not None and world > 1)
         if drawn is not None:
             idx = drawn
         if replay:

@@ -23,6 +23,7 @@ int main(int argc, char** argv){
       double dt=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
       printf("workers=%d: %.2f us/perm -> cfg4 %.3f s\n", workers, dt/(2.0*per*nblk)*1e6, dt/(2.0*per*nblk)*62000);
     }
+    if (argc>2) return 0;   // parallel part only
     auto t0=std::chrono::steady_clock::now();
     for (int b=0;b<nblk;b++){ uint16_t* d=buf[b%slots].data(); phet_mt_job j[2]={{n,d,(int64_t)n*2,2},{n,d+(size_t)per*n,(int64_t)n*2,2}}; phet_mt_shuffle_rounds(e,j,2,per);} 
     double dt=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();

@@ -58,6 +58,15 @@ def main():
                 assert np.allclose(scores, ref, rtol=1e-5, atol=1e-12)
                 k = min(100, len(ref) // 4)
                 assert np.array_equal(np.argsort(-scores[:, 0], kind="stable")[:k], np.argsort(-ref[:, 0], kind="stable")[:k])
+        # the stream: every rank stops replaying after its own genes' draws and takes the final state from the last rank --
+        # np.random must end, on EVERY rank, where a one-process fit (= the reference) leaves it
+        np.random.seed(int(g["seed"]))
+        PHet(**g["params"], distributed=False).fit_predict(X, g["y"].astype(np.int64))
+        want = np.random.get_state()
+        np.random.seed(int(g["seed"]) if rank == 0 else 999 + rank)
+        PHet(**g["params"], distributed=True).fit_predict(X, g["y"].astype(np.int64))
+        got = np.random.get_state()
+        assert np.array_equal(want[1], got[1]) and want[2] == got[2], "np.random does not end in the reference's state"
         if rank == 0:
             print("rank0 ok", name, "world", dist.get_world_size(), flush=True)
     dist.barrier()
