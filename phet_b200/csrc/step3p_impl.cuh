@@ -113,6 +113,52 @@ __device__ __forceinline__ void s3p_hist(PosFn pos_of, int n, uint32_t vals_sa, 
     }
 }
 
+// The same histogram with the positions read from a permutation table (stride `st` entries between this lane's
+// elements): the table entries of trip t + 1 are in flight while trip t is gathered and counted -- the entries come
+// from HBM / L2, and without the second buffer every trip of 8 pays that latency in full.
+template <typename T>
+__device__ __forceinline__ void s3p_hist_table(const uint32_t *__restrict__ pp, int st, int n, uint32_t vals_sa, uint32_t hbase,
+                                               float scale, float off) {
+    constexpr float kTop = 4.0f * 32 - 1.5f;
+    uint32_t cur[8], nxt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cur[u] = (u < n) ? __ldg(pp + u * st) : 0u;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nxt[u] = (j + 8 + u < n) ? __ldg(pp + (j + 8 + u) * st) : 0u;
+        uint32_t ad[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const T v = lds_pos(vals_sa, cur[u], T(0));
+            pair_bucket((float)v, scale, off, kTop, hbase, ad[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 4) {
+            const uint32_t c0 = lds_u8(ad[u]), c1 = lds_u8(ad[u + 1]), c2 = lds_u8(ad[u + 2]), c3 = lds_u8(ad[u + 3]);
+            const uint32_t e1 = (ad[u + 1] == ad[u]) ? 1u : 0u;
+            const uint32_t e2 = ((ad[u + 2] == ad[u]) ? 1u : 0u) + ((ad[u + 2] == ad[u + 1]) ? 1u : 0u);
+            const uint32_t e3 = ((ad[u + 3] == ad[u]) ? 1u : 0u) + ((ad[u + 3] == ad[u + 1]) ? 1u : 0u) +
+                                ((ad[u + 3] == ad[u + 2]) ? 1u : 0u);
+            sts_u8(ad[u], c0 + 1u);
+            sts_u8(ad[u + 1], c1 + 1u + e1);
+            sts_u8(ad[u + 2], c2 + 1u + e2);
+            sts_u8(ad[u + 3], c3 + 1u + e3);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {   // the last, partial trip (its entries are already here)
+        if (j + u < n) {
+            uint32_t ad;
+            const T v = lds_pos(vals_sa, cur[u], T(0));
+            pair_bucket((float)v, scale, off, kTop, hbase, ad);
+            sts_u8(ad, lds_u8(ad) + 1u);
+        }
+    }
+}
+
 // P threads (lanes of one warp) share a slice in phases 1 and 2; each takes every P-th element.
 template <typename T, int E, int P>
 __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs pa) {
@@ -189,6 +235,17 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
                 if (cls == 0) prefetch_row_l2(row + b0c[1], b1c[1] - b0c[1]);
                 else if (g + gridDim.x < a.g_end)
                     prefetch_row_l2(row + (size_t)gridDim.x * (size_t)a.n_pad * sizeof(T), b1c[0] - b0c[0]);
+                if (a.perm_mode != PHET_PERM_DEVICE) {
+                    // ... and so do the table rows read next: the case row of this gene, the control row of the next
+                    const size_t row_b = (size_t)a.min_c * sizeof(uint32_t);
+                    const size_t pbytes = row_b > 32 ? ((row_b - 16) & ~(size_t)15) : 0;   // (start rounded up: stay inside the row)
+                    if (cls == 0) {
+                        prefetch_row_l2(reinterpret_cast<const void *>((reinterpret_cast<uintptr_t>(permc[1]) + 15) & ~(uintptr_t)15), pbytes);
+                    } else if (g + gridDim.x < a.g_end) {
+                        const uint32_t *nx = permc[0] + (size_t)gridDim.x * (size_t)a.min_c;
+                        prefetch_row_l2(reinterpret_cast<const void *>((reinterpret_cast<uintptr_t>(nx) + 15) & ~(uintptr_t)15), pbytes);
+                    }
+                }
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -251,7 +308,7 @@ __global__ void __launch_bounds__(kS3pThreads, 1) k_step3p(const Step3PairArgs p
                     s3p_hist<T>([&](int) { const uint32_t q = xr; xr = add_mod(xr, stepj, ncls); return q; }, npart, vsa[cls], hmine, wn.x, wn.y);
                 } else {
                     const uint32_t *pp = permc[cls] + (size_t)k * (size_t)m + my_part;
-                    s3p_hist<T>([&](int j) { return __ldg(pp + j * P); }, npart, vsa[cls], hmine, wn.x, wn.y);
+                    s3p_hist_table<T>(pp, P, npart, vsa[cls], hmine, wn.x, wn.y);
                 }
             }
             if (cls == 0) {
