@@ -976,13 +976,15 @@ int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par *
     if (const char *e = getenv("PHET_REPLAY_PROCS")) procs = atoi(e) > 0 ? atoi(e) : 1;
     else if (const char *e2 = getenv("LOCAL_WORLD_SIZE")) procs = atoi(e2) > 0 ? atoi(e2) : 1;
     const unsigned budget = hw ? (hw / (unsigned)procs > 0 ? hw / (unsigned)procs : 1u) : 0u;
-    int gens = 4;
-    if (budget && budget < 9) gens = budget >= 3 ? (int)(budget - 2 < 4 ? budget - 2 : 4) : 0;
+    // 3 generators + scanner + 3 workers when the cores are there (measured end to end at config 4 on the 16-core
+    // 1-GPU box: 0.36 s; 4 + 1 + 4: 0.39 s; 2 + 1 + 2: 0.39 s); 2 + 1 + 1 on a 4-core share (a rank of 8 stores 1/8 only)
+    int gens = 3;
+    if (budget && budget < 8) gens = budget >= 4 ? 2 : (budget >= 3 ? 1 : 0);
     if (const char *w = getenv("PHET_REPLAY_GENERATORS")) gens = atoi(w) >= 0 ? atoi(w) : gens;
     if (workers <= 0) {
-        workers = 4;
-        if (budget && budget < 9) workers = (int)budget - gens - 1 >= 1 ? (int)budget - gens - 1 : 1;
-        if (workers > 4) workers = 4;
+        workers = 3;
+        if (budget && budget < 8) workers = (int)budget - gens - 1 >= 1 ? (int)budget - gens - 1 : 1;
+        if (workers > 3) workers = 3;
         if (const char *w = getenv("PHET_REPLAY_WORKERS")) workers = atoi(w) > 0 ? atoi(w) : workers;
     }
     if (budget) hw = budget;
