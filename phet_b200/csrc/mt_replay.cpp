@@ -60,6 +60,7 @@ namespace {
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
 constexpr int kCarry = 128;     // outputs of the previous block kept in front of the current one (>= the widest trip of a scan)
+constexpr int kRingMirror = 320;  // outputs of the ring's start mirrored behind its end (>= the count-only scan's look-ahead of 256)
 constexpr int kGenSteps = 41;   // copy + 40 vector steps make the next block (see phet_mt::gen_step)
 // generator steps per 64-output trip of the scan (5 * 15.6 outputs >= 64); env PHET_MT_PUMP overrides (0: whole blocks)
 static const int kPump = getenv("PHET_MT_PUMP") ? atoi(getenv("PHET_MT_PUMP")) : 0;
@@ -293,7 +294,7 @@ struct SeqSrc {
 // (b) a ring that generator threads fill ahead of the readers (parallel replay below).  E = uint16_t when every
 // permutation is of <= 65536 cells (only the low 16 bits of an output can matter): half the bytes between cores.
 struct OutRing {
-    void *w = nullptr;            // [cap + kCarry] elements: the first kCarry are mirrored behind the end
+    void *w = nullptr;            // [cap + kRingMirror] elements: the first kRingMirror are mirrored behind the end
     int ebytes = 4;
     size_t cap = 0;               // elements; a multiple of region_elems
     size_t region_elems = 0;      // 624 * blocks per region
@@ -523,20 +524,38 @@ MT_AVX512 void count_draws16_avx512(Src &in, uint32_t n) {
         }
         const __m512i vm = _mm512_set1_epi16((short)mask);
         if (mask >= 8191u) {
-            while (i >= floor_i) {
-                in.need(128);
-                const __m512i vi = _mm512_set1_epi16((short)i);
-                const uint16_t *p = reinterpret_cast<const uint16_t *>(in.p);
+            // 128 outputs per trip, SOFTWARE-PIPELINED: the vector work of trip t + 1 does not wait for trip t to be
+            // settled.  As soon as trip t is classified (sure / ambiguous lanes against its exact start i), the start of
+            // trip t + 1 is known to lie in [i - #not-rejected, i - #sure] -- a window as wide as trip t has ambiguous
+            // lanes, usually 0 -- so trip t + 1 is classified against those two bounds right away: v + k <= lower bound is
+            // accepted whatever happens, v > upper bound is rejected whatever happens, the lanes in between are settled
+            // in lane order with the exact start once trip t is done.  The chain from one trip to the next is then a
+            // popcount and a subtraction instead of broadcast -> compare -> mask moves -> popcount.
+            auto classify = [&](const uint16_t *q0, uint32_t ihi, uint32_t ilo, uint64_t &s0, uint64_t &s1, uint64_t &a0, uint64_t &a1) MT_AVX512 {
+                const __m512i vhi = _mm512_set1_epi16((short)ihi), vlo = _mm512_set1_epi16((short)ilo);
                 __mmask32 A[4], S[4];
 #pragma GCC unroll 4
                 for (int q = 0; q < 4; ++q) {
-                    const __m512i vq = _mm512_and_si512(_mm512_loadu_si512(p + 32 * q), vm);
-                    A[q] = _mm512_cmple_epu16_mask(vq, vi);                                   // not rejected: v <= i
-                    S[q] = _mm512_cmple_epu16_mask(_mm512_adds_epu16(vq, lanek[q]), vi);      // accepted for sure: v + k <= i
+                    const __m512i vq = _mm512_and_si512(_mm512_loadu_si512(q0 + 32 * q), vm);
+                    A[q] = _mm512_cmple_epu16_mask(vq, vhi);                                   // not rejected: v <= largest possible start
+                    S[q] = _mm512_cmple_epu16_mask(_mm512_adds_epu16(vq, lanek[q]), vlo);      // accepted for sure: v + k <= smallest possible start
                 }
-                uint64_t sure0 = _cvtmask64_u64(_mm512_kunpackd(S[1], S[0])), sure1 = _cvtmask64_u64(_mm512_kunpackd(S[3], S[2]));
-                uint64_t amb0 = _cvtmask64_u64(_mm512_kunpackd(A[1], A[0])) & ~sure0;
-                uint64_t amb1 = _cvtmask64_u64(_mm512_kunpackd(A[3], A[2])) & ~sure1;
+                s0 = _cvtmask64_u64(_mm512_kunpackd(S[1], S[0]));
+                s1 = _cvtmask64_u64(_mm512_kunpackd(S[3], S[2]));
+                a0 = _cvtmask64_u64(_mm512_kunpackd(A[1], A[0])) & ~s0;
+                a1 = _cvtmask64_u64(_mm512_kunpackd(A[3], A[2])) & ~s1;
+            };
+            uint64_t sure0 = 0, sure1 = 0, amb0 = 0, amb1 = 0;
+            bool have = false;   // (sure, amb) hold the classification of the trip at the current position
+            while (i >= floor_i) {
+                in.need(256);
+                const uint16_t *p = reinterpret_cast<const uint16_t *>(in.p);
+                if (!have) classify(p, i, i, sure0, sure1, amb0, amb1);
+                // the next trip, from the bounds on where it will start (i >= 8192 > 128: no wrap)
+                const uint32_t n_sure = (uint32_t)(__builtin_popcountll(sure0) + __builtin_popcountll(sure1));
+                const uint32_t n_open = (uint32_t)(__builtin_popcountll(amb0) + __builtin_popcountll(amb1));
+                uint64_t nsure0, nsure1, namb0, namb1;
+                classify(p + 128, i - n_sure, i - n_sure - n_open, nsure0, nsure1, namb0, namb1);
                 while (__builtin_expect(amb0 != 0, 0)) {   // in lane order: everything before lane k is decided
                     const int k = __builtin_ctzll(amb0);
                     const uint32_t ik = i - (uint32_t)__builtin_popcountll(sure0 & ((1ull << k) - 1ull));
@@ -560,6 +579,11 @@ MT_AVX512 void count_draws16_avx512(Src &in, uint32_t n) {
                 }
                 i -= total;
                 in.advance(used);
+                have = used == 128;   // (a trip cut short moves the next one: classify afresh)
+                sure0 = nsure0;
+                sure1 = nsure1;
+                amb0 = namb0;
+                amb1 = namb1;
             }
         } else {
             while (i >= floor_i) {
@@ -746,7 +770,7 @@ struct phet_mt_par {
                         for (int i = 0; i < kN; ++i) dst[i] = (E)out[i];
                     }
                 }
-                if (dst == w) memcpy(w + ring.cap, w, sizeof(E) * kCarry);   // the wrap-around mirror
+                if (dst == w) memcpy(w + ring.cap, w, sizeof(E) * kRingMirror);   // the wrap-around mirror
             }
             ring.ready[reg % ring.nreg].store(reg + 1, std::memory_order_release);
         }
@@ -1016,7 +1040,7 @@ int phet_mt_par_begin(phet_mt *mt, int32_t workers, int64_t max_n, phet_mt_par *
         if (r.nreg < (size_t)(2 * gens + 2)) r.nreg = (size_t)(2 * gens + 2);
         r.cap = r.nreg * r.region_elems;
         void *mem = nullptr;
-        if (posix_memalign(&mem, 64, (r.cap + kCarry + 64) * (size_t)r.ebytes) != 0 || !mem) {
+        if (posix_memalign(&mem, 64, (r.cap + kRingMirror + 64) * (size_t)r.ebytes) != 0 || !mem) {
             delete p;
             phet::set_error("out of host memory");
             return PHET_ERR_NOMEM;
