@@ -536,24 +536,40 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         y2 = smallH ? pick_reg<T, 8>(cH, raH) : tieH;
                         y3 = smallH ? pick_reg<T, 8>(cH, rbH) : tieH;
                         mark(12);
-                        if (CM > 8 && (nL > 8 || nH > 8)) {   // 9..16 candidates in a range (a few per cent of the samples): all 16 slots
+                        if (CM > 8 && (nL > 8 || nH > 8)) {   // 9..16 candidates in a range (a few per cent of the samples)
+                            // the 8 newest candidates are sorted already: the others (slots 8 .. nc - 1 of the pack, usually one
+                            // or two) are fetched one at a time and inserted into the sorted run
 #pragma unroll 1
                             for (int h = 0; h < 2; ++h) {
                                 const int nc = h ? nH : nL;
                                 if (nc <= 8 || nc > CM) continue;
-                                uint32_t pk[PW];
-#pragma unroll
-                                for (int i = 0; i < PW; ++i) pk[i] = h ? pkH[i] : pkL[i];
                                 T c16[16];
-                                uint32_t pos16[16];
 #pragma unroll
-                                for (int k = 0; k < 16; ++k) pos16[k] = (k < nc) ? (uint32_t)__ldg(ip + pack_byte<PW>(pk, k < CM ? k : 0) * 32u) : 0u;
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) {
-                                    const T v = src.at(pos16[k]);
-                                    c16[k] = (k < nc) ? v : Big<T>::v();
+                                for (int k = 0; k < 8; ++k) {
+                                    c16[k] = h ? cH[k] : cL[k];
+                                    c16[8 + k] = Big<T>::v();
                                 }
-                                sort_pow2_asc<T, 16>(c16);
+                                const uint32_t w2 = h ? pkH[PW > 2 ? 2 : 0] : pkL[PW > 2 ? 2 : 0], w3 = h ? pkH[PW > 3 ? 3 : 0] : pkL[PW > 3 ? 3 : 0];
+                                // all their index loads in flight together; the values wait in the (consumed) histogram words
+                                uint32_t pe[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const uint32_t j = ((u < 4 ? w2 : w3) >> (8 * (u & 3))) & 255u;
+                                    pe[u] = (8 + u < nc) ? (uint32_t)__ldg(ip + j * 32u) : 0u;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    if (8 + u < nc) sts_val(hbase + 128u * (uint32_t)(u * (int)(sizeof(T) / 4)), src.at(pe[u]));
+#pragma unroll 1
+                                for (int e = 8; e < nc; ++e) {
+                                    T x = lds_val(hbase + 128u * (uint32_t)((e - 8) * (int)(sizeof(T) / 4)), T(0));
+#pragma unroll
+                                    for (int k = 0; k < 16; ++k) {   // x takes its place, the larger values move up
+                                        const T lo_ = tmin(c16[k], x);
+                                        x = tmax(c16[k], x);
+                                        c16[k] = lo_;
+                                    }
+                                }
                                 const T ya = pick_reg<T, 16>(c16, h ? raH : raL), yb = pick_reg<T, 16>(c16, h ? rbH : rbL);
                                 if (h) {
                                     y2 = ya;
