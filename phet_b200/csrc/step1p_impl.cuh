@@ -170,16 +170,16 @@ __device__ __forceinline__ void sort8_asc(T (&x)[8]) {
 #undef PHET_CE
 }
 
-// Candidate element numbers (one byte each, newest in byte 0) shifted through W 32-bit registers.
-template <int W>
-__device__ __forceinline__ void push_byte(uint32_t (&p)[W], uint32_t j) {
+// Candidate element numbers (EB = 8 or 16 bits each, newest in the lowest bits) shifted through W 32-bit registers.
+template <int W, int EB>
+__device__ __forceinline__ void push_entry(uint32_t (&p)[W], uint32_t j) {
 #pragma unroll
-    for (int i = W - 1; i >= 1; --i) p[i] = __funnelshift_l(p[i - 1], p[i], 8);
-    p[0] = p[0] * 256u + j;
+    for (int i = W - 1; i >= 1; --i) p[i] = __funnelshift_l(p[i - 1], p[i], EB);
+    p[0] = (p[0] << EB) | j;
 }
-template <int W>
-__device__ __forceinline__ uint32_t pack_byte(const uint32_t (&p)[W], int k) {  // k: compile-time constant after unrolling
-    return (p[k >> 2] >> (8 * (k & 3))) & 255u;
+template <int W, int EB>
+__device__ __forceinline__ uint32_t pack_entry(const uint32_t (&p)[W], int k) {  // k: compile-time constant after unrolling
+    return (p[(k * EB) >> 5] >> ((k * EB) & 31)) & ((1u << EB) - 1u);
 }
 
 // x[r] for a runtime r < N without dynamic register indexing
@@ -457,11 +457,13 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                     rescue = rescue || wrapped;
                     mark(9);
                     T y0 = T(0), y1 = T(0), y2 = T(0), y3 = T(0);
-                    if (!BIG) {
-                        // ---- staged instantiation (m <= 255): one pass over the bucket list shifts the element numbers of the
-                        //      candidates of either bucket range into byte packs held in REGISTERS (newest in byte 0); no
-                        //      records, no element lists in shared memory.  Up to CM candidates per range (16 floats / 8 doubles).
-                        constexpr int PW = CM / 4;
+                    {
+                        // ---- one pass over the bucket list turns the words holding a candidate of either bucket range into
+                        //      records; the records are decoded into element numbers that are shifted into packs held in
+                        //      REGISTERS (8 bits per element number, 16 when m can exceed 255; newest in the lowest bits) -- no
+                        //      element lists in shared memory.  Up to CM candidates per range (16 floats / 8 doubles).
+                        constexpr int EB = BIG ? 16 : 8;
+                        constexpr int PW = CM * EB / 32;
                         uint32_t pkL[PW], pkH[PW];
 #pragma unroll
                         for (int i = 0; i < PW; ++i) pkL[i] = pkH[i] = 0u;
@@ -472,8 +474,9 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
                             const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
                             const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
-                            // words holding a candidate become records (low-range flags in bit 7 of each byte, high-range flags
-                            // in bit 6, word number in bits 0-5), compacted in place over the part of the list already consumed
+                            // records: low-range flags in bit 7 of each byte, high-range flags in bit 6, word number in bits 0-5
+                            // (BIG: < 128 words, bit 6 of the number goes to bit 8), compacted in place over the part of the
+                            // list already consumed
                             int nrec = 0;
                             for (int c = 0; c < nchunk; ++c) {
                                 const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
@@ -485,7 +488,8 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                                     const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
                                     const uint32_t f = fl | (fh >> 1);
                                     if (f) {
-                                        sts_u32(blbase + 4u * (uint32_t)nrec, f | (uint32_t)(4 * c + k));
+                                        const uint32_t wno = (uint32_t)(4 * c + k);
+                                        sts_u32(blbase + 4u * (uint32_t)nrec, f | (BIG ? ((wno & 63u) | ((wno >> 6) << 8)) : wno));
                                         ++nrec;
                                     }
                                 }
@@ -494,17 +498,17 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             // records -> element numbers, shifted into the packs of their range
                             for (int i = 0; i < nrec; ++i) {
                                 const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
-                                const uint32_t jb = (rec & 63u) * 4u;
+                                const uint32_t jb = (BIG ? ((rec & 63u) | ((rec >> 2) & 0x40u)) : (rec & 63u)) * 4u;
                                 uint32_t f = rec & 0xC0C0C0C0u;
                                 do {
                                     const int bit = __ffs((int)f) - 1;
                                     f &= f - 1u;
                                     const uint32_t j = jb + (uint32_t)(bit >> 3);
                                     if (bit & 1) {   // bit 7 of a byte: low range
-                                        push_byte<PW>(pkL, j);
+                                        push_entry<PW, EB>(pkL, j);
                                         ++nL;
                                     } else {
-                                        push_byte<PW>(pkH, j);
+                                        push_entry<PW, EB>(pkH, j);
                                         ++nH;
                                     }
                                 } while (f);
@@ -518,8 +522,8 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                             uint32_t posL[8], posH[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                posL[k] = (k < nL) ? (uint32_t)__ldg(ip + pack_byte<PW>(pkL, k) * 32u) : 0u;
-                                posH[k] = (k < nH) ? (uint32_t)__ldg(ip + pack_byte<PW>(pkH, k) * 32u) : 0u;
+                                posL[k] = (k < nL) ? (uint32_t)__ldg(ip + pack_entry<PW, EB>(pkL, k) * 32u) : 0u;
+                                posH[k] = (k < nH) ? (uint32_t)__ldg(ip + pack_entry<PW, EB>(pkH, k) * 32u) : 0u;
                             }
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                         mark(12);
                         if (CM > 8 && (nL > 8 || nH > 8)) {   // 9..16 candidates in a range (a few per cent of the samples)
                             // the 8 newest candidates are sorted already: the others (slots 8 .. nc - 1 of the pack, usually one
-                            // or two) are fetched one at a time and inserted into the sorted run
+                            // or two) are inserted into the sorted run one at a time
 #pragma unroll 1
                             for (int h = 0; h < 2; ++h) {
                                 const int nc = h ? nH : nL;
@@ -549,14 +553,14 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                                     c16[k] = h ? cH[k] : cL[k];
                                     c16[8 + k] = Big<T>::v();
                                 }
-                                const uint32_t w2 = h ? pkH[PW > 2 ? 2 : 0] : pkL[PW > 2 ? 2 : 0], w3 = h ? pkH[PW > 3 ? 3 : 0] : pkL[PW > 3 ? 3 : 0];
+                                uint32_t pk[PW];
+#pragma unroll
+                                for (int i = 0; i < PW; ++i) pk[i] = h ? pkH[i] : pkL[i];
                                 // all their index loads in flight together; the values wait in the (consumed) histogram words
                                 uint32_t pe[8];
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    const uint32_t j = ((u < 4 ? w2 : w3) >> (8 * (u & 3))) & 255u;
-                                    pe[u] = (8 + u < nc) ? (uint32_t)__ldg(ip + j * 32u) : 0u;
-                                }
+                                for (int u = 0; u < 8; ++u)
+                                    pe[u] = (8 + u < nc) ? (uint32_t)__ldg(ip + pack_entry<PW, EB>(pk, 8 + u < CM ? 8 + u : 0) * 32u) : 0u;
 #pragma unroll
                                 for (int u = 0; u < 8; ++u)
                                     if (8 + u < nc) sts_val(hbase + 128u * (uint32_t)(u * (int)(sizeof(T) / 4)), src.at(pe[u]));
@@ -578,129 +582,6 @@ __global__ void __launch_bounds__(kPairMaxThreads, 1) k_step1p(const Step1PairAr
                                     y0 = ya;
                                     y1 = yb;
                                 }
-                            }
-                        }
-                    } else {
-                        // ---- one pass over the bucket list: words holding an element of either bucket range become
-                        //      records (low-range flags in bit 7 of each byte, high-range flags in bit 6, word index in
-                        //      bits 0-5), compacted in place over the part of the list already consumed
-                        int nrec = 0;
-                        {
-                            // a range that is too big is matched by nothing here (lo > hi) and handled below
-                            const uint32_t lo4L = (smallL ? (uint32_t)B[0] : 1u) * 0x01010101u;
-                            const uint32_t hi4L = ((smallL ? (uint32_t)B[1] : 0u) * 0x01010101u) | 0x80808080u;
-                            const uint32_t lo4H = (smallH ? (uint32_t)B[2] : 1u) * 0x01010101u;
-                            const uint32_t hi4H = ((smallH ? (uint32_t)B[3] : 0u) * 0x01010101u) | 0x80808080u;
-                            for (int c = 0; c < nchunk; ++c) {
-                                const uint4 q = lds_v4(blbase + 16u * (uint32_t)c);
-    #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint32_t w = (k == 0 ? q.x : (k == 1 ? q.y : (k == 2 ? q.z : q.w)));
-                                    const uint32_t wh = w | 0x80808080u;
-                                    const uint32_t fl = (wh - lo4L) & (hi4L - w) & 0x80808080u;
-                                    const uint32_t fh = (wh - lo4H) & (hi4H - w) & 0x80808080u;
-                                    const uint32_t f = fl | (fh >> 1);
-                                    if (f) {
-                                        const uint32_t wno = (uint32_t)(4 * c + k);  // < 64 (BIG: < 128, bit 6 goes to byte 1)
-                                        sts_u32(blbase + 4u * (uint32_t)nrec, f | (BIG ? ((wno & 63u) | ((wno >> 6) << 8)) : wno));
-                                        ++nrec;
-                                    }
-                                }
-                            }
-                        }
-                        mark(10);
-                        // ---- records -> element numbers j (bytes 0..15 of the histogram area: low range, 16..31: high range)
-                        int nL = 0, nH = 0;
-                        for (int i = 0; i < nrec; ++i) {
-                            const uint32_t rec = lds_u32(blbase + 4u * (uint32_t)i);
-                            const int wj = (int)(BIG ? ((rec & 63u) | ((rec >> 2) & 0xFC0u)) : (rec & 63u)) * 4;
-                            uint32_t f = rec & 0xC0C0C0C0u;  // bit 7 of a byte: low range, bit 6: high range
-                            while (f) {
-                                const int bit = __ffs((int)f) - 1;
-                                f &= f - 1u;
-                                const bool hi = (bit & 1) == 0;
-                                const int cnt = hi ? nH : nL;
-                                if (cnt < CM) {
-                                    const uint32_t jn = (uint32_t)(wj + (bit >> 3));
-                                    sts_u8(hist_addr(hbase, (uint32_t)(cnt + (hi ? 16 : 0))), jn);  // NBW >= 8
-                                    if (BIG) sts_u8(hist_addr(hbase, (uint32_t)(32 + cnt + (hi ? 16 : 0))), jn >> 8);  // NBW >= 16
-                                }
-                                nH += hi ? 1 : 0;
-                                nL += hi ? 0 : 1;
-                            }
-                        }
-                        rescue = rescue || (smallL && nL != cntL) || (smallH && nH != cntH);  // second part never expected: guard
-                        mark(11);
-                        // ---- re-gather the candidates, four of each range per trip so that the index loads overlap;
-                        //      values land in the bucket-list area (low range: bytes 0..63, high range: 64..127)
-                        {
-                            const int nLc = nL < CM ? nL : CM, nHc = nH < CM ? nH : CM;
-                            const int nmax = nLc > nHc ? nLc : nHc;
-                            for (int i0 = 0; i0 < nmax; i0 += 4) {
-                                uint32_t pl[4], ph[4];
-    #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const bool okl = i0 + u < nLc, okh = i0 + u < nHc;
-                                    uint32_t jl = okl ? lds_u8(hist_addr(hbase, (uint32_t)(i0 + u))) : 0u;
-                                    uint32_t jh = okh ? lds_u8(hist_addr(hbase, 16u + (uint32_t)(i0 + u))) : 0u;
-                                    if (BIG) {
-                                        jl |= okl ? lds_u8(hist_addr(hbase, 32u + (uint32_t)(i0 + u))) << 8 : 0u;
-                                        jh |= okh ? lds_u8(hist_addr(hbase, 48u + (uint32_t)(i0 + u))) << 8 : 0u;
-                                    }
-                                    pl[u] = (uint32_t)__ldg(ip + jl * 32u);
-                                    ph[u] = (uint32_t)__ldg(ip + jh * 32u);
-                                }
-    #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const T vl = src.at(pl[u]), vh = src.at(ph[u]);
-                                    if (i0 + u < nLc) sts_val(blbase + (uint32_t)((i0 + u) * (int)sizeof(T)), vl);
-                                    if (i0 + u < nHc) sts_val(blbase + 64u + (uint32_t)((i0 + u) * (int)sizeof(T)), vh);
-                                }
-                            }
-                        }
-                        mark(12);
-                        // ---- sort the candidates of each range and read off the two ranks
-    #pragma unroll 1
-                        for (int h = 0; h < 2; ++h) {
-                            const int nc = h ? nH : nL;
-                            const bool small = h ? smallH : smallL;
-                            const int ra = h ? P2 - E[2] : P0 - E[0], rb = h ? P3 - E[2] : P1 - E[0];
-                            const uint32_t cb = blbase + (h ? 64u : 0u);
-                            T ya, yb;
-                            if (!small) {
-                                ya = h ? tieH : tieL;
-                                yb = ya;
-                            } else if (nc <= 8 || CM <= 8) {
-                                T c[8];
-                                if (sizeof(T) == 4) {
-                                    const uint4 q0 = lds_v4(cb), q1 = lds_v4(cb + 16u);
-                                    c[0] = (T)__uint_as_float(q0.x); c[1] = (T)__uint_as_float(q0.y);
-                                    c[2] = (T)__uint_as_float(q0.z); c[3] = (T)__uint_as_float(q0.w);
-                                    c[4] = (T)__uint_as_float(q1.x); c[5] = (T)__uint_as_float(q1.y);
-                                    c[6] = (T)__uint_as_float(q1.z); c[7] = (T)__uint_as_float(q1.w);
-                                } else {
-    #pragma unroll
-                                    for (int i = 0; i < 8; ++i) c[i] = lds_val(cb + 8u * (uint32_t)i, T(0));
-                                }
-    #pragma unroll
-                                for (int i = 0; i < 8; ++i) c[i] = (i < nc) ? c[i] : Big<T>::v();
-                                sort_pow2_asc<T, 8>(c);
-                                ya = pick_reg<T, 8>(c, ra);
-                                yb = pick_reg<T, 8>(c, rb);
-                            } else {
-                                T c[16];
-    #pragma unroll
-                                for (int i = 0; i < 16; ++i) c[i] = (i < nc) ? lds_val(cb + (uint32_t)(i * (int)sizeof(T)), T(0)) : Big<T>::v();
-                                sort_pow2_asc<T, 16>(c);
-                                ya = pick_reg<T, 16>(c, ra);
-                                yb = pick_reg<T, 16>(c, rb);
-                            }
-                            if (h) {
-                                y2 = ya;
-                                y3 = yb;
-                            } else {
-                                y0 = ya;
-                                y1 = yb;
                             }
                         }
                     }
