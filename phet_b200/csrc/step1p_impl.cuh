@@ -175,7 +175,7 @@ template <int W, int EB>
 __device__ __forceinline__ void push_entry(uint32_t (&p)[W], uint32_t j) {
 #pragma unroll
     for (int i = W - 1; i >= 1; --i) p[i] = __funnelshift_l(p[i - 1], p[i], EB);
-    p[0] = (p[0] << EB) | j;
+    p[0] = p[0] * (1u << EB) + j;   // (IMAD: the FMA pipe has room, the ALU pipe does not)
 }
 template <int W, int EB>
 __device__ __forceinline__ uint32_t pack_entry(const uint32_t (&p)[W], int k) {  // k: compile-time constant after unrolling
