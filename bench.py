@@ -13,7 +13,9 @@ Random draws (--permutations, default "reference"): the index sets and the 2 G S
 reference would draw from np.random seeded with 12345 (phet.py:401-402, 486-487), replayed natively.
 
   value   inputs resident in HBM when the timed region starts: the raw matrix, the index sets and (reference mode)
-          the permutation tables -- all "host-generated index sets" in north-star terms
+          the permutation tables -- all "host-generated index sets" in north-star terms.  The K fits are issued back to
+          back (phet_finalize_async: every fit is complete on the device, scores in PHET_BUF_SCORES; the last one is
+          copied out before the closing event), timed with CUDA events on the library's stream, max over ranks
   e2e     the user's call: PHet(...).fit_predict(X_host, y) from pinned host memory, np.random seeded just before;
           the draws (host scan of the MT19937 stream, overlapped with the device) are INSIDE the timed region
   e2e_device_perm / value_device_perm: the same with permutation="device" (a keyed bijection on the GPU instead of
