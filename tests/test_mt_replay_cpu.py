@@ -171,3 +171,33 @@ def test_ring_replay_equals_sequential(sizes, rounds, env):
     assert out[0] == "1", out
     if env.get("PHET_REPLAY_GENERATORS") == "0":
         assert out[1] == "0"
+
+
+@pytest.mark.parametrize("procs", ["1", "2", "8"])
+def test_thread_budget_per_local_process(procs):
+    """Several ranks replay one stream side by side on one host: PHET_REPLAY_PROCS (torchrun's LOCAL_WORLD_SIZE) divides the
+    cores between them and phet_mt_par_begin picks generator / worker counts from the share -- down to no ring at all
+    (the scanner generating for itself) on a one-core share.  Whatever it picks, the draws and the final state are those
+    of the one-thread scan."""
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from phet_b200._capi import MtStream\n"
+            "np.random.seed(31337); np.random.randint(0, 2**31 - 1, size=17)\n"
+            "a, b, c = MtStream.from_numpy(), MtStream.from_numpy(), MtStream.from_numpy()\n"
+            "da = a.shuffle_draws([25000, 24000], 40)\n"
+            "db = b.shuffle_draws([25000, 24000], 40, workers=0, chunks=4)\n"
+            "c.shuffle_draws([25000, 24000], 40, store=False, workers=0, chunks=4)\n"
+            "ok = all(np.array_equal(x, y) for x, y in zip(da, db))\n"
+            "for m in (b, c):\n"
+            "    ok = ok and np.array_equal(a.state()[0], m.state()[0]) and a.state()[1] == m.state()[1]\n"
+            "print(int(ok), *b.par_threads)\n" % ROOT)
+    e = dict(os.environ)
+    e["PHET_REPLAY_PROCS"] = procs
+    e.pop("PHET_REPLAY_GENERATORS", None)
+    e.pop("PHET_REPLAY_WORKERS", None)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, check=True, timeout=600).stdout.split()
+    assert out[0] == "1", out
+    gens, scanners, workers = (int(v) for v in out[1:4])
+    cores = os.cpu_count() or 1
+    share = max(cores // int(procs), 1)
+    assert scanners == 1 and workers >= 1
+    assert gens + scanners + workers <= max(share, 2) or gens == 0, (gens, workers, share)
