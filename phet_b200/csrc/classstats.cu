@@ -25,6 +25,8 @@
 // by radix select, one warp per track.  The bucket map is monotone in the value, so buckets partition the order
 // statistics exactly; a list that overflows (a tie group of thousands of equal values, a heavy-tailed gene whose
 // sample range is huge) sends the gene to the general path.
+#include <type_traits>
+
 #include "common.cuh"
 #include "warp_prims.cuh"
 
@@ -322,36 +324,60 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 pf[t] = bsel[t];
                 nm[t] = ~K(0);
             }
-            typename CsVec<T>::type nxt = {};   // the next trip's cells are in flight while this trip's are compacted
-            if (tid < nvec16) nxt = __ldg(rowv + tid);
-            for (int64_t bv = 0; bv < nvec16; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
-                const int64_t iv = bv + tid;
-                T e[VW];
-                CsVec<T>::get(nxt, e);
-                if (iv + kCsThreads < nvec16) nxt = __ldg(rowv + iv + kCsThreads);
+            // Trips whose cells all belong to one class (all but the one or two around n0) only look at that class's two
+            // tracks and the two pooled ones, and a trip in which no lane matches any of its four buckets (most trips: a
+            // bucket holds ~0.4 % of the cells) costs one ballot instead of four.  CL = 0 / 1: the class; 2: mixed trip.
+            auto trips = [&](auto cl_tag, int64_t bv0, int64_t bv1) {
+                constexpr int CL = decltype(cl_tag)::value;
+                typename CsVec<T>::type nxt = {};   // the next trip's cells are in flight while this trip's are compacted
+                if (bv0 < bv1 && bv0 + tid < nvec16) nxt = __ldg(rowv + bv0 + tid);
+                for (int64_t bv = bv0; bv < bv1; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
+                    const int64_t iv = bv + tid;
+                    T e[VW];
+                    CsVec<T>::get(nxt, e);
+                    if (bv + kCsThreads < bv1 && iv + kCsThreads < nvec16) nxt = __ldg(rowv + iv + kCsThreads);
 #pragma unroll
-                for (int k = 0; k < VW; ++k) {
-                    const int64_t i = iv * VW + k;
-                    const bool valid = iv < nvec16 && i < n;
-                    const T v = e[k];
-                    const K key = CsKey<T>::of(v);
-                    const int kp = bucket_of(v);
-                    const int c = (i < n0) ? 0 : 1;
+                    for (int k = 0; k < VW; ++k) {
+                        const int64_t i = iv * VW + k;
+                        const bool valid = iv < nvec16 && i < n;
+                        const T v = e[k];
+                        const K key = CsKey<T>::of(v);
+                        const int kp = bucket_of(v);
+                        const int c = (CL == 2) ? ((i < n0) ? 0 : 1) : CL;
+                        bool any = false;
 #pragma unroll
-                    for (int t = 0; t < kCsTracks; ++t) {
-                        const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
-                        const bool match = member && kp == pf[t];
-                        if (member && kp > pf[t] && key < nm[t]) nm[t] = key;
-                        const unsigned mask = __ballot_sync(kFull, match);
-                        if (mask) {
-                            int base = 0;
-                            if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(&llen[t], __popc(mask));
-                            base = __shfl_sync(kFull, base, __ffs((int)mask) - 1);
-                            const int pos = base + __popc(mask & ((1u << lane) - 1u));
-                            if (match && pos < LCAP) lists[t * LCAP + pos] = key;
+                        for (int t = 0; t < kCsTracks; ++t) {
+                            if (CL != 2 && (t >> 1) != 2 && (t >> 1) != CL) continue;   // the other class's tracks
+                            const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
+                            any = any || (member && kp == pf[t]);
+                            if (member && kp > pf[t] && key < nm[t]) nm[t] = key;
+                        }
+                        if (__ballot_sync(kFull, any) == 0u) continue;
+#pragma unroll
+                        for (int t = 0; t < kCsTracks; ++t) {
+                            if (CL != 2 && (t >> 1) != 2 && (t >> 1) != CL) continue;
+                            const bool member = valid && ((t >> 1) == 2 || (t >> 1) == c);
+                            const bool match = member && kp == pf[t];
+                            const unsigned mask = __ballot_sync(kFull, match);
+                            if (mask) {
+                                int base = 0;
+                                if (lane == (__ffs((int)mask) - 1)) base = atomicAdd(&llen[t], __popc(mask));
+                                base = __shfl_sync(kFull, base, __ffs((int)mask) - 1);
+                                const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                                if (match && pos < LCAP) lists[t * LCAP + pos] = key;
+                            }
                         }
                     }
                 }
+            };
+            {
+                const int64_t per_trip = (int64_t)kCsThreads;                      // vectors per trip
+                const int64_t t0 = (n0 / VW) / per_trip * per_trip;               // trips [0, t0): class 0 only
+                int64_t t1 = ((n0 + VW - 1) / VW + per_trip - 1) / per_trip * per_trip;   // trips from t1 on: class 1 only
+                if (t1 > nvec16) t1 = (nvec16 + per_trip - 1) / per_trip * per_trip;
+                trips(std::integral_constant<int, 0>{}, 0, t0);
+                trips(std::integral_constant<int, 2>{}, t0, t1);
+                trips(std::integral_constant<int, 1>{}, t1, nvec16);
             }
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) {
