@@ -251,16 +251,18 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
         constexpr int VW = CsVec<T>::width;
         const typename CsVec<T>::type *rowv = reinterpret_cast<const typename CsVec<T>::type *>(row);   // rows are 16-byte aligned, n_pad covers the tail
         const int64_t nvec16 = (n + VW - 1) / VW;
+        // (32-bit cell numbers in the two passes over the row: phet_class_stats admits at most 2^25 - 1 cells)
+        const int n_i = (int)n, n0_i = (int)n0, nvec_i = (int)nvec16;
 #pragma unroll 4
-        for (int64_t iv = tid; iv < nvec16; iv += kCsThreads) {
+        for (int iv = tid; iv < nvec_i; iv += kCsThreads) {
             T e[VW];
             CsVec<T>::get(__ldg(rowv + iv), e);
 #pragma unroll
             for (int k = 0; k < VW; ++k) {
-                const int64_t i = iv * VW + k;
-                if (i < n) {
+                const int i = iv * VW + k;
+                if (i < n_i) {
                     const T v = e[k];
-                    const int c = (i < n0) ? 0 : 1;
+                    const int c = (i < n0_i) ? 0 : 1;
                     const double d = (double)v - (c ? K1 : K0);
                     if (c) { s1 += d; d1 = fma(d, d, d1); } else { s0 += d; d0 = fma(d, d, d0); }
                     atomicAdd(&hist[c][bucket_of(v)], 1u);
@@ -327,23 +329,23 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
             // Trips whose cells all belong to one class (all but the one or two around n0) only look at that class's two
             // tracks and the two pooled ones, and a trip in which no lane matches any of its four buckets (most trips: a
             // bucket holds ~0.4 % of the cells) costs one ballot instead of four.  CL = 0 / 1: the class; 2: mixed trip.
-            auto trips = [&](auto cl_tag, int64_t bv0, int64_t bv1) {
+            auto trips = [&](auto cl_tag, int bv0, int bv1) {
                 constexpr int CL = decltype(cl_tag)::value;
                 typename CsVec<T>::type nxt = {};   // the next trip's cells are in flight while this trip's are compacted
-                if (bv0 < bv1 && bv0 + tid < nvec16) nxt = __ldg(rowv + bv0 + tid);
-                for (int64_t bv = bv0; bv < bv1; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
-                    const int64_t iv = bv + tid;
+                if (bv0 < bv1 && bv0 + tid < nvec_i) nxt = __ldg(rowv + bv0 + tid);
+                for (int bv = bv0; bv < bv1; bv += kCsThreads) {   // warp-uniform trip count (ballots inside)
+                    const int iv = bv + tid;
                     T e[VW];
                     CsVec<T>::get(nxt, e);
-                    if (bv + kCsThreads < bv1 && iv + kCsThreads < nvec16) nxt = __ldg(rowv + iv + kCsThreads);
+                    if (bv + kCsThreads < bv1 && iv + kCsThreads < nvec_i) nxt = __ldg(rowv + iv + kCsThreads);
 #pragma unroll
                     for (int k = 0; k < VW; ++k) {
-                        const int64_t i = iv * VW + k;
-                        const bool valid = iv < nvec16 && i < n;
+                        const int i = iv * VW + k;
+                        const bool valid = iv < nvec_i && i < n_i;
                         const T v = e[k];
                         const K key = CsKey<T>::of(v);
                         const int kp = bucket_of(v);
-                        const int c = (CL == 2) ? ((i < n0) ? 0 : 1) : CL;
+                        const int c = (CL == 2) ? ((i < n0_i) ? 0 : 1) : CL;
                         bool any = false;
 #pragma unroll
                         for (int t = 0; t < kCsTracks; ++t) {
@@ -371,13 +373,13 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 }
             };
             {
-                const int64_t per_trip = (int64_t)kCsThreads;                      // vectors per trip
-                const int64_t t0 = (n0 / VW) / per_trip * per_trip;               // trips [0, t0): class 0 only
-                int64_t t1 = ((n0 + VW - 1) / VW + per_trip - 1) / per_trip * per_trip;   // trips from t1 on: class 1 only
-                if (t1 > nvec16) t1 = (nvec16 + per_trip - 1) / per_trip * per_trip;
+                const int per_trip = kCsThreads;                                   // vectors per trip
+                const int t0 = (n0_i / VW) / per_trip * per_trip;                  // trips [0, t0): class 0 only
+                int t1 = ((n0_i + VW - 1) / VW + per_trip - 1) / per_trip * per_trip;   // trips from t1 on: class 1 only
+                if (t1 > nvec_i) t1 = (nvec_i + per_trip - 1) / per_trip * per_trip;
                 trips(std::integral_constant<int, 0>{}, 0, t0);
                 trips(std::integral_constant<int, 2>{}, t0, t1);
-                trips(std::integral_constant<int, 1>{}, t1, nvec16);
+                trips(std::integral_constant<int, 1>{}, t1, nvec_i);
             }
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) {
