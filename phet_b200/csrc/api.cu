@@ -474,6 +474,7 @@ int phet_ctx_destroy(phet_ctx *c) {
     c->anova_idx.release();
     c->anova_idxT.release();
     c->anova_idxU.release();
+    c->cs_ovf.release();
     c->rank_keys.release();
     c->rank_order.release();
     c->rank_sorted.release();

@@ -93,6 +93,10 @@ struct ClassStatsArgs {
     phet_quantile_pos q[3];   // positions for n0, n1 and n0 + n1 elements
     double *out;              // [7][G]: iqr0, iqr1, iqr_all, mean0, mean1, ss0, ss1
     int64_t G;
+    // two launches: the FAST instantiation (bucket selection only: small enough for two CTAs per SM) appends the genes
+    // whose candidate lists overflow to ovf_list; the general instantiation then takes exactly those (gene_list)
+    int *ovf_count, *ovf_list;
+    const int *gene_count, *gene_list;
 };
 
 // fixed-order block sum of one double per thread; result broadcast to all threads
@@ -106,17 +110,18 @@ __device__ __forceinline__ double cs_block_sum(double v, double *red, int tid) {
     return t;
 }
 
-template <typename T> struct CsList { static constexpr int cap = 4096; };   // keys per track kept in shared memory
-template <> struct CsList<double> { static constexpr int cap = 2048; };
+template <typename T, bool FAST> struct CsList { static constexpr int cap = FAST ? 3072 : 4096; };   // keys per track kept in shared memory
+template <bool FAST> struct CsList<double, FAST> { static constexpr int cap = FAST ? 1536 : 2048; };
 constexpr int kCsBuckets = 256;    // value buckets of the first pass (a linear map of the range of a 2 x 512 cell sample)
 
-template <typename T>
-__global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsArgs a) {
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(kCsThreads, FAST ? 2 : 1) k_class_stats(const ClassStatsArgs a) {
     typedef typename CsKey<T>::type K;
     constexpr int NPASS = CsKey<T>::bits / 4;
-    constexpr int LCAP = CsList<T>::cap;
-    extern __shared__ __align__(16) uint32_t cnt[];              // [warp][word][lane], two 16-bit counters per word (96 KB)
-    K *lists = reinterpret_cast<K *>(cnt + kCsTracks * 8 * kCsThreads);   // [track][LCAP] candidate keys (96 KB)
+    constexpr int LCAP = CsList<T, FAST>::cap;
+    constexpr int CW = FAST ? 8 : kCsTracks * 8;                 // private counter words per thread (FAST: the list select only)
+    extern __shared__ __align__(16) uint32_t cnt[];              // [warp][word][lane], two 16-bit counters per word (96 KB; FAST: 16 KB)
+    K *lists = reinterpret_cast<K *>(cnt + CW * kCsThreads);   // [track][LCAP] candidate keys
     __shared__ uint32_t wpart[kCsThreads / 32][kCsTracks * 16]; // per-warp digit counts
     __shared__ double red[kCsThreads / 32];
     __shared__ K prefix[kCsTracks];
@@ -129,14 +134,16 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
     __shared__ int bsel[kCsTracks];                 // bucket (index into hist) that holds the track's rank
     __shared__ T bmap[2];                           // bucket = floor((v - bmap[0]) * bmap[1]), in the storage type
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *mine = cnt + (size_t)warp * (kCsTracks * 8 * 32) + lane;   // word w of this thread at mine[32 * w]
+    uint32_t *mine = cnt + (size_t)warp * (CW * 32) + lane;   // word w of this thread at mine[32 * w]
     const int64_t n0 = a.n0, n = a.n0 + a.n1;
     const int64_t nvec[3] = {a.n0, a.n1, n};
 
-    for (int w = 0; w < kCsTracks * 8; ++w) mine[32 * w] = 0u;
+    for (int w = 0; w < CW; ++w) mine[32 * w] = 0u;
     for (int i = tid; i < 2 * (kCsBuckets + 2); i += kCsThreads) (&hist[0][0])[i] = 0u;
 
-    for (int64_t g = a.g_begin + blockIdx.x; g < a.g_end; g += gridDim.x) {
+    const int64_t n_genes = a.gene_list ? (int64_t)*a.gene_count : a.g_end - a.g_begin;
+    for (int64_t gi = blockIdx.x; gi < n_genes; gi += gridDim.x) {
+        const int64_t g = a.gene_list ? (int64_t)a.gene_list[gi] : a.g_begin + gi;
         const T *row = static_cast<const T *>(a.xg) + (size_t)(g - a.xg_g0) * (size_t)a.n_pad;
         if (tid < kCsTracks) {
             prefix[tid] = 0;
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
 
         // CTA totals of the private counters, then one thread per track fixes the next digit
         auto pick_digit = [&](int shift) {
+            if (FAST) return;
             // (a thread sees at most n / 512 + 1 elements: no 16-bit overflow for n < 2^25)
             for (int w = 0; w < kCsTracks * 8; ++w) {
                 const uint32_t x = mine[32 * w];
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
             return (int)tb + 1;
         };
         auto full_pass = [&](int pass) {
+            if (FAST) return;
             const int shift = CsKey<T>::bits - 4 * (pass + 1);
             K pf[kCsTracks];
 #pragma unroll
@@ -464,6 +473,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 }
                 if (lane == 0) prefix[t] = pk;
             }
+        } else if (FAST) {
+            // ---- this instantiation has no general path: the gene goes to the second launch
+            if (tid == 0) a.ovf_list[atomicAdd(a.ovf_count, 1)] = (int)g;
+            __syncthreads();
+            continue;   // (CTA-uniform)
         } else {
             // ---- a tie group (or a very dense bucket) larger than the list: exact radix select over the whole row,
             //      4 bits per pass, from the original ranks
@@ -473,7 +487,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
                 rank[tid] = (tid & 1) ? q.j_hi : q.j_lo;
             }
             __syncthreads();
-            for (int pass = 0; pass < NPASS; ++pass) full_pass(pass);
+            if (!FAST)   // (the full passes use 48 counter words per thread; the FAST instantiation has 8)
+                for (int pass = 0; pass < NPASS; ++pass) full_pass(pass);
             K pf[kCsTracks];
 #pragma unroll
             for (int t = 0; t < kCsTracks; ++t) pf[t] = prefix[t];
@@ -535,6 +550,38 @@ __global__ void __launch_bounds__(kCsThreads, 1) k_class_stats(const ClassStatsA
     }
 }
 
+template <typename T>
+static int launch_class_stats_T(phet_ctx *c, ClassStatsArgs a, int64_t ng) {
+    typedef typename CsKey<T>::type K;
+    // launch 1: bucket selection only, two CTAs per SM; genes whose lists overflow are listed for launch 2
+    if (int e = c->cs_ovf.alloc((size_t)c->G + 1)) return e;
+    PHET_CUDA(cudaMemsetAsync(c->cs_ovf.p, 0, sizeof(int), c->stream));
+    a.ovf_count = c->cs_ovf.p;
+    a.ovf_list = c->cs_ovf.p + 1;
+    a.gene_count = nullptr;
+    a.gene_list = nullptr;
+    const int smem_fast = 8 * kCsThreads * (int)sizeof(uint32_t) + kCsTracks * CsList<T, true>::cap * (int)sizeof(K);
+    PHET_CUDA(cudaFuncSetAttribute(k_class_stats<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fast));
+    int per_sm = 0;
+    PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_class_stats<T, true>, kCsThreads, smem_fast));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)per_sm * c->num_sms;
+    if (grid > ng) grid = ng;
+    k_class_stats<T, true><<<(unsigned)grid, kCsThreads, smem_fast, c->stream>>>(a);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    // launch 2: the general instantiation on the listed genes (it reads their number on the device: no host round trip)
+    a.gene_count = c->cs_ovf.p;
+    a.gene_list = c->cs_ovf.p + 1;
+    const int smem = kCsTracks * 8 * kCsThreads * (int)sizeof(uint32_t) + kCsTracks * CsList<T, false>::cap * (int)sizeof(K);
+    PHET_CUDA(cudaFuncSetAttribute(k_class_stats<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    grid = c->num_sms < ng ? c->num_sms : ng;
+    k_class_stats<T, false><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
+    c->launches++;
+    PHET_CUDA(cudaGetLastError());
+    return PHET_OK;
+}
+
 int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_quantile_pos *q3, double *out_dev) {
     ClassStatsArgs a;
     a.xg = c->xg.p;
@@ -549,19 +596,7 @@ int launch_class_stats(phet_ctx *c, int64_t g_begin, int64_t g_end, const phet_q
     a.G = c->G;
     const int64_t ng = g_end - g_begin;
     if (ng < 1) return PHET_OK;
-    int64_t grid = c->num_sms;
-    if (grid > ng) grid = ng;
-    const int smem = kCsTracks * 8 * kCsThreads * (int)sizeof(uint32_t) + kCsTracks * 4096 * (int)sizeof(uint32_t);  // counters + lists
-    if (c->storage == PHET_F32) {
-        PHET_CUDA(cudaFuncSetAttribute(k_class_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_class_stats<float><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
-    } else {
-        PHET_CUDA(cudaFuncSetAttribute(k_class_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k_class_stats<double><<<(unsigned)grid, kCsThreads, smem, c->stream>>>(a);
-    }
-    c->launches++;
-    PHET_CUDA(cudaGetLastError());
-    return PHET_OK;
+    return c->storage == PHET_F32 ? launch_class_stats_T<float>(c, a, ng) : launch_class_stats_T<double>(c, a, ng);
 }
 
 }  // namespace phet

@@ -162,6 +162,7 @@ struct phet_ctx {
     // multi-class Step 1 (anova.cu) and the Step-3 slicing range of a multi-class fit
     phet::DevBuf<int32_t> anova_idx;
     phet::DevBuf<uint32_t> anova_idxT, anova_idxU;
+    phet::DevBuf<int> cs_ovf;            // [1 + G]: count | genes the bucket-selection launch of phet_class_stats hands to the general one
     int64_t step3_min_size = 0;          // phet_set_option(PHET_OPT_STEP3_MIN_SIZE): slices cover [0, this) instead of [0, min(n0, n1))
     // ranking (rank.cu)
     phet::DevBuf<unsigned long long> rank_keys;

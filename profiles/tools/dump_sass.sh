@@ -13,7 +13,7 @@ for f in \
   _ZN4phet8k_step3sIfLi10ELb1ELb1EEEvNS_16Step3ScatterArgsE:k_step3s_f32_r10_ovf_device \
   _ZN4phet8k_step3sIfLi5ELb0ELb0EEEvNS_16Step3ScatterArgsE:k_step3s_f32_r5_table \
   _ZN4phet21k_normalize_transposeIffEEvPKT_llllPKiPKdS7_iPT0_:k_normalize_transpose_f32 \
-  _ZN4phet13k_class_statsIfEEvNS_14ClassStatsArgsE:k_class_stats_f32 \
+  _ZN4phet13k_class_statsIfLb1EEEvNS_14ClassStatsArgsE:k_class_stats_f32_fast \
   _ZN4phet14k_kruskal_sortIfLi6ELb1EEEvNS_9AnovaArgsEi:k_kruskal_sort_f32_e6_staged \
   _ZN4phet15k_fy_apply_smemItEEvNS_6FyArgsE:k_fy_apply_smem_u16 \
   _ZN4phet12k_build_idxTEPKilllllPt:k_build_idxT ; do
