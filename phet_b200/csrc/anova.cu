@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kKwThreads, 1) k_kruskal(const AnovaArgs a, in
 // ranks, the per-group rank sums and the tie sum are the same exact integers (phet.py:372-377 -> scipy.stats.kruskal).
 // E = registers per lane (32 E >= K m).
 template <typename T, int E, bool STAGED>
-__global__ void __launch_bounds__(kKwThreads, 1) k_kruskal_sort(const AnovaArgs a, int vec_bytes) {
+__global__ void __launch_bounds__(kKwThreads, (sizeof(T) == 4 && E <= 8) ? 2 : 1) k_kruskal_sort(const AnovaArgs a, int vec_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = kKwThreads / 32;
     constexpr int NP = 32 * E;
@@ -401,6 +401,10 @@ static int launch_kruskal_sort_E(phet_ctx *c, const AnovaArgs &a, int64_t grid) 
     const size_t vec_bytes = ((size_t)a.N * sizeof(T) + 15) & ~(size_t)15;
     if (vec_bytes + strips <= (size_t)kMaxSmemOptin - 1024) {
         PHET_CUDA(cudaFuncSetAttribute(k_kruskal_sort<T, E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(vec_bytes + strips)));
+        int per_sm = 1;   // narrow float instantiations are compiled for two CTAs per SM (64 registers)
+        PHET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kruskal_sort<T, E, true>, kKwThreads, vec_bytes + strips));
+        const int64_t ng = a.g_end - a.g_begin;
+        if (per_sm > 1) grid = (int64_t)per_sm * c->num_sms < ng ? (int64_t)per_sm * c->num_sms : ng;
         k_kruskal_sort<T, E, true><<<(unsigned)grid, kKwThreads, vec_bytes + strips, c->stream>>>(a, (int)vec_bytes);
     } else {   // a cell vector too long to stage: gathers go to L2
         PHET_CUDA(cudaFuncSetAttribute(k_kruskal_sort<T, E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strips));
